@@ -1,0 +1,134 @@
+/* retinapost.h — C ABI of libretinapost.so: RetinaNet detection post-processing on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the decode / top-k / NMS path of srihari-humbarwadi/retinanet-tensorflow2.x.
+ * The reference has no native layer (it is Python on TensorFlow ops); every entry point below names the reference
+ * interface it replaces (paths relative to the reference tree).  The Python host layers in
+ * retinanet-tensorflow2.x_b200/retinanet/ bind these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every d_* pointer is DEVICE memory owned by the caller, h_* is HOST memory;
+ *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream);
+ *     no hidden synchronisation, no allocation after rpp_create (rpp_detect_host owns staging set up lazily);
+ *   - the handle is immutable after rpp_create: concurrent calls are safe with distinct workspaces;
+ *   - return 0 on success, a negative RPP_E* code otherwise; rpp_last_error() gives the message (thread-local);
+ *     no exception crosses the ABI.  The Python shim maps RPP_EMODE -> AssertionError, others -> ValueError /
+ *     RuntimeError (the reference raises AssertionError for a bad mode, postprocessing_ops.py:194-197).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns RPP_ECUDA.
+ */
+#ifndef RETINAPOST_H_
+#define RETINAPOST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPP_OK 0
+#define RPP_EINVAL (-1)    /* bad argument / shape */
+#define RPP_EMODE (-2)     /* unsupported NMS mode (reference: AssertionError) */
+#define RPP_ECOMBO (-3)    /* Global* mode fed per-class (4-D) boxes: rank error in the reference */
+#define RPP_EWORKSPACE (-4)/* workspace too small */
+#define RPP_ECUDA (-5)     /* CUDA runtime error / no device */
+
+/* GenerateDetections._SUPPORTED_NMS_MODES (model/layers/postprocessing_ops.py:177-183), same order. */
+enum rpp_mode {
+  RPP_COMBINED_NMS = 0,
+  RPP_GLOBAL_SOFT_NMS = 1,
+  RPP_GLOBAL_HARD_NMS = 2,
+  RPP_PER_CLASS_SOFT_NMS = 3,
+  RPP_PER_CLASS_HARD_NMS = 4
+};
+
+/* Everything the four reference layers read from `params` (configs/...json: input, architecture.feature_fusion,
+ * architecture.head.num_classes, anchor_params, encoder_params, inference) — model/builder.py:153-190. */
+typedef struct rpp_config {
+  int H, W;                       /* input.input_shape */
+  int min_level, max_level;       /* architecture.feature_fusion.{min_level,max_level} */
+  int num_classes;                /* architecture.head.num_classes */
+  int n_areas;  const double* areas;          /* anchor_params.areas (one per level) */
+  int n_ratios; const double* aspect_ratios;  /* anchor_params.aspect_ratios */
+  int n_scales; const double* scales;         /* anchor_params.scales */
+  float box_variance[4];          /* encoder_params.box_variance */
+  int scale_box_targets;          /* encoder_params.scale_box_targets */
+  int mode;                       /* inference.mode as enum rpp_mode */
+  float iou_threshold;            /* inference.iou_threshold */
+  float score_threshold;          /* inference.score_threshold */
+  float soft_nms_sigma;           /* inference.soft_nms_sigma (config value; the kernel halves it, :255,:450) */
+  int pre_nms_top_k;              /* inference.pre_nms_top_k (<= 0: FilterTopKDetections skipped, builder.py:167) */
+  int filter_per_class;           /* inference.filter_per_class */
+  int max_detections;             /* inference.max_detections */
+  int soft_ignores_iou_threshold; /* 1 = TF >= 2.3 NonMaxSuppressionV5 (default); 0 = older kernel form */
+  int reserved[7];                /* must be zero */
+} rpp_config;
+
+/* Lifetime.  rpp_create validates the config (reference: GenerateDetections.__init__ :185-217 and
+ * TransformBoxesAndScores.__init__ :61-85), builds the anchor table on the device (AnchorBoxGenerator,
+ * dataloader/anchor_generator.py:24-104) and the exact score-threshold pre-image. */
+int rpp_create(const rpp_config* cfg, void** handle);
+int rpp_destroy(void* handle);
+const char* rpp_last_error(void);
+
+/* AnchorBoxGenerator.boxes / .anchor_boundaries (anchor_generator.py:106-112). */
+long rpp_num_anchors(void* handle);
+int rpp_num_levels(void* handle);
+int rpp_anchor_boundaries(void* handle, long* h_out /* num_levels + 1 */);
+int rpp_anchors(void* handle, float* d_out_N4 /* [N,4] cx,cy,w,h */, void* stream);
+
+/* Bytes of device scratch the calls below need for a batch of B images (n: rows per image for rpp_topk /
+ * rpp_nms; pass 0 for rpp_detect = number of anchors). */
+size_t rpp_workspace_bytes(void* handle, int B, long n);
+
+/* TransformBoxesAndScores.call (postprocessing_ops.py:107-117): scores = sigmoid(logits) [B,N,C],
+ * boxes = decode(deltas, anchors) / [H,W,H,W] [B,N,4].  Either output may be NULL. */
+int rpp_decode(void* handle, const float* d_logits_BNC, const float* d_deltas_BN4, int B,
+               float* d_scores_BNC, float* d_boxes_BN4, void* stream);
+
+/* FilterTopKDetections.call (postprocessing_ops.py:163-173) with the handle's pre_nms_top_k / filter_per_class:
+ *   per class : scores_out [B,k',C], boxes_out [B,k',C,4], k' = min(k, n)       (:128-147)
+ *   global    : scores_out [B,k',C], boxes_out [B,k',4],   k' = min(k, n*C)     (:149-161)
+ * Rows are in tf.nn.top_k sorted=True order (value desc, index asc).  d_index_out (optional): the selected
+ * anchor index [B,C,k'] (per class) or flat index [B,k'] (global). */
+int rpp_topk(void* handle, const float* d_scores_BnC, const float* d_boxes_Bn4, int B, long n,
+             float* d_scores_out, float* d_boxes_out, int* d_index_out,
+             void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* GenerateDetections.call (postprocessing_ops.py:537-561), non-TPU branches, with the handle's mode/thresholds.
+ *   scores [B,n,C]; boxes [B,n,q,4] with q = 1 (3-D boxes) or q = C (after the per-class filter).
+ *   outputs: boxes [B,M,4] f32, scores [B,M] f32, classes [B,M] (f32 Combined / int64 Global* / int32 PerClass*),
+ *   valid [B] i32 — dtypes and padding per mode as in the reference. */
+int rpp_nms(void* handle, const float* d_scores_BnC, const float* d_boxes_Bnq4, int B, long n, int q,
+            float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
+            void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* The fused path = ModelBuilder.add_post_processing_stage (model/builder.py:153-190) after FuseDetections:
+ * TransformBoxesAndScores -> FilterTopKDetections -> GenerateDetections, without materialising the
+ * intermediates.  Argument order mirrors the reference's own fused-op precedent, the EfficientNMS_TRT node of
+ * onnx_utils.py:13-85: (raw_boxes [B,N,4], class_logits [B,N,C]; anchors live in the handle). */
+int rpp_detect(void* handle, const float* d_deltas_BN4, const float* d_logits_BNC, int B,
+               float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
+               void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Same, from HOST buffers (the serving call of export.py:233-253 / evaluate_saved_model.py: tensors arrive from
+ * the host and detections are consumed on the host).  Copies H2D in image chunks overlapped with the kernels,
+ * then D2H of the four outputs; synchronises before returning.  Pinned host memory is recommended.
+ * device: CUDA ordinal.  Staging buffers are allocated on first use and kept in the handle. */
+int rpp_detect_host(void* handle, int device, const float* h_deltas_BN4, const float* h_logits_BNC, int B,
+                    float* h_boxes_BM4, float* h_scores_BM, void* h_classes_BM, int* h_valid_B);
+
+/* Number of kernels the last rpp_detect / rpp_nms / rpp_topk / rpp_decode call on this thread launched. */
+int rpp_last_launch_count(void);
+
+/* Size in bytes of one element of the classes output for the handle's mode (4, 8 or 4). */
+int rpp_classes_itemsize(void* handle);
+
+/* Debug/testing knobs (not part of the reference surface): force the exact slow path of the candidate
+ * selection (1), or restore the default sampled pre-threshold (0). */
+int rpp_debug_force_exact_scan(void* handle, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RETINAPOST_H_ */

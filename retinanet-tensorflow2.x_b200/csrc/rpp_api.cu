@@ -1,0 +1,423 @@
+// rpp_api.cu — C ABI of libretinapost.so (include/retinapost.h): handle, workspace layout and kernel launches.
+// Host logic only; every result is computed by the kernels in rpp_kernels.cuh.  There is no CPU compute path.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/retinapost.h"
+#include "rpp_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e__ = (expr);                                                                      \
+    if (e__ != cudaSuccess) return fail(RPP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__));      \
+  } while (0)
+
+#define LAUNCHED()                                                                                 \
+  do {                                                                                             \
+    ++g_launches;                                                                                  \
+    cudaError_t e__ = cudaPeekAtLastError();                                                       \
+    if (e__ != cudaSuccess) return fail(RPP_ECUDA, "kernel launch (%s:%d): %s", __FILE__, __LINE__, \
+                                        cudaGetErrorString(e__));                                  \
+  } while (0)
+
+struct SamplePlan {
+  bool on;
+  int stride, G, rows_per_group, rank;
+  int CAP;
+};
+
+struct Handle {
+  rpp_config cfg;
+  std::vector<double> areas, ratios, scales;
+  long N;
+  int levels;
+  AnchorParams ap;
+  float4* d_anchors;
+  float T_logit;   // smallest logit whose sigmoid exceeds score_threshold
+  int device;
+  int sm_count;
+  int force_scan;
+  DecodeParams dp;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// target ~1536 candidates per problem, capacity 4096; small columns are collected whole.
+SamplePlan make_plan(long n, int target) {
+  SamplePlan s{};
+  s.on = false;
+  s.CAP = (int)n;
+  if (n < 16384 || n <= 8L * target) return s;
+  const int G = 96;
+  int S = (int)std::floor(target / (0.916 * G));
+  if (S < 1) S = 1;
+  const long g = n / ((long)S * G);
+  if (g < 8) return s;
+  const double q = std::pow(1.0 - (double)target / (double)n, (double)g);
+  int rank = (int)std::floor(q * G);
+  if (rank < 2) rank = 2;
+  if (rank > G - 3) rank = G - 3;
+  s.on = true;
+  s.stride = S;
+  s.G = G;
+  s.rows_per_group = (int)g;
+  s.rank = rank;
+  s.CAP = 4096;
+  return s;
+}
+
+struct Workspace {
+  float* T;
+  u32* cand_count;
+  int* sel_cnt;
+  u64* sel_key;
+  float4* sel_box;
+  uint2* cand;
+  size_t bytes;
+};
+
+Workspace layout_cols(void* base, size_t P, int M, int CAP) {
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return base ? (char*)base + o : (char*)nullptr;
+  };
+  w.T = (float*)take(P * sizeof(float));
+  w.cand_count = (u32*)take(P * sizeof(u32));
+  w.sel_cnt = (int*)take(P * sizeof(int));
+  w.sel_key = (u64*)take(P * (size_t)M * sizeof(u64));
+  w.sel_box = (float4*)take(P * (size_t)M * sizeof(float4));
+  w.cand = (uint2*)take(P * (size_t)CAP * sizeof(uint2));
+  w.bytes = off;
+  return w;
+}
+
+bool is_per_class_mode(int mode) {
+  return mode == RPP_COMBINED_NMS || mode == RPP_PER_CLASS_HARD_NMS || mode == RPP_PER_CLASS_SOFT_NMS;
+}
+
+int launch_collect(Handle* h, const float* x, const Workspace& w, const SamplePlan& plan, int B, long n, int C,
+                   float T_min, cudaStream_t st) {
+  const size_t P = (size_t)B * C;
+  CUDA_OK(cudaMemsetAsync(w.cand_count, 0, P * sizeof(u32), st));
+  if (plan.on && !h->force_scan) {
+    int threads = (1024 / C) * C;
+    if (threads > 960) threads = (960 / C) * C;
+    if (threads < C) return fail(RPP_EINVAL, "num_classes %d too large for the sampling kernel", C);
+    const size_t smem = (size_t)plan.G * C * sizeof(u32);
+    sample_threshold_kernel<<<B, threads, smem, st>>>(x, n, C, plan.stride, plan.G, plan.rows_per_group, plan.rank,
+                                                      T_min, w.T);
+    LAUNCHED();
+  } else {
+    fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.T, P, T_min);
+    LAUNCHED();
+  }
+  if (h->force_scan) return RPP_OK;
+  if (C % 4 == 0 && ((uintptr_t)x % 16) == 0 && C / 4 <= 512) {
+    const int C4 = C / 4;
+    int lanes = 512 / C4;
+    if (lanes < 1) lanes = 1;
+    const int threads = (int)align_up((size_t)lanes * C4, 32);
+    const int UNROLL = 4;
+    const int rows_per_tile = lanes * UNROLL * 2;
+    const int tiles_per_image = (int)((n + rows_per_tile - 1) / rows_per_tile);
+    const long n_tiles = (long)B * tiles_per_image;
+    long grid = (long)h->sm_count * 4;
+    if (grid > n_tiles) grid = n_tiles;
+    collect_cols4_kernel<UNROLL><<<(unsigned)grid, threads, 0, st>>>((const float4*)x, w.T, w.cand_count, w.cand,
+                                                                     plan.CAP, B, n, C4, lanes, rows_per_tile,
+                                                                     tiles_per_image);
+    LAUNCHED();
+  } else {
+    const size_t tot = (size_t)B * n * C;
+    size_t grid = (tot + 255) / 256;
+    if (grid > (size_t)h->sm_count * 32) grid = (size_t)h->sm_count * 32;
+    collect_cols1_kernel<<<(unsigned)grid, 256, 0, st>>>(x, w.T, w.cand_count, w.cand, plan.CAP, B, n, C);
+    LAUNCHED();
+  }
+  return RPP_OK;
+}
+
+// per-(image, class) NMS problems over the columns of x [B,n,C] + per-image merge
+int run_per_class(Handle* h, const float* x, int is_logit, const float4* deltas, const float4* boxes, int q, int B,
+                  long n, long k_lim, int row0_mode, float4* out_boxes, float* out_scores, void* out_classes,
+                  int* out_valid, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const rpp_config& c = h->cfg;
+  const int C = c.num_classes, M = c.max_detections;
+  const size_t P = (size_t)B * C;
+  const SamplePlan plan = make_plan(n, 1536);
+  Workspace w = layout_cols(ws, P, M, plan.CAP);
+  if (w.bytes > ws_bytes) return fail(RPP_EWORKSPACE, "workspace: need %zu bytes, got %zu", w.bytes, ws_bytes);
+  const float T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
+  int rc = launch_collect(h, x, w, plan, B, n, C, T_min, st);
+  if (rc) return rc;
+
+  if (c.mode == RPP_PER_CLASS_SOFT_NMS) return fail(RPP_EINVAL, "PerClassSoftNMS: not implemented yet");
+  ColProblemParams pp{};
+  pp.x = x; pp.is_logit = is_logit; pp.N = n; pp.C = C;
+  pp.deltas = deltas; pp.anchors = h->d_anchors; pp.boxes = boxes; pp.q = q; pp.dp = h->dp;
+  pp.clip_before = c.mode != RPP_COMBINED_NMS;
+  pp.iou_threshold = c.iou_threshold;
+  pp.score_threshold = c.score_threshold;
+  pp.T_min = T_min;
+  pp.M = M;
+  pp.M_lim = c.mode == RPP_COMBINED_NMS ? (int)std::min<long>(M, k_lim) : M;
+  pp.k_lim = k_lim;
+  pp.T = w.T; pp.cand_count = w.cand_count; pp.cand = w.cand; pp.CAP = plan.CAP;
+  pp.force_scan = h->force_scan;
+  pp.sel_key = w.sel_key; pp.sel_box = w.sel_box; pp.sel_cnt = w.sel_cnt;
+  const size_t smem = nms_shared_bytes(pp.M_lim);
+  col_hard_nms_kernel<<<(unsigned)P, RPP_NMS_NT, smem, st>>>(pp);
+  LAUNCHED();
+
+  MergeParams mp{};
+  mp.C = C; mp.M = M; mp.combined = c.mode == RPP_COMBINED_NMS;
+  mp.sel_key = w.sel_key; mp.sel_box = w.sel_box; mp.sel_cnt = w.sel_cnt;
+  mp.x = x; mp.is_logit = is_logit; mp.N = n;
+  mp.deltas = deltas; mp.anchors = h->d_anchors; mp.boxes = boxes; mp.q = q; mp.dp = h->dp;
+  mp.row0_mode = row0_mode;
+  mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_classes = out_classes; mp.out_valid = out_valid;
+  merge_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mp);
+  LAUNCHED();
+  return RPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rpp_last_error(void) { return g_err; }
+int rpp_last_launch_count(void) { return g_launches; }
+
+int rpp_create(const rpp_config* cfg, void** handle) {
+  if (!cfg || !handle) return fail(RPP_EINVAL, "null argument");
+  *handle = nullptr;
+  if (cfg->mode < 0 || cfg->mode > 4)
+    return fail(RPP_EMODE, "Requested unsupported mode: %d, available modes are: CombinedNMS, GlobalSoftNMS, "
+                           "GlobalHardNMS, PerClassSoftNMS, PerClassHardNMS", cfg->mode);
+  const int levels = cfg->max_level - cfg->min_level + 1;
+  if (cfg->H <= 0 || cfg->W <= 0 || levels <= 0 || levels > 16 || cfg->min_level < 0 || cfg->max_level > 30)
+    return fail(RPP_EINVAL, "bad input_shape / levels");
+  if (cfg->num_classes <= 0) return fail(RPP_EINVAL, "num_classes must be positive");
+  if (cfg->n_areas < levels || cfg->n_areas > 16 || !cfg->areas)
+    return fail(RPP_EINVAL, "anchor_params.areas needs one entry per level (got %d for %d levels)", cfg->n_areas,
+                levels);
+  if (cfg->n_ratios <= 0 || cfg->n_ratios > 8 || cfg->n_scales <= 0 || cfg->n_scales > 8 || !cfg->aspect_ratios ||
+      !cfg->scales)
+    return fail(RPP_EINVAL, "anchor_params.aspect_ratios / scales: 1..8 entries each");
+  if (cfg->max_detections <= 0 || cfg->max_detections > 1024)
+    return fail(RPP_EINVAL, "max_detections must be in 1..1024");
+  if ((cfg->mode == RPP_GLOBAL_SOFT_NMS || cfg->mode == RPP_PER_CLASS_SOFT_NMS) && !(cfg->soft_nms_sigma == cfg->soft_nms_sigma))
+    return fail(RPP_EINVAL, "soft_nms_sigma is required for the soft NMS modes");
+
+  int dev = 0, count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(RPP_ECUDA, "no CUDA device: libretinapost has no CPU path");
+  CUDA_OK(cudaGetDevice(&dev));
+  Handle* h = new (std::nothrow) Handle();
+  if (!h) return fail(RPP_EINVAL, "out of host memory");
+  h->cfg = *cfg;
+  h->areas.assign(cfg->areas, cfg->areas + cfg->n_areas);
+  h->ratios.assign(cfg->aspect_ratios, cfg->aspect_ratios + cfg->n_ratios);
+  h->scales.assign(cfg->scales, cfg->scales + cfg->n_scales);
+  h->cfg.areas = h->areas.data();
+  h->cfg.aspect_ratios = h->ratios.data();
+  h->cfg.scales = h->scales.data();
+  h->levels = levels;
+  h->device = dev;
+  h->force_scan = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+
+  AnchorParams& ap = h->ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.H = cfg->H; ap.W = cfg->W; ap.min_level = cfg->min_level; ap.num_levels = levels;
+  ap.n_ratios = cfg->n_ratios; ap.n_scales = cfg->n_scales;
+  const int A = cfg->n_ratios * cfg->n_scales;
+  long n = 0;
+  ap.bounds[0] = 0;
+  for (int li = 0; li < levels; ++li) {
+    const double s = std::pow(2.0, cfg->min_level + li);
+    const int fh = (int)std::ceil(cfg->H / s), fw = (int)std::ceil(cfg->W / s);  // anchor_generator.py:42-49
+    ap.fw[li] = fw;
+    n += (long)fh * fw * A;
+    ap.bounds[li + 1] = n;
+    ap.areas[li] = cfg->areas[li];
+  }
+  for (int i = 0; i < cfg->n_ratios; ++i) ap.ratios[i] = cfg->aspect_ratios[i];
+  for (int i = 0; i < cfg->n_scales; ++i) ap.scales[i] = cfg->scales[i];
+  h->N = n;
+  if (n <= 0 || n >= 0x7fffffffL) { delete h; return fail(RPP_EINVAL, "anchor count out of range"); }
+
+  h->dp.shape[0] = (float)cfg->H; h->dp.shape[1] = (float)cfg->W;
+  h->dp.shape[2] = (float)cfg->H; h->dp.shape[3] = (float)cfg->W;
+  for (int i = 0; i < 4; ++i) h->dp.var[i] = cfg->box_variance[i];
+  h->dp.scale = cfg->scale_box_targets;
+
+  cudaError_t e = cudaMalloc(&h->d_anchors, (size_t)n * sizeof(float4));
+  if (e != cudaSuccess) { delete h; return fail(RPP_ECUDA, "cudaMalloc anchors: %s", cudaGetErrorString(e)); }
+  anchors_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ap, n, h->d_anchors);
+  float* d_t = nullptr;
+  e = cudaMalloc(&d_t, sizeof(float));
+  if (e == cudaSuccess) {
+    logit_threshold_kernel<<<1, 32>>>(cfg->score_threshold, d_t);
+    e = cudaMemcpy(&h->T_logit, d_t, sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_t);
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(h->d_anchors);
+    delete h;
+    return fail(RPP_ECUDA, "create kernels: %s", cudaGetErrorString(e));
+  }
+  cudaFuncSetAttribute(col_hard_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  *handle = h;
+  return RPP_OK;
+}
+
+int rpp_destroy(void* handle) {
+  Handle* h = (Handle*)handle;
+  if (!h) return RPP_OK;
+  cudaFree(h->d_anchors);
+  delete h;
+  return RPP_OK;
+}
+
+long rpp_num_anchors(void* handle) { return handle ? ((Handle*)handle)->N : -1; }
+int rpp_num_levels(void* handle) { return handle ? ((Handle*)handle)->levels : -1; }
+int rpp_anchor_boundaries(void* handle, long* h_out) {
+  Handle* h = (Handle*)handle;
+  if (!h || !h_out) return fail(RPP_EINVAL, "null argument");
+  for (int i = 0; i <= h->levels; ++i) h_out[i] = h->ap.bounds[i];
+  return RPP_OK;
+}
+int rpp_classes_itemsize(void* handle) {
+  Handle* h = (Handle*)handle;
+  if (!h) return -1;
+  return (h->cfg.mode == RPP_GLOBAL_SOFT_NMS || h->cfg.mode == RPP_GLOBAL_HARD_NMS) ? 8 : 4;
+}
+int rpp_debug_force_exact_scan(void* handle, int on) {
+  if (!handle) return fail(RPP_EINVAL, "null handle");
+  ((Handle*)handle)->force_scan = on ? 1 : 0;
+  return RPP_OK;
+}
+
+int rpp_anchors(void* handle, float* d_out, void* stream) {
+  Handle* h = (Handle*)handle;
+  if (!h || !d_out) return fail(RPP_EINVAL, "null argument");
+  CUDA_OK(cudaMemcpyAsync(d_out, h->d_anchors, (size_t)h->N * sizeof(float4), cudaMemcpyDeviceToDevice,
+                          (cudaStream_t)stream));
+  return RPP_OK;
+}
+
+size_t rpp_workspace_bytes(void* handle, int B, long n) {
+  Handle* h = (Handle*)handle;
+  if (!h || B <= 0) return 0;
+  if (n <= 0) n = h->N;
+  const int C = h->cfg.num_classes;
+  const SamplePlan plan = make_plan(n, 1536);
+  const Workspace w = layout_cols(nullptr, (size_t)B * C, h->cfg.max_detections, plan.CAP);
+  return w.bytes + 4096;
+}
+
+int rpp_decode(void* handle, const float* d_logits, const float* d_deltas, int B, float* d_scores, float* d_boxes,
+               void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || B <= 0) return fail(RPP_EINVAL, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = h->cfg.num_classes;
+  if (d_scores) {
+    if (!d_logits) return fail(RPP_EINVAL, "null logits");
+    const size_t n = (size_t)B * h->N * C;
+    size_t grid = (n + 255) / 256;
+    if (grid > (size_t)h->sm_count * 16) grid = (size_t)h->sm_count * 16;
+    sigmoid_kernel<<<(unsigned)grid, 256, 0, st>>>(d_logits, d_scores, n);
+    LAUNCHED();
+  }
+  if (d_boxes) {
+    if (!d_deltas) return fail(RPP_EINVAL, "null deltas");
+    const size_t n = (size_t)B * h->N;
+    size_t grid = (n + 255) / 256;
+    if (grid > (size_t)h->sm_count * 16) grid = (size_t)h->sm_count * 16;
+    decode_kernel<<<(unsigned)grid, 256, 0, st>>>((const float4*)d_deltas, h->d_anchors, B, h->N, h->dp,
+                                                  (float4*)d_boxes);
+    LAUNCHED();
+  }
+  return RPP_OK;
+}
+
+int rpp_topk(void* handle, const float* d_scores, const float* d_boxes, int B, long n, float* d_scores_out,
+             float* d_boxes_out, int* d_index_out, void* ws, size_t ws_bytes, void* stream) {
+  (void)handle; (void)d_scores; (void)d_boxes; (void)B; (void)n; (void)d_scores_out; (void)d_boxes_out;
+  (void)d_index_out; (void)ws; (void)ws_bytes; (void)stream;
+  g_launches = 0;
+  return fail(RPP_EINVAL, "rpp_topk: not implemented yet");
+}
+
+int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, long n, int q, float* d_boxes_out,
+            float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes, void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !d_scores || !d_boxes || B <= 0 || n <= 0) return fail(RPP_EINVAL, "bad argument");
+  const rpp_config& c = h->cfg;
+  if (q != 1 && q != c.num_classes) return fail(RPP_EINVAL, "boxes must be [B,n,4] or [B,n,num_classes,4]");
+  if (!is_per_class_mode(c.mode)) {
+    if (q != 1) return fail(RPP_ECOMBO, "Global* NMS modes need class-agnostic [B,n,4] boxes "
+                                        "(inference.filter_per_class=false)");
+    return fail(RPP_EINVAL, "Global* modes: not implemented yet");
+  }
+  return run_per_class(h, d_scores, 0, nullptr, (const float4*)d_boxes, q, B, n, n, 0, (float4*)d_boxes_out,
+                       d_scores_out, d_classes_out, d_valid_out, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int rpp_detect(void* handle, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,
+               float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes, void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
+  const rpp_config& c = h->cfg;
+  const bool filtered = c.pre_nms_top_k > 0;
+  if (is_per_class_mode(c.mode)) {
+    if (!filtered || c.filter_per_class) {
+      const long k_lim = filtered ? std::min<long>(c.pre_nms_top_k, h->N) : h->N;
+      return run_per_class(h, d_logits, 1, (const float4*)d_deltas, nullptr, 1, B, h->N, k_lim, filtered ? 1 : 0,
+                           (float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out, ws, ws_bytes,
+                           (cudaStream_t)stream);
+    }
+    return fail(RPP_EINVAL, "global pre-NMS filter: not implemented yet");
+  }
+  if (filtered && c.filter_per_class)
+    return fail(RPP_ECOMBO, "Global* NMS modes need inference.filter_per_class=false (per-class filtered boxes are "
+                            "4-D; the reference fails with a rank error)");
+  return fail(RPP_EINVAL, "Global* modes: not implemented yet");
+}
+
+int rpp_detect_host(void* handle, int device, const float* h_deltas, const float* h_logits, int B, float* h_boxes,
+                    float* h_scores, void* h_classes, int* h_valid) {
+  (void)handle; (void)device; (void)h_deltas; (void)h_logits; (void)B; (void)h_boxes; (void)h_scores;
+  (void)h_classes; (void)h_valid;
+  return fail(RPP_EINVAL, "rpp_detect_host: not implemented yet");
+}
+
+}  // extern "C"

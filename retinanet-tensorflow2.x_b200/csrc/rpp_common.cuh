@@ -1,0 +1,148 @@
+// rpp_common.cuh — arithmetic and block primitives shared by the retinapost kernels (sm_100a).
+//
+// Arithmetic that decides results (decode, IoU, sigmoid) is written with explicit round-to-nearest intrinsics so
+// that no FMA contraction can change a result relative to the reference's unfused TensorFlow ops
+// (SURVEY.md A.1, A.6); the translation unit is additionally compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define RPP_FULL_MASK 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------------------------
+// keys: a candidate is ordered by (score descending, tie index ascending) — the total order of TF's TopKV2
+//  and of NonMaxSuppressionV5's priority queue (A.2).  One u64, larger = better, 0 = invalid.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 ord_f32(float f) {
+  f = __fadd_rn(f, 0.0f);  // -0.0 -> +0.0 (they compare equal in the reference)
+  u32 b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float unord_f32(u32 o) {
+  u32 b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ u64 make_key(float score, u32 tie) {
+  return ((u64)ord_f32(score) << 32) | (u64)(0xffffffffu - tie);
+}
+__device__ __forceinline__ float key_score(u64 k) { return unord_f32((u32)(k >> 32)); }
+__device__ __forceinline__ u32 key_tie(u64 k) { return 0xffffffffu - (u32)k; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// elementwise numerics
+// ---------------------------------------------------------------------------------------------------------------
+// tf.nn.sigmoid (postprocessing_ops.py:114): the exact logistic evaluated in binary64 and rounded once to
+// binary32 (DESIGN.md "Numerics").  Only evaluated for candidates that survive the raw-logit pre-threshold.
+__device__ __forceinline__ float sigmoid_f32(float x) { return (float)(1.0 / (1.0 + exp(-(double)x))); }
+// tf.math.exp (postprocessing_ops.py:97)
+__device__ __forceinline__ float exp_f32(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+__device__ __forceinline__ float4 clip01(float4 b) {
+  return make_float4(clip01(b.x), clip01(b.y), clip01(b.z), clip01(b.w));
+}
+
+struct DecodeParams {
+  float shape[4];   // [H, W, H, W] applied to [x1, y1, x2, y2] (postprocessing_ops.py:65-69, :104)
+  float var[4];     // encoder_params.box_variance
+  int scale;        // encoder_params.scale_box_targets (:90-91)
+};
+
+// TransformBoxesAndScores._transform_box_predictions (postprocessing_ops.py:87-105); anchor = [cx, cy, w, h].
+__device__ __forceinline__ float4 decode_box(float4 d, float4 a, const DecodeParams& p) {
+  if (p.scale) {
+    d.x = __fmul_rn(d.x, p.var[0]); d.y = __fmul_rn(d.y, p.var[1]);
+    d.z = __fmul_rn(d.z, p.var[2]); d.w = __fmul_rn(d.w, p.var[3]);
+  }
+  const float cx = __fadd_rn(__fmul_rn(d.x, a.z), a.x);
+  const float cy = __fadd_rn(__fmul_rn(d.y, a.w), a.y);
+  const float hw = __fdiv_rn(__fmul_rn(exp_f32(d.z), a.z), 2.0f);
+  const float hh = __fdiv_rn(__fmul_rn(exp_f32(d.w), a.w), 2.0f);
+  return make_float4(__fdiv_rn(__fsub_rn(cx, hw), p.shape[0]), __fdiv_rn(__fsub_rn(cy, hh), p.shape[1]),
+                     __fdiv_rn(__fadd_rn(cx, hw), p.shape[2]), __fdiv_rn(__fadd_rn(cy, hh), p.shape[3]));
+}
+
+// IoU of TF's NMS kernels.  canon_box returns (min0, min1, max0, max1) and the area.
+__device__ __forceinline__ float4 canon_box(float4 b, float& area) {
+  float4 c = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
+  area = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+  return c;
+}
+__device__ __forceinline__ float iou_canon(float4 a, float area_a, float4 b, float area_b) {
+  if (area_a <= 0.0f || area_b <= 0.0f) return 0.0f;
+  const float h0 = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float h1 = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  const float inter = __fmul_rn(h0, h1);
+  if (inter <= 0.0f) return 0.0f;  // 0 / (positive) == 0
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// block primitives (NT threads, NT a multiple of 32, <= 1024)
+// ---------------------------------------------------------------------------------------------------------------
+template <int NT>
+struct BlockScratch {
+  u64 a[NT / 32];
+  u64 b[NT / 32];
+  u32 c[NT / 32];
+  u64 ra, rb;
+  u32 rc;
+};
+
+// count / max / min of a per-thread (cnt, mx, mn) triple; result broadcast to all threads.
+template <int NT>
+__device__ __forceinline__ void block_cnt_max_min(u32& cnt, u64& mx, u64& mn, BlockScratch<NT>* s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(RPP_FULL_MASK, cnt, o);
+    u64 m2 = __shfl_xor_sync(RPP_FULL_MASK, mx, o);
+    u64 n2 = __shfl_xor_sync(RPP_FULL_MASK, mn, o);
+    mx = m2 > mx ? m2 : mx;
+    mn = n2 < mn ? n2 : mn;
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect scratch reuse
+  if (l == 0) { s->a[w] = mx; s->b[w] = mn; s->c[w] = cnt; }
+  __syncthreads();
+  if (w == 0) {
+    u64 m = l < NT / 32 ? s->a[l] : 0ull;
+    u64 n = l < NT / 32 ? s->b[l] : ~0ull;
+    u32 c = l < NT / 32 ? s->c[l] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(RPP_FULL_MASK, c, o);
+      u64 m2 = __shfl_xor_sync(RPP_FULL_MASK, m, o);
+      u64 n2 = __shfl_xor_sync(RPP_FULL_MASK, n, o);
+      m = m2 > m ? m2 : m;
+      n = n2 < n ? n2 : n;
+    }
+    if (l == 0) { s->ra = m; s->rb = n; s->rc = c; }
+  }
+  __syncthreads();
+  mx = s->ra; mn = s->rb; cnt = s->rc;
+}
+
+// Descending bitonic sort of P2 (power of two) u64 keys in shared (or global) memory.
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_desc(u64* k, int P2) {
+  for (int size = 2; size <= P2; size <<= 1) {
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (P2 >> 1); t += NT) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const u64 a = k[i], b = k[p];
+        const bool desc = (i & size) == 0;
+        if (desc ? (a < b) : (a > b)) { k[i] = b; k[p] = a; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}

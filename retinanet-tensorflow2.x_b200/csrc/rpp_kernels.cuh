@@ -1,0 +1,534 @@
+// rpp_kernels.cuh — device kernels of libretinapost (sm_100a).  See DESIGN.md for the data layout and the
+// per-kernel roofline; reference citations are relative to /root/reference/retinanet/.
+#pragma once
+#include "rpp_common.cuh"
+#include "rpp_select.cuh"
+
+// ===============================================================================================================
+// K0a  anchors — AnchorBoxGenerator (dataloader/anchor_generator.py:24-104).  One thread per anchor.
+// ===============================================================================================================
+struct AnchorParams {
+  int H, W, min_level, num_levels, n_ratios, n_scales;
+  long bounds[17];     // cumulative anchors per level
+  int fw[16];          // feature width per level
+  double areas[16];
+  double ratios[8];
+  double scales[8];
+};
+
+__global__ void anchors_kernel(AnchorParams ap, long N, float4* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int li = 0;
+  while (li + 1 < ap.num_levels && i >= ap.bounds[li + 1]) ++li;
+  const int A = ap.n_ratios * ap.n_scales;
+  const long r = i - ap.bounds[li];
+  const int a = (int)(r % A);
+  const long cell = r / A;
+  const int x = (int)(cell % ap.fw[li]), y = (int)(cell / ap.fw[li]);
+  const float stride = (float)(1 << (ap.min_level + li));
+  // _compute_dims :51-63 — area/ratio in float64 (Python), then fp32 sqrt / div / mul; ratio-major, scale-minor
+  const int ri = a / ap.n_scales, si = a % ap.n_scales;
+  const float h = __fsqrt_rn((float)(ap.areas[li] / ap.ratios[ri]));
+  const float w = __fdiv_rn((float)ap.areas[li], h);
+  const float s = (float)ap.scales[si];
+  out[i] = make_float4(__fmul_rn(__fadd_rn((float)x, 0.5f), stride), __fmul_rn(__fadd_rn((float)y, 0.5f), stride),
+                       __fmul_rn(s, w), __fmul_rn(s, h));
+}
+
+// ===============================================================================================================
+// K0b  exact pre-image of the score threshold: the smallest logit x with sigmoid(x) > score_threshold, found by
+// bisection over the ordered float encoding with the device sigmoid itself, so `logit >= T` <=> `score > thr`.
+// ===============================================================================================================
+__global__ void logit_threshold_kernel(float score_threshold, float* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // ordered encodings of -inf .. +inf
+  u32 lo = ord_f32(-INFINITY), hi = ord_f32(INFINITY);
+  if (sigmoid_f32(unord_f32(lo)) > score_threshold) { *out = -INFINITY; return; }
+  if (!(sigmoid_f32(unord_f32(hi)) > score_threshold)) { *out = INFINITY; return; }  // callers treat +inf as "none"
+  // invariant: S(lo) <= thr < S(hi)
+  while (hi - lo > 1u) {
+    const u32 mid = lo + ((hi - lo) >> 1);
+    if (sigmoid_f32(unord_f32(mid)) > score_threshold) hi = mid; else lo = mid;
+  }
+  *out = unord_f32(hi);
+}
+
+// ===============================================================================================================
+// K0c  TransformBoxesAndScores.call materialised (postprocessing_ops.py:107-117) — stage-wise entry rpp_decode.
+// ===============================================================================================================
+__global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = sigmoid_f32(x[i]);
+}
+
+__global__ void decode_kernel(const float4* __restrict__ deltas, const float4* __restrict__ anchors, long B, long N,
+                              DecodeParams dp, float4* __restrict__ out) {
+  const size_t tot = (size_t)B * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = decode_box(deltas[i], anchors[i % N], dp);
+}
+
+// ===============================================================================================================
+// K1  sample -> per-(image, class) pre-threshold.
+//
+// Candidates for one NMS problem are "the best few thousand of a column of N logits".  A strided sample of the
+// column (every `stride`-th anchor, interleaved into G groups) gives G group maxima; their r-th smallest is an
+// estimate of the logit whose upper tail holds ~target elements.  The estimate only has to be roughly right: the
+// problem kernel consumes candidates lazily and falls back to an exact scan of the column if the list runs dry,
+// so results never depend on it.  One block per image; thread = (class, row lane); loads are row-contiguous.
+//   T[b*C + c] = max(estimate, T_min)   (T_min = exact logit pre-image of the score threshold, or -inf)
+// ===============================================================================================================
+__global__ void sample_threshold_kernel(const float* __restrict__ x /*[B,N,C]*/, long N, int C, int stride, int G,
+                                        int rows_per_group, int rank, float T_min, float* __restrict__ T) {
+  extern __shared__ u32 gm[];  // [G][C] ordered-float group maxima
+  const int b = blockIdx.x;
+  const int lanes = blockDim.x / C;  // row lanes
+  const int c = threadIdx.x % C, rl = threadIdx.x / C;
+  for (int i = threadIdx.x; i < G * C; i += blockDim.x) gm[i] = 0u;
+  __syncthreads();
+  const long n_s = (long)G * rows_per_group;
+  if (rl < lanes) {
+    const float* base = x + (size_t)b * N * C + c;
+    for (long s = rl; s < n_s; s += lanes) {
+      const float v = __ldg(base + (size_t)(s * stride) * C);
+      atomicMax(&gm[(int)(s % G) * C + c], ord_f32(v));
+    }
+  }
+  __syncthreads();
+  // r-th smallest of the G maxima of each class: rank counting, one (class, element) pair per thread step
+  for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
+    const int cc = i % C;
+    const u32 v = gm[i];
+    int less = 0, eq = 0;
+    for (int g = 0; g < G; ++g) {
+      const u32 o = gm[g * C + cc];
+      less += o < v;
+      eq += o == v;
+    }
+    if (less <= rank && rank < less + eq) T[(size_t)b * C + cc] = fmaxf(unord_f32(v), T_min);
+  }
+}
+
+__global__ void fill_kernel(float* p, size_t n, float v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ===============================================================================================================
+// K2  collect — the HBM-bound stream.  Reads class_logits [B,N,C] exactly once with 128-bit streaming loads and
+// appends every element with logit >= T[b,c] to that problem's candidate list as (logit bits, anchor index).
+// No sigmoid here: the comparison is on raw logits (monotone pre-image of the score), so the kernel issues one
+// LDG.128 and four compares per 16 bytes.  Thread = (class quad, row lane) so its four thresholds live in
+// registers for a whole tile; UNROLL independent loads in flight per thread.
+// ===============================================================================================================
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void append_cand(u32* cand_count, uint2* cand, int CAP, size_t p, float v, u32 idx) {
+  const u32 slot = atomicAdd(&cand_count[p], 1u);
+  if (slot < (u32)CAP) cand[p * (size_t)CAP + slot] = make_uint2(__float_as_uint(v), idx);
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(1024)
+collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* __restrict__ T /*[B*C]*/,
+                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C4,
+                     int lanes /*row lanes per block*/, int rows_per_tile, int tiles_per_image) {
+  const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
+  if (rl >= lanes) return;
+  const int C = C4 * 4;
+  const long n_tiles = (long)B * tiles_per_image;
+  for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_per_image);
+    const long r0 = (long)(tile % tiles_per_image) * rows_per_tile;
+    const long r1 = r0 + rows_per_tile < N ? r0 + rows_per_tile : N;
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(T + (size_t)b * C) + cq);
+    const float4* src = x4 + (size_t)b * N * C4 + cq;
+    const size_t pbase = (size_t)b * C + cq * 4;
+    for (long row = r0 + rl; row < r1; row += (long)lanes * UNROLL) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long r = row + (long)u * lanes;
+        v[u] = r < r1 ? ld_stream_f4(src + (size_t)r * C4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const u32 r = (u32)(row + (long)u * lanes);
+        // NaN never passes >=; a -inf fill never passes a finite threshold and T = -inf only with real rows
+        const bool h0 = v[u].x >= t4.x, h1 = v[u].y >= t4.y, h2 = v[u].z >= t4.z, h3 = v[u].w >= t4.w;
+        if ((h0 | h1 | h2 | h3) && (long)r < r1) {
+          if (h0) append_cand(cand_count, cand, CAP, pbase + 0, v[u].x, r);
+          if (h1) append_cand(cand_count, cand, CAP, pbase + 1, v[u].y, r);
+          if (h2) append_cand(cand_count, cand, CAP, pbase + 2, v[u].z, r);
+          if (h3) append_cand(cand_count, cand, CAP, pbase + 3, v[u].w, r);
+        }
+      }
+    }
+  }
+}
+
+// generic C (C % 4 != 0, or unaligned base): one element per thread step
+__global__ void collect_cols1_kernel(const float* __restrict__ x, const float* __restrict__ T,
+                                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N,
+                                     int C) {
+  const size_t tot = (size_t)B * N * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + e);
+    const size_t row = e / C;
+    const int c = (int)(e - row * C);
+    const int b = (int)(row / N);
+    const size_t p = (size_t)b * C + c;
+    if (v >= T[p]) append_cand(cand_count, cand, CAP, p, v, (u32)(row - (size_t)b * N));
+  }
+}
+
+// ===============================================================================================================
+// K3  per-(image, class) problem kernel: lazy exact selection + greedy hard NMS
+//     (CombinedNMS per-class stage;  PerClassHardNMS = NonMaxSuppressionV5 hard, A.2).
+// ===============================================================================================================
+#define RPP_NMS_NT 128
+#define RPP_CHUNK_CAP 1024
+#define RPP_LIST_SMEM 2048
+
+struct ColProblemParams {
+  // source: columns of a [B, N, C] tensor
+  const float* x;          // logits (is_logit = 1) or scores (is_logit = 0)
+  int is_logit;
+  long N;                  // rows per image
+  int C;
+  // boxes: decoded on demand (deltas + anchors) or gathered from a dense [B, N, q, 4] tensor
+  const float4* deltas;    // [B,N] (fused) or nullptr
+  const float4* anchors;   // [N]
+  const float4* boxes;     // dense boxes (stage-wise) or nullptr
+  int q;
+  DecodeParams dp;
+  int clip_before;         // clip boxes to [0,1] before IoU (every mode but CombinedNMS; B6)
+  float iou_threshold;
+  float score_threshold;
+  float T_min;             // raw pre-image of the score threshold (candidates have raw >= T_min)
+  int M_lim;               // max kept per problem
+  long k_lim;              // max candidates consumed (pre_nms_top_k after clamping; N when unfiltered)
+  int M;                   // stride of the sel_* arrays
+  // candidate lists
+  const float* T;          // [P] thresholds used by the collect pass
+  const u32* cand_count;   // [P]
+  uint2* cand;             // [P][CAP]
+  int CAP;
+  int force_scan;          // debug: ignore the lists, use the exact column scan only
+  // outputs per problem
+  u64* sel_key;            // [P][M]  (score bits | ~row index)
+  float4* sel_box;         // [P][M]  kept boxes as they leave NMS (clipped iff clip_before)
+  int* sel_cnt;            // [P]
+};
+
+struct NmsShared {
+  SelectScratch<RPP_NMS_NT> sel;
+  u64 chunk[RPP_CHUNK_CAP];
+  u64 lkeys[RPP_LIST_SMEM];
+  float4 cbox[RPP_NMS_NT];   // canonical boxes of the current group
+  float carea[RPP_NMS_NT];
+  float4 corig[RPP_NMS_NT];  // boxes as emitted
+  int nkept;
+  int done;
+  // followed in dynamic shared memory by: float4 kbox[M_lim] (kept, canonical), float karea[M_lim]
+};
+__device__ __forceinline__ float4* nms_kbox(NmsShared* sh) { return reinterpret_cast<float4*>(sh + 1); }
+__device__ __forceinline__ float* nms_karea(NmsShared* sh, int M_lim) {
+  return reinterpret_cast<float*>(nms_kbox(sh) + M_lim);
+}
+static inline size_t nms_shared_bytes(int M_lim) { return sizeof(NmsShared) + (size_t)M_lim * 20 + 16; }
+
+__device__ __forceinline__ float col_score(const ColProblemParams& P, float raw) {
+  return P.is_logit ? sigmoid_f32(raw) : raw;
+}
+
+__device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int c, u32 row) {
+  if (P.boxes) {
+    const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;  // boxes[:, min(q-1, c)] (:440)
+    return P.boxes[((size_t)b * P.N + row) * P.q + qi];
+  }
+  return decode_box(P.deltas[(size_t)b * P.N + row], P.anchors[row], P.dp);
+}
+
+// Greedy hard NMS over one sorted chunk.  Returns with sh->done set when M_lim kept or k_lim consumed.
+__device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b, int c, size_t p, int m,
+                                 long& consumed) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4* kbox = nms_kbox(sh);
+  float* karea = nms_karea(sh, P.M_lim);
+  long room = P.k_lim - consumed;
+  int m_eff = (long)m < room ? m : (int)room;
+  for (int g0 = 0; g0 < m_eff; g0 += RPP_NMS_NT) {
+    const int j = g0 + tid;
+    if (j < m_eff) {
+      float4 bx = col_box(P, b, c, key_tie(sh->chunk[j]));
+      if (P.clip_before) bx = clip01(bx);
+      float area;
+      sh->corig[tid] = bx;
+      sh->cbox[tid] = canon_box(bx, area);
+      sh->carea[tid] = area;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int nk = sh->nkept;
+      const int gcount = m_eff - g0 < RPP_NMS_NT ? m_eff - g0 : RPP_NMS_NT;
+      bool done = false;
+      for (int t0 = 0; t0 < gcount && !done; t0 += 32) {
+        const int ci = t0 + lane;
+        bool alive = ci < gcount;
+        const float4 bx = sh->cbox[ci < RPP_NMS_NT ? ci : 0];
+        const float area = sh->carea[ci < RPP_NMS_NT ? ci : 0];
+        for (int t = 0; t < nk; ++t) {
+          if (alive && iou_canon(bx, area, kbox[t], karea[t]) > P.iou_threshold) alive = false;
+          if (!__any_sync(RPP_FULL_MASK, alive)) break;
+        }
+        u32 rem = __ballot_sync(RPP_FULL_MASK, alive);
+        while (rem) {
+          const int f = __ffs(rem) - 1;
+          const float4 fb = make_float4(__shfl_sync(RPP_FULL_MASK, bx.x, f), __shfl_sync(RPP_FULL_MASK, bx.y, f),
+                                        __shfl_sync(RPP_FULL_MASK, bx.z, f), __shfl_sync(RPP_FULL_MASK, bx.w, f));
+          const float fa = __shfl_sync(RPP_FULL_MASK, area, f);
+          if (lane == f) {
+            kbox[nk] = bx;
+            karea[nk] = area;
+            P.sel_key[p * P.M + nk] = sh->chunk[g0 + ci];
+            P.sel_box[p * P.M + nk] = sh->corig[ci];
+          }
+          ++nk;
+          if (nk >= P.M_lim) { done = true; break; }
+          if (alive && lane > f && iou_canon(bx, area, fb, fa) > P.iou_threshold) alive = false;
+          rem = __ballot_sync(RPP_FULL_MASK, alive) & ~((2u << f) - 1u);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        sh->nkept = nk;
+        if (done) sh->done = 1;
+      }
+    }
+    __syncthreads();
+    if (sh->done) break;
+  }
+  consumed += m_eff;
+  if (consumed >= P.k_lim) {
+    __syncthreads();
+    if (tid == 0) sh->done = 1;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(RPP_NMS_NT) col_hard_nms_kernel(ColProblemParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsShared* sh = reinterpret_cast<NmsShared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const size_t p = blockIdx.x;
+  const int b = (int)(p / P.C), c = (int)(p % P.C);
+  if (tid == 0) { sh->nkept = 0; sh->done = 0; }
+  __syncthreads();
+
+  long consumed = 0;
+  const float T = P.T[p];
+  u32 n_raw = P.cand_count[p];
+  const bool overflow = n_raw > (u32)P.CAP;
+  int n_list = (overflow || P.force_scan) ? 0 : (int)n_raw;
+  const bool list_complete = !(T > P.T_min);  // the list holds every element above the score threshold
+  float s_edge = P.score_threshold;
+  if (!list_complete) s_edge = col_score(P, T);
+  if (overflow || P.force_scan) s_edge = INFINITY;
+
+  // ---- phase A: the collected list -------------------------------------------------------------------------
+  if (n_list > 0) {
+    uint2* lst = P.cand + p * (size_t)P.CAP;
+    u64* gkeys = reinterpret_cast<u64*>(lst);
+    u64* keys = n_list <= RPP_LIST_SMEM ? sh->lkeys : gkeys;
+    for (int i = tid; i < n_list; i += RPP_NMS_NT) {
+      const uint2 e = lst[i];
+      const float s = col_score(P, __uint_as_float(e.x));
+      // consumable now: strictly above everything that was NOT collected (those score <= s_edge)
+      const bool ok = s > P.score_threshold && (list_complete || s > s_edge);
+      keys[i] = ok ? make_key(s, e.y) : 0ull;
+    }
+    __syncthreads();
+    u64 KB = ~0ull;
+    int want = 256;
+    while (!sh->done) {
+      const int m = select_chunk<RPP_NMS_NT>([&](int i) { return keys[i]; }, n_list, KB, want, sh->chunk,
+                                             RPP_CHUNK_CAP, &sh->sel);
+      if (m == 0) break;
+      hard_nms_consume(P, sh, b, c, p, m, consumed);
+      want = RPP_CHUNK_CAP;
+    }
+  }
+  // ---- phase B: exact scan of the column for everything at or below the edge ---------------------------------
+  if (!sh->done && (!list_complete || overflow || P.force_scan)) {
+    u64 KB = (s_edge == INFINITY) ? ~0ull : ((u64)(ord_f32(s_edge) + 1u) << 32);
+    const float* col = P.x + (size_t)b * P.N * P.C + c;
+    auto keyfn = [&](int i) -> u64 {
+      const float raw = __ldg(col + (size_t)i * P.C);
+      if (!(raw >= P.T_min)) return 0ull;
+      const float s = col_score(P, raw);
+      return s > P.score_threshold ? make_key(s, (u32)i) : 0ull;
+    };
+    int want = 256;
+    while (!sh->done) {
+      const int m = select_chunk<RPP_NMS_NT>(keyfn, (int)P.N, KB, want, sh->chunk, RPP_CHUNK_CAP, &sh->sel);
+      if (m == 0) break;
+      hard_nms_consume(P, sh, b, c, p, m, consumed);
+      want = RPP_CHUNK_CAP;
+    }
+  }
+  if (tid == 0) P.sel_cnt[p] = sh->nkept;
+}
+
+// ===============================================================================================================
+// K4  per-image merge (PerClass*: concat C*M + tf.nn.top_k(M) + positional mask, postprocessing_ops.py:471-490;
+//     CombinedNMS: SelectResultPerBatch).  One block per image.
+// ===============================================================================================================
+#define RPP_MERGE_NT 256
+
+struct MergeParams {
+  int C, M;
+  int combined;            // 1: CombinedNMS output convention, 0: PerClass*
+  const u64* sel_key;      // [B*C][M]
+  const float4* sel_box;   // [B*C][M]
+  const int* sel_cnt;      // [B*C]
+  // pad box of a class with no candidates = its row 0 (:453 gather of index 0): needs the column argmax
+  const float* x; int is_logit; long N;
+  const float4* deltas; const float4* anchors; const float4* boxes; int q; DecodeParams dp;
+  int row0_mode;           // 0: row 0 = index 0 of the source; 1: row 0 = best of the column (per-class top-k ran)
+  float4* out_boxes;       // [B][M]
+  float* out_scores;       // [B][M]
+  void* out_classes;       // [B][M] f32 (combined) / i32
+  int* out_valid;          // [B]
+};
+
+struct MergeShared {
+  SelectScratch<RPP_MERGE_NT> sel;
+  u64 chunk[RPP_CHUNK_CAP];
+  u64 top[1024];
+  int need[1024];
+  int npos;
+};
+
+__global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MergeShared* sh = reinterpret_cast<MergeShared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int C = P.C, M = P.M;
+  const u64* sk = P.sel_key + (size_t)b * C * M;
+  const int* scnt = P.sel_cnt + (size_t)b * C;
+  auto keyfn = [&](int i) -> u64 {
+    const int c = i / M, slot = i - c * M;
+    if (slot < scnt[c]) return make_key(key_score(sk[i]), (u32)i);
+    return P.combined ? 0ull : make_key(0.0f, (u32)i);  // NMSV5 pads scores with 0.0 (A.2)
+  };
+  u64 KB = ~0ull;
+  int got = 0;
+  while (got < M) {
+    const int m = select_chunk<RPP_MERGE_NT>(keyfn, C * M, KB, M - got, sh->chunk, RPP_CHUNK_CAP, &sh->sel);
+    if (m == 0) break;
+    const int take = m < M - got ? m : M - got;
+    for (int i = tid; i < take; i += RPP_MERGE_NT) sh->top[got + i] = sh->chunk[i];
+    got += take;
+    __syncthreads();
+  }
+  // valid count
+  if (tid == 0) sh->npos = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < got; i += RPP_MERGE_NT)
+    if (P.combined || key_score(sh->top[i]) > 0.0f) ++local;  // :481-482 count(score > 0)
+  if (local) atomicAdd(&sh->npos, local);
+  __syncthreads();
+  const int valid = sh->npos;
+  if (tid == 0) P.out_valid[b] = valid;
+
+  float4* ob = P.out_boxes + (size_t)b * M;
+  float* os = P.out_scores + (size_t)b * M;
+  for (int i = tid; i < M; i += RPP_MERGE_NT) {
+    sh->need[i] = -1;
+    if (P.combined) {
+      if (i < valid) {
+        const u32 flat = key_tie(sh->top[i]);
+        ob[i] = clip01(P.sel_box[(size_t)b * C * M + flat]);  // clip_boxes=True (:234)
+        os[i] = key_score(sh->top[i]);
+        ((float*)P.out_classes)[(size_t)b * M + i] = (float)(flat / M);
+      } else {
+        ob[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        os[i] = 0.0f;
+        ((float*)P.out_classes)[(size_t)b * M + i] = 0.0f;
+      }
+    } else {
+      const u32 flat = key_tie(sh->top[i]);
+      const int c = flat / M, slot = flat - c * M;
+      os[i] = i < valid ? key_score(sh->top[i]) : -1.0f;                       // :484-486
+      ((int*)P.out_classes)[(size_t)b * M + i] = i < valid ? c : -1;           // :488-490
+      if (slot < scnt[c]) ob[i] = P.sel_box[(size_t)b * C * M + flat];
+      else if (P.row0_mode == 1 && scnt[c] > 0) ob[i] = P.sel_box[((size_t)b * C + c) * M];  // row 0 = best kept
+      else sh->need[i] = c;   // NMSV5 pads indices with 0 (:453): row 0 of this class's input list
+    }
+  }
+  if (P.combined) return;
+  __syncthreads();
+  // pad boxes that are "row 0" of a class: index 0 of a dense / unfiltered input (row0_mode 0), or the best element
+  // of the column when the per-class top-k ran first and the class kept nothing (row0_mode 1).
+  int last_c = -1;
+  float4 last_box = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < M; ++i) {
+    const int c = sh->need[i];  // uniform across the block
+    if (c < 0) continue;
+    if (c != last_c) {
+      u32 row = 0;
+      if (P.row0_mode == 1) {
+        // argmax of the column under (score desc, index asc)
+        const float* col = P.x + (size_t)b * P.N * P.C + c;
+        u64 best = 0ull;
+        for (long r = tid; r < P.N; r += RPP_MERGE_NT) {
+          const float raw = __ldg(col + (size_t)r * P.C);
+          const u64 k = ((u64)ord_f32(raw) << 32) | (u64)(0xffffffffu - (u32)r);
+          best = k > best ? k : best;
+        }
+        u32 cnt = 0; u64 mn = ~0ull;
+        block_cnt_max_min<RPP_MERGE_NT>(cnt, best, mn, &sh->sel.bs);
+        row = 0xffffffffu - (u32)best;
+        if (P.is_logit) {
+          // different logits can round to the same score: the reference's order is by SCORE then index
+          const float raw_max = unord_f32((u32)(best >> 32));
+          const float s_max = sigmoid_f32(raw_max);
+          // lowest logit that still rounds to s_max (sigmoid is monotone): bisection on the ordered encoding
+          u32 lo_o = ord_f32(-INFINITY), hi_o = (u32)(best >> 32);   // S(lo) < s_max (or lo = -inf), S(hi) == s_max
+          if (sigmoid_f32(-INFINITY) == s_max) hi_o = lo_o;
+          while (hi_o - lo_o > 1u) {
+            const u32 mid = lo_o + ((hi_o - lo_o) >> 1);
+            if (sigmoid_f32(unord_f32(mid)) == s_max) hi_o = mid; else lo_o = mid;
+          }
+          const float raw_lo = unord_f32(hi_o);
+          u64 best2 = 0ull;
+          for (long r = tid; r < P.N; r += RPP_MERGE_NT) {
+            const float raw = __ldg(col + (size_t)r * P.C);
+            if (raw >= raw_lo) { const u64 k = (u64)(0xffffffffu - (u32)r); best2 = k > best2 ? k : best2; }
+          }
+          cnt = 0; mn = ~0ull;
+          block_cnt_max_min<RPP_MERGE_NT>(cnt, best2, mn, &sh->sel.bs);
+          row = 0xffffffffu - (u32)best2;
+        }
+      }
+      float4 bx;
+      if (P.boxes) {
+        const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;
+        bx = P.boxes[((size_t)b * P.N + row) * P.q + qi];
+      } else {
+        bx = decode_box(P.deltas[(size_t)b * P.N + row], P.anchors[row], P.dp);
+      }
+      last_box = clip01(bx);
+      last_c = c;
+    }
+    if (tid == 0) ob[i] = last_box;
+  }
+}

@@ -1,0 +1,91 @@
+"""ctypes binding of libretinapost.so (C ABI: include/retinapost.h).
+
+There is no CPU path and no fallback: importing this module without the built library, or calling it without a CUDA
+device, raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libretinapost.so')
+
+MODES = ['CombinedNMS', 'GlobalSoftNMS', 'GlobalHardNMS', 'PerClassSoftNMS', 'PerClassHardNMS']
+
+RPP_OK, RPP_EINVAL, RPP_EMODE, RPP_ECOMBO, RPP_EWORKSPACE, RPP_ECUDA = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    'rpp_create', 'rpp_destroy', 'rpp_last_error', 'rpp_num_anchors', 'rpp_num_levels', 'rpp_anchor_boundaries',
+    'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_nms', 'rpp_detect', 'rpp_detect_host',
+    'rpp_last_launch_count', 'rpp_classes_itemsize', 'rpp_debug_force_exact_scan',
+]
+
+
+class RppConfig(ctypes.Structure):
+    _fields_ = [
+        ('H', ctypes.c_int), ('W', ctypes.c_int),
+        ('min_level', ctypes.c_int), ('max_level', ctypes.c_int),
+        ('num_classes', ctypes.c_int),
+        ('n_areas', ctypes.c_int), ('areas', ctypes.POINTER(ctypes.c_double)),
+        ('n_ratios', ctypes.c_int), ('aspect_ratios', ctypes.POINTER(ctypes.c_double)),
+        ('n_scales', ctypes.c_int), ('scales', ctypes.POINTER(ctypes.c_double)),
+        ('box_variance', ctypes.c_float * 4),
+        ('scale_box_targets', ctypes.c_int),
+        ('mode', ctypes.c_int),
+        ('iou_threshold', ctypes.c_float),
+        ('score_threshold', ctypes.c_float),
+        ('soft_nms_sigma', ctypes.c_float),
+        ('pre_nms_top_k', ctypes.c_int),
+        ('filter_per_class', ctypes.c_int),
+        ('max_detections', ctypes.c_int),
+        ('soft_ignores_iou_threshold', ctypes.c_int),
+        ('reserved', ctypes.c_int * 7),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                'libretinapost.so is not built ({}). Run `python -c "import __graft_entry__ as g; g.build()"` or '
+                '`make -C retinanet-tensorflow2.x_b200/csrc`. There is no CPU fallback.'.format(LIB_PATH))
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, cl, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+        L.rpp_create.argtypes = [ctypes.POINTER(RppConfig), ctypes.POINTER(vp)]
+        L.rpp_destroy.argtypes = [vp]
+        L.rpp_last_error.restype = ctypes.c_char_p
+        L.rpp_num_anchors.argtypes = [vp]
+        L.rpp_num_anchors.restype = cl
+        L.rpp_num_levels.argtypes = [vp]
+        L.rpp_anchor_boundaries.argtypes = [vp, ctypes.POINTER(cl)]
+        L.rpp_anchors.argtypes = [vp, vp, vp]
+        L.rpp_workspace_bytes.argtypes = [vp, ci, cl]
+        L.rpp_workspace_bytes.restype = ctypes.c_size_t
+        L.rpp_decode.argtypes = [vp, vp, vp, ci, vp, vp, vp]
+        L.rpp_topk.argtypes = [vp, vp, vp, ci, cl, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        L.rpp_nms.argtypes = [vp, vp, vp, ci, cl, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        L.rpp_detect.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        L.rpp_detect_host.argtypes = [vp, ci, vp, vp, ci, vp, vp, vp, vp]
+        L.rpp_classes_itemsize.argtypes = [vp]
+        L.rpp_debug_force_exact_scan.argtypes = [vp, ci]
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().rpp_last_error().decode('utf-8', 'replace')
+
+
+def check(rc):
+    """Map return codes to the reference's exception types (postprocessing_ops.py:194-197 raises AssertionError)."""
+    if rc == RPP_OK:
+        return
+    msg = last_error()
+    if rc == RPP_EMODE:
+        raise AssertionError(msg)
+    if rc in (RPP_EINVAL, RPP_ECOMBO, RPP_EWORKSPACE):
+        raise ValueError(msg)
+    raise RuntimeError(msg)

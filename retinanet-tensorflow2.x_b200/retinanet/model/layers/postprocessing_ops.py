@@ -1,0 +1,370 @@
+"""The four post-processing layers of the reference (retinanet/model/layers/postprocessing_ops.py), same names,
+constructor signatures, dict keys, output dtypes and padding, running on hand-written sm_100a kernels.
+
+    FuseDetections           postprocessing_ops.py:7-56
+    TransformBoxesAndScores  postprocessing_ops.py:59-117
+    FilterTopKDetections     postprocessing_ops.py:120-173
+    GenerateDetections       postprocessing_ops.py:176-561   (non-TPU branches)
+
+Tensors are torch CUDA tensors.  Each layer alone calls its stage entry point of libretinapost.so (rpp_decode,
+rpp_topk, rpp_nms); `FusedPostProcessing` — what ModelBuilder.add_post_processing_stage builds when the whole chain
+is requested — calls rpp_detect, which never materialises the [B,N,C] score tensor.  There is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from retinanet import _native
+
+_CLASS_DTYPES = {
+    'CombinedNMS': torch.float32,      # TF kernel output (B7)
+    'GlobalSoftNMS': torch.int64,      # tf.argmax (:259)
+    'GlobalHardNMS': torch.int64,
+    'PerClassSoftNMS': torch.int32,    # tf.fill of python ints (:468)
+    'PerClassHardNMS': torch.int32,
+}
+
+
+def _get(params, key):
+    return params[key] if isinstance(params, dict) else getattr(params, key)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _as_f32(t):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('expected a torch.Tensor, got {}'.format(type(t)))
+    if not t.is_cuda:
+        raise RuntimeError('retinapost layers run on CUDA tensors only (no CPU fallback); got a {} tensor'
+                           .format(t.device))
+    return t.to(torch.float32).contiguous()   # tf.cast(..., tf.float32) (:111-112, :539-540)
+
+
+class _Handle:
+    """Owns one rpp handle (include/retinapost.h rpp_create/rpp_destroy) and its cached workspaces."""
+
+    _DUMMY_ANCHORS = {'areas': [1.0], 'aspect_ratios': [1.0], 'scales': [1.0]}
+
+    def __init__(self, H=8, W=8, min_level=3, max_level=3, num_classes=1, anchor_params=None,
+                 box_variance=(0.1, 0.1, 0.2, 0.2), scale_box_targets=False, mode='CombinedNMS',
+                 iou_threshold=0.5, score_threshold=0.05, soft_nms_sigma=0.0, pre_nms_top_k=-1,
+                 filter_per_class=True, max_detections=100, soft_ignores_iou_threshold=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError('retinapost needs a CUDA device: there is no CPU fallback')
+        ap = anchor_params or self._DUMMY_ANCHORS
+        areas = [float(a) for a in _get(ap, 'areas')]
+        ratios = [float(a) for a in _get(ap, 'aspect_ratios')]
+        scales = [float(a) for a in _get(ap, 'scales')]
+        self._keep = (
+            (ctypes.c_double * len(areas))(*areas),
+            (ctypes.c_double * len(ratios))(*ratios),
+            (ctypes.c_double * len(scales))(*scales),
+        )
+        cfg = _native.RppConfig()
+        cfg.H, cfg.W = int(H), int(W)
+        cfg.min_level, cfg.max_level = int(min_level), int(max_level)
+        cfg.num_classes = int(num_classes)
+        cfg.n_areas, cfg.areas = len(areas), self._keep[0]
+        cfg.n_ratios, cfg.aspect_ratios = len(ratios), self._keep[1]
+        cfg.n_scales, cfg.scales = len(scales), self._keep[2]
+        cfg.box_variance = (ctypes.c_float * 4)(*[float(v) for v in box_variance])
+        cfg.scale_box_targets = int(bool(scale_box_targets))
+        cfg.mode = _native.MODES.index(mode) if mode in _native.MODES else -1
+        cfg.iou_threshold = float(iou_threshold)
+        cfg.score_threshold = float(score_threshold)
+        cfg.soft_nms_sigma = float('nan') if soft_nms_sigma is None else float(soft_nms_sigma)
+        cfg.pre_nms_top_k = int(pre_nms_top_k)
+        cfg.filter_per_class = int(bool(filter_per_class))
+        cfg.max_detections = int(max_detections)
+        cfg.soft_ignores_iou_threshold = int(bool(soft_ignores_iou_threshold))
+        self.mode = mode
+        self.num_classes = int(num_classes)
+        self.max_detections = int(max_detections)
+        self.ptr = ctypes.c_void_p()
+        _native.check(_native.lib().rpp_create(ctypes.byref(cfg), ctypes.byref(self.ptr)))
+        self.num_anchors = int(_native.lib().rpp_num_anchors(self.ptr))
+        self._ws = {}
+
+    def workspace(self, B, n, device):
+        key = (int(B), int(n), str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = int(_native.lib().rpp_workspace_bytes(self.ptr, int(B), int(n)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws = {key: ws}   # keep one
+        return ws
+
+    def outputs(self, B, device):
+        M = self.max_detections
+        return {
+            'boxes': torch.empty((B, M, 4), dtype=torch.float32, device=device),
+            'scores': torch.empty((B, M), dtype=torch.float32, device=device),
+            'classes': torch.empty((B, M), dtype=_CLASS_DTYPES[self.mode], device=device),
+            'valid_detections': torch.empty((B,), dtype=torch.int32, device=device),
+        }
+
+    def close(self):
+        if self.ptr:
+            _native.lib().rpp_destroy(self.ptr)
+            self.ptr = ctypes.c_void_p()
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Layer:
+    """Stand-in for tf.keras.layers.Layer: `layer(x)` dispatches to `layer.call(x)`; accepts `name=`."""
+
+    def __init__(self, name=None, **kwargs):
+        self.name = name or type(self).__name__.lower()
+
+    def __call__(self, *args, **kwargs):
+        return self.call(*args, **kwargs)
+
+
+class FuseDetections(Layer):
+    """postprocessing_ops.py:7-56 — reshape each level's NHWC head output to [B, H*W*A, C] / [B, H*W*A, 4] and
+    concatenate the levels.  Pure data movement (torch views + one concat)."""
+
+    def __init__(self, min_level, max_level, **kwargs):
+        super(FuseDetections, self).__init__(**kwargs)
+
+        self.min_level = min_level
+        self.max_level = max_level
+
+    def call(self, predictions):
+        class_predictions = predictions['class-predictions']
+        box_predictions = predictions['box-predictions']
+
+        box_shape = list(box_predictions[str(self.min_level)].shape)
+        class_shape = list(class_predictions[str(self.min_level)].shape)
+
+        anchors_at_each_location = box_shape[-1] // 4
+        num_classes = class_shape[-1] // anchors_at_each_location
+        batch_size = box_shape[0] or 1
+
+        class_logits = []
+        encoded_boxes = []
+        for level in range(self.min_level, self.max_level + 1):
+            level = str(level)
+            class_logits.append(class_predictions[level].reshape(batch_size, -1, num_classes))
+            encoded_boxes.append(box_predictions[level].reshape(batch_size, -1, 4))
+
+        return {
+            'class_logits': torch.cat(class_logits, dim=1),
+            'encoded_boxes': torch.cat(encoded_boxes, dim=1)
+        }
+
+
+class TransformBoxesAndScores(Layer):
+    """postprocessing_ops.py:59-117 — scores = sigmoid(class_logits), boxes = decode(encoded_boxes, anchors)
+    normalised by [H, W, H, W].  Stage entry point: rpp_decode."""
+
+    def __init__(self, params, **kwargs):
+        super(TransformBoxesAndScores, self).__init__(**kwargs)
+        self._params = params
+        self._handles = {}
+
+    def _handle(self, num_classes):
+        h = self._handles.get(num_classes)
+        if h is None:
+            p = self._params
+            h = _Handle(H=p.input.input_shape[0], W=p.input.input_shape[1],
+                        min_level=p.architecture.feature_fusion.min_level,
+                        max_level=p.architecture.feature_fusion.max_level,
+                        num_classes=num_classes, anchor_params=p.anchor_params,
+                        box_variance=p.encoder_params.box_variance,
+                        scale_box_targets=p.encoder_params.scale_box_targets)
+            self._handles[num_classes] = h
+        return h
+
+    def call(self, predictions):
+        class_logits = _as_f32(predictions['class_logits'])
+        encoded_boxes = _as_f32(predictions['encoded_boxes'])
+        B, N, C = class_logits.shape
+        h = self._handle(C)
+        if N != h.num_anchors or tuple(encoded_boxes.shape) != (B, N, 4):
+            raise ValueError('expected class_logits [B,{0},C] and encoded_boxes [B,{0},4], got {1} and {2}'.format(
+                h.num_anchors, tuple(class_logits.shape), tuple(encoded_boxes.shape)))
+        scores = torch.empty_like(class_logits)
+        boxes = torch.empty_like(encoded_boxes)
+        _native.check(_native.lib().rpp_decode(h.ptr, class_logits.data_ptr(), encoded_boxes.data_ptr(), B,
+                                               scores.data_ptr(), boxes.data_ptr(), _stream()))
+        return {'scores': scores, 'boxes': boxes}
+
+
+class FilterTopKDetections(Layer):
+    """postprocessing_ops.py:120-173 — pre-NMS top-k over the fused anchor axis, per class (:128-147) or over
+    anchors x classes (:149-161).  Rows come back in tf.nn.top_k sorted=True order.  Stage entry: rpp_topk."""
+
+    def __init__(self, top_k=100, filter_per_class=True, **kwargs):
+        super(FilterTopKDetections, self).__init__(**kwargs)
+
+        self.top_k = top_k
+        self.filter_per_class = filter_per_class
+        self._handles = {}
+
+    def _handle(self, num_classes):
+        h = self._handles.get(num_classes)
+        if h is None:
+            h = _Handle(num_classes=num_classes, pre_nms_top_k=self.top_k, filter_per_class=self.filter_per_class)
+            self._handles[num_classes] = h
+        return h
+
+    def call(self, predictions):
+        scores = _as_f32(predictions['scores'])
+        boxes = _as_f32(predictions['boxes'])
+        B, n, C = scores.shape
+        if tuple(boxes.shape) != (B, n, 4):
+            raise ValueError('expected boxes [B,n,4], got {}'.format(tuple(boxes.shape)))
+        h = self._handle(C)
+        if self.filter_per_class:
+            k = min(self.top_k, n)
+            out_scores = torch.empty((B, k, C), dtype=torch.float32, device=scores.device)
+            out_boxes = torch.empty((B, k, C, 4), dtype=torch.float32, device=scores.device)
+        else:
+            k = min(self.top_k, n * C)
+            out_scores = torch.empty((B, k, C), dtype=torch.float32, device=scores.device)
+            out_boxes = torch.empty((B, k, 4), dtype=torch.float32, device=scores.device)
+        ws = h.workspace(B, n, scores.device)
+        _native.check(_native.lib().rpp_topk(h.ptr, scores.data_ptr(), boxes.data_ptr(), B, n,
+                                             out_scores.data_ptr(), out_boxes.data_ptr(), None,
+                                             ws.data_ptr(), ws.numel(), _stream()))
+        return {'scores': out_scores, 'boxes': out_boxes}
+
+
+class GenerateDetections(Layer):
+    """postprocessing_ops.py:176-561 — the five NMS modes, non-TPU branches, with the reference's per-mode output
+    dtypes and padding.  Stage entry point: rpp_nms."""
+
+    _SUPPORTED_NMS_MODES = [
+        'CombinedNMS',
+        'GlobalSoftNMS',
+        'GlobalHardNMS',
+        'PerClassSoftNMS',
+        'PerClassHardNMS',
+    ]
+
+    def __init__(self,
+                 iou_threshold=0.5,
+                 score_threshold=0.05,
+                 max_detections=100,
+                 soft_nms_sigma=None,
+                 num_classes=None,
+                 mode='CombinedNMS',
+                 **kwargs):
+
+        if mode not in GenerateDetections._SUPPORTED_NMS_MODES:
+            raise AssertionError(
+                'Requested unsupported mode: {}, available modes are: {}'
+                .format(mode, GenerateDetections._SUPPORTED_NMS_MODES))
+
+        self._running_on_tpu = False
+
+        super(GenerateDetections, self).__init__(**kwargs)
+
+        self.iou_threshold = iou_threshold
+        self.score_threshold = score_threshold
+        self.max_detections = max_detections
+        self.soft_nms_sigma = soft_nms_sigma
+        self.num_classes = num_classes
+        self.mode = mode
+        self._handles = {}
+
+    def _handle(self, num_classes):
+        h = self._handles.get(num_classes)
+        if h is None:
+            if self.mode in ('GlobalSoftNMS', 'PerClassSoftNMS') and self.soft_nms_sigma is None:
+                # the reference evaluates `None / 2` here (:255, :450)
+                raise TypeError("unsupported operand type(s) for /: 'NoneType' and 'int' "
+                                "(soft NMS modes need soft_nms_sigma)")
+            h = _Handle(num_classes=num_classes, mode=self.mode, iou_threshold=self.iou_threshold,
+                        score_threshold=self.score_threshold, soft_nms_sigma=self.soft_nms_sigma or 0.0,
+                        max_detections=self.max_detections)
+            self._handles[num_classes] = h
+        return h
+
+    def call(self, predictions):
+        scores = _as_f32(predictions['scores'])
+        boxes = _as_f32(predictions['boxes'])
+        B, n, C = scores.shape
+        q = 1 if boxes.dim() == 3 else boxes.shape[2]
+        if self.num_classes is not None and self.mode.startswith('PerClass') and self.num_classes != C:
+            raise ValueError('num_classes={} but scores have {} classes'.format(self.num_classes, C))
+        h = self._handle(C)
+        out = h.outputs(B, scores.device)
+        ws = h.workspace(B, n, scores.device)
+        _native.check(_native.lib().rpp_nms(h.ptr, scores.data_ptr(), boxes.data_ptr(), B, n, q,
+                                            out['boxes'].data_ptr(), out['scores'].data_ptr(),
+                                            out['classes'].data_ptr(), out['valid_detections'].data_ptr(),
+                                            ws.data_ptr(), ws.numel(), _stream()))
+        return {
+            'scores': out['scores'],
+            'boxes': out['boxes'],
+            'classes': out['classes'],
+            'valid_detections': out['valid_detections'],
+        }
+
+
+class FusedPostProcessing(Layer):
+    """TransformBoxesAndScores -> FilterTopKDetections -> GenerateDetections as ONE call (rpp_detect): the chain
+    ModelBuilder.add_post_processing_stage wires (model/builder.py:162-181), without the [B,N,C] score tensor, the
+    transposes or the [B,k,C,4] gather ever reaching HBM.  Input: {'class_logits', 'encoded_boxes'}."""
+
+    def __init__(self, params, **kwargs):
+        super(FusedPostProcessing, self).__init__(**kwargs)
+        inf = params.inference
+        if inf.mode not in GenerateDetections._SUPPORTED_NMS_MODES:
+            raise AssertionError(
+                'Requested unsupported mode: {}, available modes are: {}'
+                .format(inf.mode, GenerateDetections._SUPPORTED_NMS_MODES))
+        self._params = params
+        self.mode = inf.mode
+        self._handles = {}
+
+    def handle(self, num_classes):
+        h = self._handles.get(num_classes)
+        if h is None:
+            p = self._params
+            inf = p.inference
+            if self.mode in ('GlobalSoftNMS', 'PerClassSoftNMS') and inf.soft_nms_sigma is None:
+                raise TypeError("unsupported operand type(s) for /: 'NoneType' and 'int' "
+                                "(soft NMS modes need soft_nms_sigma)")
+            h = _Handle(H=p.input.input_shape[0], W=p.input.input_shape[1],
+                        min_level=p.architecture.feature_fusion.min_level,
+                        max_level=p.architecture.feature_fusion.max_level,
+                        num_classes=num_classes, anchor_params=p.anchor_params,
+                        box_variance=p.encoder_params.box_variance,
+                        scale_box_targets=p.encoder_params.scale_box_targets,
+                        mode=inf.mode, iou_threshold=inf.iou_threshold, score_threshold=inf.score_threshold,
+                        soft_nms_sigma=inf.soft_nms_sigma or 0.0, pre_nms_top_k=inf.pre_nms_top_k,
+                        filter_per_class=inf.filter_per_class, max_detections=inf.max_detections)
+            self._handles[num_classes] = h
+        return h
+
+    def call(self, predictions):
+        class_logits = _as_f32(predictions['class_logits'])
+        encoded_boxes = _as_f32(predictions['encoded_boxes'])
+        B, N, C = class_logits.shape
+        h = self.handle(C)
+        if N != h.num_anchors or tuple(encoded_boxes.shape) != (B, N, 4):
+            raise ValueError('expected class_logits [B,{0},C] and encoded_boxes [B,{0},4], got {1} and {2}'.format(
+                h.num_anchors, tuple(class_logits.shape), tuple(encoded_boxes.shape)))
+        out = h.outputs(B, class_logits.device)
+        ws = h.workspace(B, N, class_logits.device)
+        _native.check(_native.lib().rpp_detect(h.ptr, encoded_boxes.data_ptr(), class_logits.data_ptr(), B,
+                                               out['boxes'].data_ptr(), out['scores'].data_ptr(),
+                                               out['classes'].data_ptr(), out['valid_detections'].data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream()))
+        return {
+            'scores': out['scores'],
+            'boxes': out['boxes'],
+            'classes': out['classes'],
+            'valid_detections': out['valid_detections'],
+        }
