@@ -128,6 +128,13 @@ int rpp_classes_itemsize(void* handle);
  * selection (1), or restore the default sampled pre-threshold (0). */
 int rpp_debug_force_exact_scan(void* handle, int on);
 
+/* Per-stage device timing for bench.py's roofline: when on, every rpp_detect / rpp_nms call records CUDA events on
+ * the caller's stream at the stage boundaries.  rpp_debug_stage_ms synchronises on the last event and returns the
+ * mean milliseconds of the 4 stages {pre-threshold sample, collect stream, NMS problems, merge} over the calls
+ * recorded since the last read. */
+int rpp_debug_stage_timing(void* handle, int on);
+int rpp_debug_stage_ms(void* handle, float* h_ms4, int* n_calls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,7 +55,37 @@ struct Handle {
   int sm_count;
   int force_scan;
   DecodeParams dp;
+  // optional per-stage timing (bench.py roofline): 5 events per call = boundaries of sample|collect|nms|merge
+  int timing;
+  std::vector<cudaEvent_t> events;
+  int timed_calls;
+  // rpp_detect_host staging (allocated on first use)
+  struct HostPath {
+    int chunk = 0, B_out = 0;
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    float* d_logits[2] = {nullptr, nullptr};
+    float* d_deltas[2] = {nullptr, nullptr};
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    float* d_boxes = nullptr; float* d_scores = nullptr; void* d_classes = nullptr; int* d_valid = nullptr;
+  } hp;
 };
+
+const int kStages = 4;
+const int kMaxTimedCalls = 512;
+
+inline void stage_mark(Handle* h, int boundary, cudaStream_t st) {
+  if (!h->timing || h->timed_calls >= kMaxTimedCalls) return;
+  const size_t idx = (size_t)h->timed_calls * (kStages + 1) + boundary;
+  while (h->events.size() <= idx) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    h->events.push_back(e);
+  }
+  cudaEventRecord(h->events[idx], st);
+  if (boundary == kStages) ++h->timed_calls;
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -119,6 +149,7 @@ int launch_collect(Handle* h, const float* x, const Workspace& w, const SamplePl
                    float T_min, cudaStream_t st) {
   const size_t P = (size_t)B * C;
   CUDA_OK(cudaMemsetAsync(w.cand_count, 0, P * sizeof(u32), st));
+  stage_mark(h, 0, st);
   if (plan.on && !h->force_scan) {
     int threads = (1024 / C) * C;
     if (threads > 960) threads = (960 / C) * C;
@@ -131,6 +162,7 @@ int launch_collect(Handle* h, const float* x, const Workspace& w, const SamplePl
     fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.T, P, T_min);
     LAUNCHED();
   }
+  stage_mark(h, 1, st);
   if (h->force_scan) return RPP_OK;
   if (C % 4 == 0 && ((uintptr_t)x % 16) == 0 && C / 4 <= 512) {
     const int C4 = C / 4;
@@ -170,6 +202,7 @@ int run_per_class(Handle* h, const float* x, int is_logit, const float4* deltas,
   const float T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
   int rc = launch_collect(h, x, w, plan, B, n, C, T_min, st);
   if (rc) return rc;
+  stage_mark(h, 2, st);
 
   if (c.mode == RPP_PER_CLASS_SOFT_NMS) return fail(RPP_EINVAL, "PerClassSoftNMS: not implemented yet");
   ColProblemParams pp{};
@@ -188,6 +221,7 @@ int run_per_class(Handle* h, const float* x, int is_logit, const float4* deltas,
   const size_t smem = nms_shared_bytes(pp.M_lim);
   col_hard_nms_kernel<<<(unsigned)P, RPP_NMS_NT, smem, st>>>(pp);
   LAUNCHED();
+  stage_mark(h, 3, st);
 
   MergeParams mp{};
   mp.C = C; mp.M = M; mp.combined = c.mode == RPP_COMBINED_NMS;
@@ -198,10 +232,15 @@ int run_per_class(Handle* h, const float* x, int is_logit, const float4* deltas,
   mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_classes = out_classes; mp.out_valid = out_valid;
   merge_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mp);
   LAUNCHED();
+  stage_mark(h, 4, st);
   return RPP_OK;
 }
 
 }  // namespace
+
+namespace {
+void host_path_free(Handle* h);
+}
 
 extern "C" {
 
@@ -245,6 +284,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   h->levels = levels;
   h->device = dev;
   h->force_scan = 0;
+  h->timing = 0;
+  h->timed_calls = 0;
   CUDA_OK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
 
   AnchorParams& ap = h->ap;
@@ -299,6 +340,8 @@ int rpp_destroy(void* handle) {
   Handle* h = (Handle*)handle;
   if (!h) return RPP_OK;
   cudaFree(h->d_anchors);
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  host_path_free(h);
   delete h;
   return RPP_OK;
 }
@@ -319,6 +362,33 @@ int rpp_classes_itemsize(void* handle) {
 int rpp_debug_force_exact_scan(void* handle, int on) {
   if (!handle) return fail(RPP_EINVAL, "null handle");
   ((Handle*)handle)->force_scan = on ? 1 : 0;
+  return RPP_OK;
+}
+
+int rpp_debug_stage_timing(void* handle, int on) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(RPP_EINVAL, "null handle");
+  h->timing = on ? 1 : 0;
+  h->timed_calls = 0;
+  return RPP_OK;
+}
+
+int rpp_debug_stage_ms(void* handle, float* h_ms, int* n_calls) {
+  Handle* h = (Handle*)handle;
+  if (!h || !h_ms) return fail(RPP_EINVAL, "null argument");
+  for (int s = 0; s < kStages; ++s) h_ms[s] = 0.f;
+  const int n = h->timed_calls;
+  if (n_calls) *n_calls = n;
+  if (n == 0) return RPP_OK;
+  CUDA_OK(cudaEventSynchronize(h->events[(size_t)(n - 1) * (kStages + 1) + kStages]));
+  for (int c = 0; c < n; ++c)
+    for (int s = 0; s < kStages; ++s) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, h->events[(size_t)c * (kStages + 1) + s],
+                                   h->events[(size_t)c * (kStages + 1) + s + 1]));
+      h_ms[s] += ms / n;
+    }
+  h->timed_calls = 0;
   return RPP_OK;
 }
 
@@ -391,10 +461,9 @@ int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, lo
                        d_scores_out, d_classes_out, d_valid_out, ws, ws_bytes, (cudaStream_t)stream);
 }
 
-int rpp_detect(void* handle, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,
-               float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes, void* stream) {
-  Handle* h = (Handle*)handle;
-  g_launches = 0;
+static int detect_impl(Handle* h, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,
+                       float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes,
+                       void* stream) {
   if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
   const rpp_config& c = h->cfg;
   const bool filtered = c.pre_nms_top_k > 0;
@@ -413,11 +482,89 @@ int rpp_detect(void* handle, const float* d_deltas, const float* d_logits, int B
   return fail(RPP_EINVAL, "Global* modes: not implemented yet");
 }
 
+int rpp_detect(void* handle, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,
+               float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes, void* stream) {
+  g_launches = 0;
+  return detect_impl((Handle*)handle, d_deltas, d_logits, B, d_boxes_out, d_scores_out, d_classes_out, d_valid_out,
+                     ws, ws_bytes, stream);
+}
+
+}  // extern "C"
+
+namespace {
+void host_path_free(Handle* h) {
+  Handle::HostPath& hp = h->hp;
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(hp.d_logits[i]); cudaFree(hp.d_deltas[i]);
+    if (hp.ready[i]) cudaEventDestroy(hp.ready[i]);
+    if (hp.done[i]) cudaEventDestroy(hp.done[i]);
+  }
+  cudaFree(hp.ws); cudaFree(hp.d_boxes); cudaFree(hp.d_scores); cudaFree(hp.d_classes); cudaFree(hp.d_valid);
+  if (hp.s_copy) cudaStreamDestroy(hp.s_copy);
+  if (hp.s_comp) cudaStreamDestroy(hp.s_comp);
+  hp = Handle::HostPath();
+}
+}  // namespace
+
+extern "C" {
+
 int rpp_detect_host(void* handle, int device, const float* h_deltas, const float* h_logits, int B, float* h_boxes,
                     float* h_scores, void* h_classes, int* h_valid) {
-  (void)handle; (void)device; (void)h_deltas; (void)h_logits; (void)B; (void)h_boxes; (void)h_scores;
-  (void)h_classes; (void)h_valid;
-  return fail(RPP_EINVAL, "rpp_detect_host: not implemented yet");
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !h_deltas || !h_logits || !h_boxes || !h_scores || !h_classes || !h_valid || B <= 0)
+    return fail(RPP_EINVAL, "bad argument");
+  CUDA_OK(cudaSetDevice(device));
+  Handle::HostPath& hp = h->hp;
+  const int C = h->cfg.num_classes, M = h->cfg.max_detections;
+  const size_t lg_img = (size_t)h->N * C * sizeof(float), dl_img = (size_t)h->N * 4 * sizeof(float);
+  // chunk: ~256 MB of logits per staging buffer, at least one image
+  int chunk = (int)std::max<size_t>(1, (256u << 20) / lg_img);
+  if (chunk > B) chunk = B;
+  const int csz = rpp_classes_itemsize(h);
+  if (hp.chunk < chunk || hp.B_out < B) {
+    host_path_free(h);
+    CUDA_OK(cudaStreamCreateWithFlags(&hp.s_copy, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&hp.s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(cudaEventCreateWithFlags(&hp.ready[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+      CUDA_OK(cudaMalloc(&hp.d_logits[i], lg_img * chunk));
+      CUDA_OK(cudaMalloc(&hp.d_deltas[i], dl_img * chunk));
+    }
+    hp.ws_bytes = rpp_workspace_bytes(h, chunk, 0);
+    CUDA_OK(cudaMalloc(&hp.ws, hp.ws_bytes));
+    CUDA_OK(cudaMalloc(&hp.d_boxes, (size_t)B * M * 4 * sizeof(float)));
+    CUDA_OK(cudaMalloc(&hp.d_scores, (size_t)B * M * sizeof(float)));
+    CUDA_OK(cudaMalloc(&hp.d_classes, (size_t)B * M * csz));
+    CUDA_OK(cudaMalloc(&hp.d_valid, (size_t)B * sizeof(int)));
+    hp.chunk = chunk;
+    hp.B_out = B;
+  }
+  chunk = hp.chunk < B ? hp.chunk : B;
+  int i = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++i) {
+    const int bc = B - b0 < chunk ? B - b0 : chunk;
+    const int buf = i & 1;
+    if (i >= 2) CUDA_OK(cudaStreamWaitEvent(hp.s_copy, hp.done[buf], 0));
+    CUDA_OK(cudaMemcpyAsync(hp.d_logits[buf], (const char*)h_logits + lg_img * b0, lg_img * bc,
+                            cudaMemcpyHostToDevice, hp.s_copy));
+    CUDA_OK(cudaMemcpyAsync(hp.d_deltas[buf], (const char*)h_deltas + dl_img * b0, dl_img * bc,
+                            cudaMemcpyHostToDevice, hp.s_copy));
+    CUDA_OK(cudaEventRecord(hp.ready[buf], hp.s_copy));
+    CUDA_OK(cudaStreamWaitEvent(hp.s_comp, hp.ready[buf], 0));
+    int rc = detect_impl(h, hp.d_deltas[buf], hp.d_logits[buf], bc, hp.d_boxes + (size_t)b0 * M * 4,
+                         hp.d_scores + (size_t)b0 * M, (char*)hp.d_classes + (size_t)b0 * M * csz, hp.d_valid + b0,
+                         hp.ws, hp.ws_bytes, hp.s_comp);
+    if (rc) return rc;
+    CUDA_OK(cudaEventRecord(hp.done[buf], hp.s_comp));
+  }
+  CUDA_OK(cudaMemcpyAsync(h_boxes, hp.d_boxes, (size_t)B * M * 4 * sizeof(float), cudaMemcpyDeviceToHost, hp.s_comp));
+  CUDA_OK(cudaMemcpyAsync(h_scores, hp.d_scores, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToHost, hp.s_comp));
+  CUDA_OK(cudaMemcpyAsync(h_classes, hp.d_classes, (size_t)B * M * csz, cudaMemcpyDeviceToHost, hp.s_comp));
+  CUDA_OK(cudaMemcpyAsync(h_valid, hp.d_valid, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, hp.s_comp));
+  CUDA_OK(cudaStreamSynchronize(hp.s_comp));
+  return RPP_OK;
 }
 
 }  // extern "C"
