@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -39,7 +40,7 @@ int fail(int code, const char* fmt, ...) {
 
 struct SamplePlan {
   bool on;
-  int stride, G, rows_per_group, rank;
+  int stride, G, lanes, rows_per_group, rank;
   int CAP;
 };
 
@@ -54,6 +55,7 @@ struct Handle {
   int device;
   int sm_count;
   int force_scan;
+  int collect_variant;   // tuning knob (env RPP_COLLECT_VARIANT): 0 = unroll 4 / 3 CTAs per SM, 1 = 4/2, 2 = 8/2
   DecodeParams dp;
   // optional per-stage timing (bench.py roofline): 5 events per call = boundaries of sample|collect|nms|merge
   int timing;
@@ -89,13 +91,16 @@ inline void stage_mark(Handle* h, int boundary, cudaStream_t st) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// target ~1536 candidates per problem, capacity 4096; small columns are collected whole.
-SamplePlan make_plan(long n, int target) {
+// Pre-threshold plan for columns of n rows and C classes: aim at ~`target` candidates per problem with list
+// capacity 4096; small columns are collected whole (no sampling).
+SamplePlan make_plan(long n, int C, int target) {
   SamplePlan s{};
   s.on = false;
   s.CAP = (int)n;
-  if (n < 16384 || n <= 8L * target) return s;
-  const int G = 96;
+  if (n < 16384 || n <= 8L * target || C > 1024) return s;
+  int lanes = 1024 / C;
+  if (lanes > 12) lanes = 12;
+  const int G = lanes * RPP_GPT;
   int S = (int)std::floor(target / (0.916 * G));
   if (S < 1) S = 1;
   const long g = n / ((long)S * G);
@@ -104,18 +109,25 @@ SamplePlan make_plan(long n, int target) {
   int rank = (int)std::floor(q * G);
   if (rank < 2) rank = 2;
   if (rank > G - 3) rank = G - 3;
+  if (G < 8) return s;
   s.on = true;
   s.stride = S;
   s.G = G;
+  s.lanes = lanes;
   s.rows_per_group = (int)g;
   s.rank = rank;
   s.CAP = 4096;
   return s;
 }
 
+const int kTarget = 1024;
+
 struct Workspace {
   float* T;
-  u32* cand_count;
+  u32* cand_count;     // [P], followed by the tile counter and gm: zeroed together by one memset
+  u32* tile_counter;
+  u32* gm;             // [B][G][C] group maxima of the sampling pass
+  size_t zero_bytes;
   int* sel_cnt;
   u64* sel_key;
   float4* sel_box;
@@ -123,7 +135,7 @@ struct Workspace {
   size_t bytes;
 };
 
-Workspace layout_cols(void* base, size_t P, int M, int CAP) {
+Workspace layout_cols(void* base, size_t P, int M, int CAP, size_t gm_elems) {
   Workspace w{};
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -133,6 +145,9 @@ Workspace layout_cols(void* base, size_t P, int M, int CAP) {
   };
   w.T = (float*)take(P * sizeof(float));
   w.cand_count = (u32*)take(P * sizeof(u32));
+  w.tile_counter = (u32*)take(256);
+  w.gm = (u32*)take(gm_elems * sizeof(u32));
+  w.zero_bytes = (size_t)((char*)w.gm - (char*)w.cand_count) + gm_elems * sizeof(u32);
   w.sel_cnt = (int*)take(P * sizeof(int));
   w.sel_key = (u64*)take(P * (size_t)M * sizeof(u64));
   w.sel_box = (float4*)take(P * (size_t)M * sizeof(float4));
@@ -148,15 +163,16 @@ bool is_per_class_mode(int mode) {
 int launch_collect(Handle* h, const float* x, const Workspace& w, const SamplePlan& plan, int B, long n, int C,
                    float T_min, cudaStream_t st) {
   const size_t P = (size_t)B * C;
-  CUDA_OK(cudaMemsetAsync(w.cand_count, 0, P * sizeof(u32), st));
+  CUDA_OK(cudaMemsetAsync(w.cand_count, 0, w.zero_bytes, st));
   stage_mark(h, 0, st);
   if (plan.on && !h->force_scan) {
-    int threads = (1024 / C) * C;
-    if (threads > 960) threads = (960 / C) * C;
-    if (threads < C) return fail(RPP_EINVAL, "num_classes %d too large for the sampling kernel", C);
+    const int threads = (int)align_up((size_t)plan.lanes * C, 32);
+    int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
+    sample_max_kernel<<<dim3(B, split), threads, 0, st>>>(x, n, C, plan.stride, plan.lanes, plan.rows_per_group,
+                                                          w.gm);
+    LAUNCHED();
     const size_t smem = (size_t)plan.G * C * sizeof(u32);
-    sample_threshold_kernel<<<B, threads, smem, st>>>(x, n, C, plan.stride, plan.G, plan.rows_per_group, plan.rank,
-                                                      T_min, w.T);
+    sample_rank_kernel<<<B, 1024, smem, st>>>(w.gm, C, plan.G, plan.rank, T_min, w.T);
     LAUNCHED();
   } else {
     fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.T, P, T_min);
@@ -164,20 +180,28 @@ int launch_collect(Handle* h, const float* x, const Workspace& w, const SamplePl
   }
   stage_mark(h, 1, st);
   if (h->force_scan) return RPP_OK;
-  if (C % 4 == 0 && ((uintptr_t)x % 16) == 0 && C / 4 <= 512) {
+  if (C % 4 == 0 && ((uintptr_t)x % 16) == 0 && C / 4 <= RPP_COLLECT_NT) {
     const int C4 = C / 4;
-    int lanes = 512 / C4;
-    if (lanes < 1) lanes = 1;
-    const int threads = (int)align_up((size_t)lanes * C4, 32);
-    const int UNROLL = 4;
-    const int rows_per_tile = lanes * UNROLL * 2;
+    const int lanes = RPP_COLLECT_NT / C4;
+    const int UNROLL = h->collect_variant == 2 ? 8 : 4;
+    const int MINB = h->collect_variant == 0 ? 3 : 2;
+    // tile: ~10 expected hits per class (stage capacity 32) when the plan aims at kTarget candidates per column
+    long rows_per_tile = plan.on ? (long)(10.0 * n / kTarget) : 4L * lanes * UNROLL;
+    rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
+    if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
     const int tiles_per_image = (int)((n + rows_per_tile - 1) / rows_per_tile);
     const long n_tiles = (long)B * tiles_per_image;
-    long grid = (long)h->sm_count * 4;
+    long grid = (long)h->sm_count * MINB;
     if (grid > n_tiles) grid = n_tiles;
-    collect_cols4_kernel<UNROLL><<<(unsigned)grid, threads, 0, st>>>((const float4*)x, w.T, w.cand_count, w.cand,
-                                                                     plan.CAP, B, n, C4, lanes, rows_per_tile,
-                                                                     tiles_per_image);
+    const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(u32) + 2 * (size_t)C * sizeof(u32);
+#define RPP_LAUNCH_COLLECT(U, MB)                                                                              \
+    collect_cols4_kernel<U, MB><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(                                 \
+        (const float4*)x, w.T, w.cand_count, w.cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,            \
+        tiles_per_image, w.tile_counter)
+    if (h->collect_variant == 0) RPP_LAUNCH_COLLECT(4, 3);
+    else if (h->collect_variant == 1) RPP_LAUNCH_COLLECT(4, 2);
+    else RPP_LAUNCH_COLLECT(8, 2);
+#undef RPP_LAUNCH_COLLECT
     LAUNCHED();
   } else {
     const size_t tot = (size_t)B * n * C;
@@ -196,8 +220,8 @@ int run_per_class(Handle* h, const float* x, int is_logit, const float4* deltas,
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
   const size_t P = (size_t)B * C;
-  const SamplePlan plan = make_plan(n, 1536);
-  Workspace w = layout_cols(ws, P, M, plan.CAP);
+  const SamplePlan plan = make_plan(n, C, kTarget);
+  Workspace w = layout_cols(ws, P, M, plan.CAP, plan.on ? (size_t)B * plan.G * C : 0);
   if (w.bytes > ws_bytes) return fail(RPP_EWORKSPACE, "workspace: need %zu bytes, got %zu", w.bytes, ws_bytes);
   const float T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
   int rc = launch_collect(h, x, w, plan, B, n, C, T_min, st);
@@ -284,6 +308,11 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   h->levels = levels;
   h->device = dev;
   h->force_scan = 0;
+  {
+    const char* v = getenv("RPP_COLLECT_VARIANT");
+    h->collect_variant = v ? atoi(v) : 0;
+    if (h->collect_variant < 0 || h->collect_variant > 2) h->collect_variant = 0;
+  }
   h->timing = 0;
   h->timed_calls = 0;
   CUDA_OK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -331,7 +360,10 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   }
   cudaFuncSetAttribute(col_hard_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols4_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   *handle = h;
   return RPP_OK;
 }
@@ -405,8 +437,9 @@ size_t rpp_workspace_bytes(void* handle, int B, long n) {
   if (!h || B <= 0) return 0;
   if (n <= 0) n = h->N;
   const int C = h->cfg.num_classes;
-  const SamplePlan plan = make_plan(n, 1536);
-  const Workspace w = layout_cols(nullptr, (size_t)B * C, h->cfg.max_detections, plan.CAP);
+  const SamplePlan plan = make_plan(n, C, kTarget);
+  const Workspace w = layout_cols(nullptr, (size_t)B * C, h->cfg.max_detections, plan.CAP,
+                                  plan.on ? (size_t)B * plan.G * C : 0);
   return w.bytes + 4096;
 }
 

@@ -72,37 +72,55 @@ __global__ void decode_kernel(const float4* __restrict__ deltas, const float4* _
 // ===============================================================================================================
 // K1  sample -> per-(image, class) pre-threshold.
 //
-// Candidates for one NMS problem are "the best few thousand of a column of N logits".  A strided sample of the
-// column (every `stride`-th anchor, interleaved into G groups) gives G group maxima; their r-th smallest is an
-// estimate of the logit whose upper tail holds ~target elements.  The estimate only has to be roughly right: the
-// problem kernel consumes candidates lazily and falls back to an exact scan of the column if the list runs dry,
-// so results never depend on it.  One block per image; thread = (class, row lane); loads are row-contiguous.
-//   T[b*C + c] = max(estimate, T_min)   (T_min = exact logit pre-image of the score threshold, or -inf)
+// Candidates for one NMS problem are "the best few hundred of a column of N logits".  A strided sample of the
+// column (every `stride`-th anchor, dealt round-robin into G groups) gives G group maxima; their r-th smallest is
+// an estimate of the logit whose upper tail holds ~target elements.  The estimate only has to be roughly right:
+// the problem kernel consumes candidates lazily and falls back to an exact scan of the column if the list runs
+// dry, so results never depend on it.
+//   K1a  sample_max_kernel   grid (B, SPLIT): thread = (class, row lane) keeps RPP_GPT group maxima in registers
+//                            over its share of the rounds (row-contiguous loads, RPP_GPT independent loads in
+//                            flight), then merges them into gm[b][g][c] with atomicMax.
+//   K1b  sample_rank_kernel  grid B: r-th smallest of the G maxima per class -> T[b*C + c] = max(est, T_min).
 // ===============================================================================================================
-__global__ void sample_threshold_kernel(const float* __restrict__ x /*[B,N,C]*/, long N, int C, int stride, int G,
-                                        int rows_per_group, int rank, float T_min, float* __restrict__ T) {
-  extern __shared__ u32 gm[];  // [G][C] ordered-float group maxima
-  const int b = blockIdx.x;
-  const int lanes = blockDim.x / C;  // row lanes
+#define RPP_GPT 8   // groups per thread; G = lanes * RPP_GPT
+
+__global__ void sample_max_kernel(const float* __restrict__ x /*[B,N,C]*/, long N, int C, int stride, int lanes,
+                                  int rounds, u32* __restrict__ gm /*[B][G][C]*/) {
+  const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
   const int c = threadIdx.x % C, rl = threadIdx.x / C;
-  for (int i = threadIdx.x; i < G * C; i += blockDim.x) gm[i] = 0u;
-  __syncthreads();
-  const long n_s = (long)G * rows_per_group;
-  if (rl < lanes) {
-    const float* base = x + (size_t)b * N * C + c;
-    for (long s = rl; s < n_s; s += lanes) {
-      const float v = __ldg(base + (size_t)(s * stride) * C);
-      atomicMax(&gm[(int)(s % G) * C + c], ord_f32(v));
+  if (rl >= lanes) return;
+  const int G = lanes * RPP_GPT;
+  float m[RPP_GPT];
+#pragma unroll
+  for (int i = 0; i < RPP_GPT; ++i) m[i] = -INFINITY;
+  const float* base = x + (size_t)b * N * C + c;
+  for (int r = split; r < rounds; r += nsplit) {
+    float v[RPP_GPT];
+#pragma unroll
+    for (int i = 0; i < RPP_GPT; ++i) {
+      const long s = (long)r * G + rl + i * lanes;  // sampled row index; group = rl + i * lanes
+      v[i] = __ldg(base + (size_t)(s * stride) * C);
     }
+#pragma unroll
+    for (int i = 0; i < RPP_GPT; ++i) m[i] = fmaxf(m[i], v[i]);
   }
+#pragma unroll
+  for (int i = 0; i < RPP_GPT; ++i)
+    atomicMax(&gm[((size_t)b * G + rl + i * lanes) * C + c], ord_f32(m[i]));
+}
+
+__global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int rank, float T_min,
+                                   float* __restrict__ T) {
+  extern __shared__ u32 s_gm[];  // [G][C]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < G * C; i += blockDim.x) s_gm[i] = gm[(size_t)b * G * C + i];
   __syncthreads();
-  // r-th smallest of the G maxima of each class: rank counting, one (class, element) pair per thread step
   for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
     const int cc = i % C;
-    const u32 v = gm[i];
+    const u32 v = s_gm[i];
     int less = 0, eq = 0;
     for (int g = 0; g < G; ++g) {
-      const u32 o = gm[g * C + cc];
+      const u32 o = s_gm[g * C + cc];
       less += o < v;
       eq += o == v;
     }
@@ -118,8 +136,10 @@ __global__ void fill_kernel(float* p, size_t n, float v) {
 // K2  collect — the HBM-bound stream.  Reads class_logits [B,N,C] exactly once with 128-bit streaming loads and
 // appends every element with logit >= T[b,c] to that problem's candidate list as (logit bits, anchor index).
 // No sigmoid here: the comparison is on raw logits (monotone pre-image of the score), so the kernel issues one
-// LDG.128 and four compares per 16 bytes.  Thread = (class quad, row lane) so its four thresholds live in
-// registers for a whole tile; UNROLL independent loads in flight per thread.
+// LDG.128 and four compares per 16 bytes.  Thread = (class quad, row lane): its four thresholds live in registers
+// for a whole tile and UNROLL independent loads are in flight per thread.  Hits (~1 %) are staged per class in
+// shared memory and flushed once per tile with ONE global atomic per (tile, class); a class that overflows its
+// stage appends directly.  Tiles are handed out dynamically (atomic tile counter) so the tail is balanced.
 // ===============================================================================================================
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;
@@ -133,42 +153,86 @@ __device__ __forceinline__ void append_cand(u32* cand_count, uint2* cand, int CA
   if (slot < (u32)CAP) cand[p * (size_t)CAP + slot] = make_uint2(__float_as_uint(v), idx);
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(1024)
+#define RPP_STAGE_CAP 32
+#define RPP_COLLECT_NT 512
+
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(RPP_COLLECT_NT, MINB)
 collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* __restrict__ T /*[B*C]*/,
                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C4,
-                     int lanes /*row lanes per block*/, int rows_per_tile, int tiles_per_image) {
-  const int cq = threadIdx.x % C4, rl = threadIdx.x / C4;
-  if (rl >= lanes) return;
+                     int lanes /*row lanes per block*/, int rows_per_tile, int tiles_per_image,
+                     u32* __restrict__ tile_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = C4 * 4;
+  u32* s_rows = reinterpret_cast<u32*>(smem_raw);        // [C][RPP_STAGE_CAP] staged row indices
+  u32* s_cnt = s_rows + (size_t)C * RPP_STAGE_CAP;       // [C]
+  u32* s_base = s_cnt + C;                               // [C]
+  __shared__ long s_tile;
+  const int tid = threadIdx.x;
+  const int cq = tid % C4, rl = tid / C4;
+  const bool active = rl < lanes;
   const long n_tiles = (long)B * tiles_per_image;
-  for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const float* x = reinterpret_cast<const float*>(x4);
+  for (;;) {
+    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    __syncthreads();
+    const long tile = s_tile;
+    if (tile >= n_tiles) break;
     const int b = (int)(tile / tiles_per_image);
     const long r0 = (long)(tile % tiles_per_image) * rows_per_tile;
     const long r1 = r0 + rows_per_tile < N ? r0 + rows_per_tile : N;
-    const float4 t4 = __ldg(reinterpret_cast<const float4*>(T + (size_t)b * C) + cq);
-    const float4* src = x4 + (size_t)b * N * C4 + cq;
-    const size_t pbase = (size_t)b * C + cq * 4;
-    for (long row = r0 + rl; row < r1; row += (long)lanes * UNROLL) {
-      float4 v[UNROLL];
+    const size_t pbase = (size_t)b * C;
+    const float* xb = x + (size_t)b * N * C;
+    if (active) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(T + (size_t)b * C) + cq);
+      const float4* src = x4 + (size_t)b * N * C4 + cq;
+      for (long row = r0 + rl; row < r1; row += (long)lanes * UNROLL) {
+        float4 v[UNROLL];
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const long r = row + (long)u * lanes;
-        v[u] = r < r1 ? ld_stream_f4(src + (size_t)r * C4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      }
+        for (int u = 0; u < UNROLL; ++u) {
+          const long r = row + (long)u * lanes;
+          v[u] = r < r1 ? ld_stream_f4(src + (size_t)r * C4)
+                        : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        u32 mask = 0u;  // bit 4u+i: component i of load u passes its class threshold (NaN never passes >=)
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const u32 r = (u32)(row + (long)u * lanes);
-        // NaN never passes >=; a -inf fill never passes a finite threshold and T = -inf only with real rows
-        const bool h0 = v[u].x >= t4.x, h1 = v[u].y >= t4.y, h2 = v[u].z >= t4.z, h3 = v[u].w >= t4.w;
-        if ((h0 | h1 | h2 | h3) && (long)r < r1) {
-          if (h0) append_cand(cand_count, cand, CAP, pbase + 0, v[u].x, r);
-          if (h1) append_cand(cand_count, cand, CAP, pbase + 1, v[u].y, r);
-          if (h2) append_cand(cand_count, cand, CAP, pbase + 2, v[u].z, r);
-          if (h3) append_cand(cand_count, cand, CAP, pbase + 3, v[u].w, r);
+        for (int u = 0; u < UNROLL; ++u) {
+          u32 m = (v[u].x >= t4.x ? 1u : 0u) | (v[u].y >= t4.y ? 2u : 0u) | (v[u].z >= t4.z ? 4u : 0u) |
+                  (v[u].w >= t4.w ? 8u : 0u);
+          if (row + (long)u * lanes >= r1) m = 0u;
+          mask |= m << (4 * u);
+        }
+        // rare path (~1 % of elements): stage the ROW INDEX only; the value is re-read from L2 at the flush
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const int c = cq * 4 + (bit & 3);
+          const u32 r = (u32)(row + (long)(bit >> 2) * lanes);
+          const u32 slot = atomicAdd(&s_cnt[c], 1u);
+          if (slot < RPP_STAGE_CAP) s_rows[c * RPP_STAGE_CAP + slot] = r;
+          else append_cand(cand_count, cand, CAP, pbase + c, __ldg(xb + (size_t)r * C + c), r);
         }
       }
     }
+    __syncthreads();
+    // flush: one global atomic per class that staged anything
+    for (int c = tid; c < C; c += RPP_COLLECT_NT) {
+      const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+      s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+    }
+    __syncthreads();
+    for (int e = tid; e < C * RPP_STAGE_CAP; e += RPP_COLLECT_NT) {
+      const int c = e / RPP_STAGE_CAP, r = e - c * RPP_STAGE_CAP;
+      const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+      if ((u32)r < n) {
+        const u32 slot = s_base[c] + (u32)r;
+        const u32 rowi = s_rows[e];
+        if (slot < (u32)CAP)
+          cand[(pbase + c) * (size_t)CAP + slot] = make_uint2(__float_as_uint(__ldg(xb + (size_t)rowi * C + c)), rowi);
+      }
+    }
+    __syncthreads();
   }
 }
 
