@@ -256,8 +256,9 @@ __global__ void collect_cols1_kernel(const float* __restrict__ x, const float* _
 //     (CombinedNMS per-class stage;  PerClassHardNMS = NonMaxSuppressionV5 hard, A.2).
 // ===============================================================================================================
 #define RPP_NMS_NT 128
-#define RPP_CHUNK_CAP 1024
-#define RPP_LIST_SMEM 2048
+#define RPP_CHUNK_CAP 1024   // merge kernel
+#define RPP_NMS_CHUNK 512
+#define RPP_LIST_SMEM 1536
 
 struct ColProblemParams {
   // source: columns of a [B, N, C] tensor
@@ -292,7 +293,7 @@ struct ColProblemParams {
 
 struct NmsShared {
   SelectScratch<RPP_NMS_NT> sel;
-  u64 chunk[RPP_CHUNK_CAP];
+  u64 chunk[RPP_NMS_CHUNK];
   u64 lkeys[RPP_LIST_SMEM];
   float4 cbox[RPP_NMS_NT];   // canonical boxes of the current group
   float carea[RPP_NMS_NT];
@@ -319,63 +320,93 @@ __device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int 
   return decode_box(P.deltas[(size_t)b * P.N + row], P.anchors[row], P.dp);
 }
 
-// Greedy hard NMS over one sorted chunk.  Returns with sh->done set when M_lim kept or k_lim consumed.
+// Greedy hard NMS over one sorted chunk (m keys in sh->chunk).  The chunk is walked in groups of RPP_NMS_NT
+// candidates (thread t owns candidate t: its box stays in registers) and each group in tiles of 32 = one warp:
+//   (a) every unresolved candidate tests itself against the boxes kept since its last test (all warps busy);
+//   (b) the tile's warp builds the 32x32 suppression mask among its still-alive candidates and resolves the
+//       greedy order with a register bit-chain (no IoU on the serial path);
+//   (c) the newly kept boxes are appended to the kept list; later tiles see them in their next (a).
+// Equivalent to NonMaxSuppressionV5's hard branch / CombinedNMS's per-class loop: a candidate is kept iff no
+// earlier kept box overlaps it by more than the threshold (the reverse-order early break of A.2 does not change
+// the outcome).  Sets sh->done when M_lim are kept or k_lim candidates were consumed.
+__device__ __forceinline__ bool iou_gt(float4 a, float area_a, float4 b, float area_b, float thr) {
+  // degenerate boxes are stored as the empty box (inf, inf, -inf, -inf) with area 0: inter == 0 below (A.1)
+  const float h0 = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float h1 = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  const float inter = __fmul_rn(h0, h1);
+  float iou = 0.0f;
+  if (inter > 0.0f) iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return iou > thr;
+}
+
 __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b, int c, size_t p, int m,
                                  long& consumed) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* kbox = nms_kbox(sh);
   float* karea = nms_karea(sh, P.M_lim);
-  long room = P.k_lim - consumed;
-  int m_eff = (long)m < room ? m : (int)room;
+  const long room = P.k_lim - consumed;
+  const int m_eff = (long)m < room ? m : (int)room;
+  const float thr = P.iou_threshold;
   for (int g0 = 0; g0 < m_eff; g0 += RPP_NMS_NT) {
-    const int j = g0 + tid;
-    if (j < m_eff) {
-      float4 bx = col_box(P, b, c, key_tie(sh->chunk[j]));
-      if (P.clip_before) bx = clip01(bx);
-      float area;
-      sh->corig[tid] = bx;
-      sh->cbox[tid] = canon_box(bx, area);
+    const int gcount = m_eff - g0 < RPP_NMS_NT ? m_eff - g0 : RPP_NMS_NT;
+    bool alive = tid < gcount;
+    float4 bx = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    float area = 0.0f;
+    if (alive) {
+      float4 orig = col_box(P, b, c, key_tie(sh->chunk[g0 + tid]));
+      if (P.clip_before) orig = clip01(orig);
+      sh->corig[tid] = orig;
+      const float4 cb = canon_box(orig, area);
+      if (area > 0.0f) bx = cb; else area = 0.0f;
+      sh->cbox[tid] = bx;
       sh->carea[tid] = area;
     }
     __syncthreads();
-    if (warp == 0) {
-      int nk = sh->nkept;
-      const int gcount = m_eff - g0 < RPP_NMS_NT ? m_eff - g0 : RPP_NMS_NT;
-      bool done = false;
-      for (int t0 = 0; t0 < gcount && !done; t0 += 32) {
-        const int ci = t0 + lane;
-        bool alive = ci < gcount;
-        const float4 bx = sh->cbox[ci < RPP_NMS_NT ? ci : 0];
-        const float area = sh->carea[ci < RPP_NMS_NT ? ci : 0];
-        for (int t = 0; t < nk; ++t) {
-          if (alive && iou_canon(bx, area, kbox[t], karea[t]) > P.iou_threshold) alive = false;
-          if (!__any_sync(RPP_FULL_MASK, alive)) break;
-        }
-        u32 rem = __ballot_sync(RPP_FULL_MASK, alive);
-        while (rem) {
-          const int f = __ffs(rem) - 1;
-          const float4 fb = make_float4(__shfl_sync(RPP_FULL_MASK, bx.x, f), __shfl_sync(RPP_FULL_MASK, bx.y, f),
-                                        __shfl_sync(RPP_FULL_MASK, bx.z, f), __shfl_sync(RPP_FULL_MASK, bx.w, f));
-          const float fa = __shfl_sync(RPP_FULL_MASK, area, f);
-          if (lane == f) {
-            kbox[nk] = bx;
-            karea[nk] = area;
-            P.sel_key[p * P.M + nk] = sh->chunk[g0 + ci];
-            P.sel_box[p * P.M + nk] = sh->corig[ci];
-          }
-          ++nk;
-          if (nk >= P.M_lim) { done = true; break; }
-          if (alive && lane > f && iou_canon(bx, area, fb, fa) > P.iou_threshold) alive = false;
-          rem = __ballot_sync(RPP_FULL_MASK, alive) & ~((2u << f) - 1u);
-        }
-        __syncwarp();
+    int tested = 0;
+    const int ntiles = (gcount + 31) >> 5;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int nk = sh->nkept;
+      if (alive && warp >= tile) {
+        for (int k = tested; k < nk; ++k)
+          if (iou_gt(bx, area, kbox[k], karea[k], thr)) { alive = false; break; }
       }
-      if (lane == 0) {
-        sh->nkept = nk;
-        if (done) sh->done = 1;
+      tested = nk;
+      if (warp == tile) {
+        const u32 cand_bits = __ballot_sync(RPP_FULL_MASK, alive);
+        u32 row = 0u;  // bit j: alive candidate j < lane of this tile overlaps me
+        for (int j = 0; j < 31; ++j) {
+          if (!((cand_bits >> j) & 1u)) continue;  // uniform
+          const float4 ob = sh->cbox[tile * 32 + j];
+          const float oa = sh->carea[tile * 32 + j];
+          if (alive && j < lane && iou_gt(bx, area, ob, oa, thr)) row |= 1u << j;
+        }
+        u32 kept_bits = 0u;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+          const u32 r = __shfl_sync(RPP_FULL_MASK, row, l);
+          if (((cand_bits >> l) & 1u) && (r & kept_bits) == 0u) kept_bits |= 1u << l;
+        }
+        int nnew = __popc(kept_bits);
+        const int room_k = P.M_lim - nk;
+        while (nnew > room_k) {  // keep only the first room_k
+          kept_bits &= ~(1u << (31 - __clz(kept_bits)));
+          --nnew;
+        }
+        if ((kept_bits >> lane) & 1u) {
+          const int pos = nk + __popc(kept_bits & ((1u << lane) - 1u));
+          kbox[pos] = bx;
+          karea[pos] = area;
+          P.sel_key[p * P.M + pos] = sh->chunk[g0 + tid];
+          P.sel_box[p * P.M + pos] = sh->corig[tid];
+        }
+        if (lane == 0) {
+          sh->nkept = nk + nnew;
+          if (nk + nnew >= P.M_lim) sh->done = 1;
+        }
       }
+      __syncthreads();
+      if (sh->done) break;
     }
-    __syncthreads();
     if (sh->done) break;
   }
   consumed += m_eff;
@@ -422,10 +453,10 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_hard_nms_kernel(ColProblemPara
     int want = 256;
     while (!sh->done) {
       const int m = select_chunk<RPP_NMS_NT>([&](int i) { return keys[i]; }, n_list, KB, want, sh->chunk,
-                                             RPP_CHUNK_CAP, &sh->sel);
+                                             RPP_NMS_CHUNK, &sh->sel);
       if (m == 0) break;
       hard_nms_consume(P, sh, b, c, p, m, consumed);
-      want = RPP_CHUNK_CAP;
+      want = RPP_NMS_CHUNK;
     }
   }
   // ---- phase B: exact scan of the column for everything at or below the edge ---------------------------------
@@ -440,10 +471,10 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_hard_nms_kernel(ColProblemPara
     };
     int want = 256;
     while (!sh->done) {
-      const int m = select_chunk<RPP_NMS_NT>(keyfn, (int)P.N, KB, want, sh->chunk, RPP_CHUNK_CAP, &sh->sel);
+      const int m = select_chunk<RPP_NMS_NT>(keyfn, (int)P.N, KB, want, sh->chunk, RPP_NMS_CHUNK, &sh->sel);
       if (m == 0) break;
       hard_nms_consume(P, sh, b, c, p, m, consumed);
-      want = RPP_CHUNK_CAP;
+      want = RPP_NMS_CHUNK;
     }
   }
   if (tid == 0) P.sel_cnt[p] = sh->nkept;
