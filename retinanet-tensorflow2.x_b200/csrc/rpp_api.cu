@@ -1,5 +1,6 @@
 // rpp_api.cu — C ABI of libretinapost.so (include/retinapost.h): handle, workspace layout and kernel launches.
 // Host logic only; every result is computed by the kernels in rpp_kernels.cuh.  There is no CPU compute path.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -122,142 +123,343 @@ SamplePlan make_plan(long n, int C, int target) {
 
 const int kTarget = 1024;
 
-struct Workspace {
-  float* T;
-  u32* cand_count;     // [P], followed by the tile counter and gm: zeroed together by one memset
-  u32* tile_counter;
-  u32* gm;             // [B][G][C] group maxima of the sampling pass
-  size_t zero_bytes;
-  int* sel_cnt;
-  u64* sel_key;
-  float4* sel_box;
-  uint2* cand;
-  size_t bytes;
+// Bump allocator over the caller's workspace.  Every pipeline below is written once and run twice: a dry pass
+// (no launches) sizes the workspace — rpp_workspace_bytes and the capacity check share it — then the real pass.
+struct Arena {
+  char* base;
+  size_t off;
+  bool dry;
+  template <class T> T* take(size_t count) {
+    const size_t o = off;
+    off = align_up(off + count * sizeof(T), 256);
+    return dry ? nullptr : reinterpret_cast<T*>(base + o);
+  }
 };
-
-Workspace layout_cols(void* base, size_t P, int M, int CAP, size_t gm_elems) {
-  Workspace w{};
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    size_t o = off;
-    off = align_up(off + bytes, 256);
-    return base ? (char*)base + o : (char*)nullptr;
-  };
-  w.T = (float*)take(P * sizeof(float));
-  w.cand_count = (u32*)take(P * sizeof(u32));
-  w.tile_counter = (u32*)take(256);
-  w.gm = (u32*)take(gm_elems * sizeof(u32));
-  w.zero_bytes = (size_t)((char*)w.gm - (char*)w.cand_count) + gm_elems * sizeof(u32);
-  w.sel_cnt = (int*)take(P * sizeof(int));
-  w.sel_key = (u64*)take(P * (size_t)M * sizeof(u64));
-  w.sel_box = (float4*)take(P * (size_t)M * sizeof(float4));
-  w.cand = (uint2*)take(P * (size_t)CAP * sizeof(uint2));
-  w.bytes = off;
-  return w;
-}
 
 bool is_per_class_mode(int mode) {
   return mode == RPP_COMBINED_NMS || mode == RPP_PER_CLASS_HARD_NMS || mode == RPP_PER_CLASS_SOFT_NMS;
 }
 
-int launch_collect(Handle* h, const float* x, const Workspace& w, const SamplePlan& plan, int B, long n, int C,
-                   float T_min, cudaStream_t st) {
+// One set of P = B * C "column problems": columns of x [B, n, C] -> lazily sorted candidates -> consumer.
+struct ProblemSet {
+  // in
+  const float* x; int is_logit; int B; long n; int C;
+  const float4* deltas; const float4* boxes; int q;
+  int consumer;            // RPP_CONSUME_*
+  long k_lim; int M_lim; int M;
+  int clip_before; float iou_threshold; float score_threshold; float T_min;
+  float soft_sigma_tf; int tie_is_rank;
+  // out (workspace)
+  u64* sel_key; float4* sel_box; int* sel_cnt; u64* emit_key;
+};
+
+int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st) {
+  const int B = ps.B, C = ps.C;
+  const long n = ps.n;
   const size_t P = (size_t)B * C;
-  CUDA_OK(cudaMemsetAsync(w.cand_count, 0, w.zero_bytes, st));
+  const bool emit = ps.consumer == RPP_CONSUME_EMIT;
+  const int target = emit ? (int)std::min<long>(ps.k_lim + std::max<long>(256, ps.k_lim / 8), 1 << 30) : kTarget;
+  SamplePlan plan = make_plan(n, C, target);
+  if (plan.on && emit) plan.CAP = 2 * target;
+  const size_t gm_elems = plan.on ? (size_t)B * plan.G * C : 0;
+
+  float* T = ar.take<float>(P);
+  u32* cand_count = ar.take<u32>(P);
+  u32* tile_counter = ar.take<u32>(64);
+  u32* gm = ar.take<u32>(gm_elems);
+  const size_t zero_bytes = ar.dry ? 0 : (size_t)((char*)gm - (char*)cand_count) + gm_elems * sizeof(u32);
+  uint2* cand = ar.take<uint2>(P * (size_t)plan.CAP);
+  ps.sel_cnt = nullptr; ps.sel_key = nullptr; ps.sel_box = nullptr; ps.emit_key = nullptr;
+  u64* r_key = nullptr; uint2* r_meta = nullptr; float4* r_box = nullptr;
+  long r_cap = 0;
+  if (emit) {
+    ps.emit_key = ar.take<u64>(P * (size_t)ps.k_lim);
+  } else {
+    ps.sel_cnt = ar.take<int>(P);
+    ps.sel_key = ar.take<u64>(P * (size_t)ps.M);
+    ps.sel_box = ar.take<float4>(P * (size_t)ps.M);
+    if (ps.consumer == RPP_CONSUME_SOFT) {
+      r_cap = std::max<long>(0, std::min<long>(ps.k_lim, n) - RPP_SOFT_RS) + 1;
+      r_key = ar.take<u64>(P * (size_t)r_cap);
+      r_meta = ar.take<uint2>(P * (size_t)r_cap);
+      r_box = ar.take<float4>(P * (size_t)r_cap);
+    }
+  }
+  if (ar.dry) return RPP_OK;
+
+  // ---- stage 0/1: thresholds ---------------------------------------------------------------------------------
+  CUDA_OK(cudaMemsetAsync(cand_count, 0, zero_bytes, st));
   stage_mark(h, 0, st);
   if (plan.on && !h->force_scan) {
     const int threads = (int)align_up((size_t)plan.lanes * C, 32);
-    int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
-    sample_max_kernel<<<dim3(B, split), threads, 0, st>>>(x, n, C, plan.stride, plan.lanes, plan.rows_per_group,
-                                                          w.gm);
+    const int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
+    sample_max_kernel<<<dim3(B, split), threads, 0, st>>>(ps.x, n, C, plan.stride, plan.lanes, plan.rows_per_group, gm);
     LAUNCHED();
     const size_t smem = (size_t)plan.G * C * sizeof(u32);
-    sample_rank_kernel<<<B, 1024, smem, st>>>(w.gm, C, plan.G, plan.rank, T_min, w.T);
+    sample_rank_kernel<<<B, 1024, smem, st>>>(gm, C, plan.G, plan.rank, ps.T_min, T);
     LAUNCHED();
   } else {
-    fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(w.T, P, T_min);
+    fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(T, P, ps.T_min);
     LAUNCHED();
   }
   stage_mark(h, 1, st);
-  if (h->force_scan) return RPP_OK;
-  if (C % 4 == 0 && ((uintptr_t)x % 16) == 0 && C / 4 <= RPP_COLLECT_NT) {
-    const int C4 = C / 4;
-    const int lanes = RPP_COLLECT_NT / C4;
-    const int UNROLL = h->collect_variant == 2 ? 8 : 4;
-    const int MINB = h->collect_variant == 0 ? 3 : 2;
-    // tile: ~10 expected hits per class (stage capacity 32) when the plan aims at kTarget candidates per column
-    long rows_per_tile = plan.on ? (long)(10.0 * n / kTarget) : 4L * lanes * UNROLL;
-    rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
-    if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
-    const int tiles_per_image = (int)((n + rows_per_tile - 1) / rows_per_tile);
-    const long n_tiles = (long)B * tiles_per_image;
-    long grid = (long)h->sm_count * MINB;
-    if (grid > n_tiles) grid = n_tiles;
-    const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(u32) + 2 * (size_t)C * sizeof(u32);
-#define RPP_LAUNCH_COLLECT(U, MB)                                                                              \
-    collect_cols4_kernel<U, MB><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(                                 \
-        (const float4*)x, w.T, w.cand_count, w.cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,            \
-        tiles_per_image, w.tile_counter)
-    if (h->collect_variant == 0) RPP_LAUNCH_COLLECT(4, 3);
-    else if (h->collect_variant == 1) RPP_LAUNCH_COLLECT(4, 2);
-    else RPP_LAUNCH_COLLECT(8, 2);
+  // ---- stage 2: collect --------------------------------------------------------------------------------------
+  if (!h->force_scan) {
+    if (C % 4 == 0 && ((uintptr_t)ps.x % 16) == 0 && C / 4 <= RPP_COLLECT_NT) {
+      const int C4 = C / 4;
+      const int lanes = RPP_COLLECT_NT / C4;
+      const int UNROLL = h->collect_variant == 2 ? 8 : 4;
+      const int MINB = h->collect_variant == 0 ? 3 : 2;
+      // tile: ~10 expected hits per class (stage capacity 32) when the plan aims at `target` candidates per column
+      long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
+      rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
+      if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
+      const int tiles_per_image = (int)((n + rows_per_tile - 1) / rows_per_tile);
+      const long n_tiles = (long)B * tiles_per_image;
+      long grid = (long)h->sm_count * MINB;
+      if (grid > n_tiles) grid = n_tiles;
+      const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(u32) + 2 * (size_t)C * sizeof(u32);
+#define RPP_LAUNCH_COLLECT(U, MB)                                                                               \
+      collect_cols4_kernel<U, MB><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(                                \
+          (const float4*)ps.x, T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,              \
+          tiles_per_image, tile_counter)
+      if (h->collect_variant == 0) RPP_LAUNCH_COLLECT(4, 3);
+      else if (h->collect_variant == 1) RPP_LAUNCH_COLLECT(4, 2);
+      else RPP_LAUNCH_COLLECT(8, 2);
 #undef RPP_LAUNCH_COLLECT
-    LAUNCHED();
-  } else {
-    const size_t tot = (size_t)B * n * C;
-    size_t grid = (tot + 255) / 256;
-    if (grid > (size_t)h->sm_count * 32) grid = (size_t)h->sm_count * 32;
-    collect_cols1_kernel<<<(unsigned)grid, 256, 0, st>>>(x, w.T, w.cand_count, w.cand, plan.CAP, B, n, C);
-    LAUNCHED();
+      LAUNCHED();
+    } else {
+      const size_t tot = (size_t)B * n * C;
+      size_t grid = (tot + 255) / 256;
+      if (grid > (size_t)h->sm_count * 32) grid = (size_t)h->sm_count * 32;
+      collect_cols1_kernel<<<(unsigned)grid, 256, 0, st>>>(ps.x, T, cand_count, cand, plan.CAP, B, n, C);
+      LAUNCHED();
+    }
   }
+  stage_mark(h, 2, st);
+  // ---- stage 3: problems -------------------------------------------------------------------------------------
+  ColProblemParams pp{};
+  pp.x = ps.x; pp.is_logit = ps.is_logit; pp.N = n; pp.C = C;
+  pp.deltas = ps.deltas; pp.anchors = h->d_anchors; pp.boxes = ps.boxes; pp.q = ps.q; pp.dp = h->dp;
+  pp.clip_before = ps.clip_before;
+  pp.iou_threshold = ps.iou_threshold;
+  pp.score_threshold = ps.score_threshold;
+  pp.T_min = ps.T_min;
+  pp.M = ps.M; pp.M_lim = ps.M_lim; pp.k_lim = ps.k_lim;
+  pp.T = T; pp.cand_count = cand_count; pp.cand = cand; pp.CAP = plan.CAP;
+  pp.force_scan = h->force_scan;
+  pp.sel_key = ps.sel_key; pp.sel_box = ps.sel_box; pp.sel_cnt = ps.sel_cnt;
+  pp.soft_scale = ps.soft_sigma_tf > 0.0f ? -0.5f / ps.soft_sigma_tf : 0.0f;
+  pp.soft_ignores_iou = h->cfg.soft_ignores_iou_threshold;
+  pp.tie_is_rank = ps.tie_is_rank;
+  pp.r_key = r_key; pp.r_meta = r_meta; pp.r_box = r_box; pp.r_cap = r_cap;
+  pp.emit_key = ps.emit_key;
+  const size_t smem_nms = align_up(nms_shared_bytes(pp.M_lim), 16);
+  if (ps.consumer == RPP_CONSUME_HARD)
+    col_problem_kernel<RPP_CONSUME_HARD><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+  else if (ps.consumer == RPP_CONSUME_SOFT)
+    col_problem_kernel<RPP_CONSUME_SOFT><<<(unsigned)P, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
+  else
+    col_problem_kernel<RPP_CONSUME_EMIT><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+  LAUNCHED();
+  stage_mark(h, 3, st);
   return RPP_OK;
 }
 
-// per-(image, class) NMS problems over the columns of x [B,n,C] + per-image merge
-int run_per_class(Handle* h, const float* x, int is_logit, const float4* deltas, const float4* boxes, int q, int B,
-                  long n, long k_lim, int row0_mode, float4* out_boxes, float* out_scores, void* out_classes,
-                  int* out_valid, void* ws, size_t ws_bytes, cudaStream_t st) {
+struct Outputs {
+  float4* boxes; float* scores; void* classes; int* valid;
+};
+
+// NonMaxSuppressionV5's (iou_threshold, soft_nms_sigma) as the reference passes them (:253-255, :448-450).
+void nms_v5_args(const rpp_config& c, float* iou_thr, float* sigma_tf) {
+  float sigma = 0.0f;
+  if (c.mode == RPP_GLOBAL_SOFT_NMS || c.mode == RPP_PER_CLASS_SOFT_NMS) sigma = c.soft_nms_sigma;
+  if (c.mode == RPP_GLOBAL_SOFT_NMS || c.mode == RPP_GLOBAL_HARD_NMS)
+    *iou_thr = (sigma == 0.0f) ? 1.0f : c.iou_threshold;   // `1.0 if not sigma else iou` (B1, B2)
+  else
+    *iou_thr = (sigma != 0.0f) ? 1.0f : c.iou_threshold;   // `1.0 if sigma else iou` (B3)
+  *sigma_tf = sigma / 2.0f;                                 // soft_nms_sigma = sigma / 2 (B4)
+}
+
+// CombinedNMS / PerClass*: per-(image, class) problems over the columns of x [B,n,C], then the per-image merge.
+int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
+                       int q, int B, long n, long k_lim, int row0_mode, int tie_is_rank, const Outputs& out,
+                       cudaStream_t st) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
-  const size_t P = (size_t)B * C;
-  const SamplePlan plan = make_plan(n, C, kTarget);
-  Workspace w = layout_cols(ws, P, M, plan.CAP, plan.on ? (size_t)B * plan.G * C : 0);
-  if (w.bytes > ws_bytes) return fail(RPP_EWORKSPACE, "workspace: need %zu bytes, got %zu", w.bytes, ws_bytes);
-  const float T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
-  int rc = launch_collect(h, x, w, plan, B, n, C, T_min, st);
-  if (rc) return rc;
-  stage_mark(h, 2, st);
-
-  if (c.mode == RPP_PER_CLASS_SOFT_NMS) return fail(RPP_EINVAL, "PerClassSoftNMS: not implemented yet");
-  ColProblemParams pp{};
-  pp.x = x; pp.is_logit = is_logit; pp.N = n; pp.C = C;
-  pp.deltas = deltas; pp.anchors = h->d_anchors; pp.boxes = boxes; pp.q = q; pp.dp = h->dp;
-  pp.clip_before = c.mode != RPP_COMBINED_NMS;
-  pp.iou_threshold = c.iou_threshold;
-  pp.score_threshold = c.score_threshold;
-  pp.T_min = T_min;
-  pp.M = M;
-  pp.M_lim = c.mode == RPP_COMBINED_NMS ? (int)std::min<long>(M, k_lim) : M;
-  pp.k_lim = k_lim;
-  pp.T = w.T; pp.cand_count = w.cand_count; pp.cand = w.cand; pp.CAP = plan.CAP;
-  pp.force_scan = h->force_scan;
-  pp.sel_key = w.sel_key; pp.sel_box = w.sel_box; pp.sel_cnt = w.sel_cnt;
-  const size_t smem = nms_shared_bytes(pp.M_lim);
-  col_hard_nms_kernel<<<(unsigned)P, RPP_NMS_NT, smem, st>>>(pp);
-  LAUNCHED();
-  stage_mark(h, 3, st);
+  ProblemSet ps{};
+  ps.x = x; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = C;
+  ps.deltas = deltas; ps.boxes = boxes; ps.q = q;
+  ps.k_lim = k_lim; ps.M = M;
+  ps.score_threshold = c.score_threshold;
+  ps.T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
+  ps.tie_is_rank = tie_is_rank;
+  if (c.mode == RPP_COMBINED_NMS) {
+    ps.consumer = RPP_CONSUME_HARD;
+    ps.clip_before = 0;
+    ps.iou_threshold = c.iou_threshold;
+    ps.M_lim = (int)std::min<long>(M, k_lim);
+  } else {
+    float iou_thr, sigma_tf;
+    nms_v5_args(c, &iou_thr, &sigma_tf);
+    ps.consumer = sigma_tf > 0.0f ? RPP_CONSUME_SOFT : RPP_CONSUME_HARD;
+    ps.clip_before = 1;
+    ps.iou_threshold = iou_thr;
+    ps.soft_sigma_tf = sigma_tf;
+    ps.M_lim = M;
+  }
+  int rc = run_problem_set(h, ar, ps, st);
+  if (rc || ar.dry) return rc;
 
   MergeParams mp{};
   mp.C = C; mp.M = M; mp.combined = c.mode == RPP_COMBINED_NMS;
-  mp.sel_key = w.sel_key; mp.sel_box = w.sel_box; mp.sel_cnt = w.sel_cnt;
+  mp.sel_key = ps.sel_key; mp.sel_box = ps.sel_box; mp.sel_cnt = ps.sel_cnt;
   mp.x = x; mp.is_logit = is_logit; mp.N = n;
   mp.deltas = deltas; mp.anchors = h->d_anchors; mp.boxes = boxes; mp.q = q; mp.dp = h->dp;
   mp.row0_mode = row0_mode;
-  mp.out_boxes = out_boxes; mp.out_scores = out_scores; mp.out_classes = out_classes; mp.out_valid = out_valid;
+  mp.out_boxes = out.boxes; mp.out_scores = out.scores; mp.out_classes = out.classes; mp.out_valid = out.valid;
   merge_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mp);
   LAUNCHED();
   stage_mark(h, 4, st);
   return RPP_OK;
+}
+
+// Global*: NonMaxSuppressionV5 per image on the row maxima of x [B,n,C].
+int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
+                    int B, long n, const Outputs& out, cudaStream_t st) {
+  const rpp_config& c = h->cfg;
+  const int C = c.num_classes, M = c.max_detections;
+  float* mraw = ar.take<float>((size_t)B * n);
+  if (!ar.dry) {
+    const size_t rows = (size_t)B * n;
+    size_t grid = (rows * 32 + 255) / 256;
+    if (grid > (size_t)h->sm_count * 16) grid = (size_t)h->sm_count * 16;
+    rowmax_kernel<<<(unsigned)grid, 256, 0, st>>>(x, rows, C, mraw);
+    LAUNCHED();
+  }
+  float iou_thr, sigma_tf;
+  nms_v5_args(c, &iou_thr, &sigma_tf);
+  ProblemSet ps{};
+  ps.x = mraw; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = 1;
+  ps.deltas = deltas; ps.boxes = boxes; ps.q = 1;
+  ps.k_lim = n; ps.M = M; ps.M_lim = M;
+  ps.score_threshold = c.score_threshold;
+  ps.T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
+  ps.tie_is_rank = 0;
+  ps.consumer = sigma_tf > 0.0f ? RPP_CONSUME_SOFT : RPP_CONSUME_HARD;
+  ps.clip_before = 1;
+  ps.iou_threshold = iou_thr;
+  ps.soft_sigma_tf = sigma_tf;
+  int rc = run_problem_set(h, ar, ps, st);
+  if (rc || ar.dry) return rc;
+  GlobalOutParams gp{};
+  gp.M = M; gp.sel_key = ps.sel_key; gp.sel_box = ps.sel_box; gp.sel_cnt = ps.sel_cnt;
+  gp.x = x; gp.is_logit = is_logit; gp.n = n; gp.C = C;
+  gp.deltas = deltas; gp.anchors = h->d_anchors; gp.boxes = boxes; gp.dp = h->dp;
+  gp.out_boxes = out.boxes; gp.out_scores = out.scores; gp.out_classes = (long long*)out.classes;
+  gp.out_valid = out.valid;
+  global_out_kernel<<<B, 128, 0, st>>>(gp);
+  LAUNCHED();
+  stage_mark(h, 4, st);
+  return RPP_OK;
+}
+
+// Sorted top-k keys of every column of x [B,n,C] (C = 1 with n = rows*classes for the global filter).
+int topk_keys(Handle* h, Arena& ar, const float* x, int is_logit, int B, long n, int C, long k, u64** emit_key,
+              cudaStream_t st) {
+  ProblemSet ps{};
+  ps.x = x; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = C;
+  ps.q = 1;
+  ps.consumer = RPP_CONSUME_EMIT;
+  ps.k_lim = k; ps.M = 1; ps.M_lim = 1;
+  ps.score_threshold = -INFINITY;   // tf.nn.top_k has no threshold
+  ps.T_min = -INFINITY;
+  int rc = run_problem_set(h, ar, ps, st);
+  *emit_key = ps.emit_key;
+  return rc;
+}
+
+// GenerateDetections on dense scores [B,n,C] / boxes [B,n,q,4]
+int nms_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, int B, long n, int q, const Outputs& out,
+              cudaStream_t st) {
+  if (is_per_class_mode(h->cfg.mode))
+    return per_class_pipeline(h, ar, scores, 0, nullptr, boxes, q, B, n, n, 0, 0, out, st);
+  return global_pipeline(h, ar, scores, 0, nullptr, boxes, B, n, out, st);
+}
+
+// FilterTopKDetections on dense scores / boxes
+int topk_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, int B, long n, float* scores_out,
+               float4* boxes_out, int* idx_out, cudaStream_t st) {
+  const rpp_config& c = h->cfg;
+  const int C = c.num_classes;
+  u64* keys = nullptr;
+  if (c.filter_per_class) {
+    const long k = std::min<long>(c.pre_nms_top_k, n);
+    int rc = topk_keys(h, ar, scores, 0, B, n, C, k, &keys, st);
+    if (rc || ar.dry) return rc;
+    const size_t tot = (size_t)B * k * C;
+    size_t grid = std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
+    topk_gather_per_class_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, boxes, B, n, C, k, scores_out, boxes_out,
+                                                                idx_out);
+    LAUNCHED();
+    return RPP_OK;
+  }
+  const long k = std::min<long>(c.pre_nms_top_k, n * C);
+  int rc = topk_keys(h, ar, scores, 0, B, n * C, 1, k, &keys, st);
+  if (rc || ar.dry) return rc;
+  const size_t tot = (size_t)B * k * C;
+  size_t grid = std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
+  topk_gather_global_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, scores, boxes, B, n, C, k, scores_out, boxes_out,
+                                                           idx_out);
+  LAUNCHED();
+  return RPP_OK;
+}
+
+// add_post_processing_stage fused: logits + deltas -> detections
+int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* logits, int B, const Outputs& out,
+                    cudaStream_t st) {
+  const rpp_config& c = h->cfg;
+  const int C = c.num_classes;
+  const long N = h->N;
+  const bool filtered = c.pre_nms_top_k > 0;
+  const bool per_class = is_per_class_mode(c.mode);
+  if (!per_class && filtered && c.filter_per_class)
+    return fail(RPP_ECOMBO, "Global* NMS modes need inference.filter_per_class=false (per-class filtered boxes are "
+                            "4-D; the reference fails with a rank error)");
+  if (!filtered)   // TransformBoxesAndScores -> GenerateDetections on all N rows
+    return per_class ? per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, N, 0, 0, out, st)
+                     : global_pipeline(h, ar, logits, 1, deltas, nullptr, B, N, out, st);
+  if (c.filter_per_class) {
+    const long k = std::min<long>(c.pre_nms_top_k, N);
+    return per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, k, 1, 1, out, st);
+  }
+  // global filter (:149-161): top-k over the flat (anchor, class) axis on raw logits, then the k selected rows are
+  // transformed (sigmoid of the whole row, decoded box) and fed to GenerateDetections as in the reference.
+  const long k = std::min<long>(c.pre_nms_top_k, N * C);
+  u64* keys = nullptr;
+  int rc = topk_keys(h, ar, logits, 1, B, N * C, 1, k, &keys, st);
+  if (rc) return rc;
+  float* row_scores = ar.take<float>((size_t)B * k * C);
+  float4* row_boxes = ar.take<float4>((size_t)B * k);
+  if (!ar.dry) {
+    const size_t tot = (size_t)B * k * C;
+    size_t grid = std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
+    fused_global_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, logits, deltas, h->d_anchors, h->dp, B, N, C, k,
+                                                            row_scores, row_boxes);
+    LAUNCHED();
+  }
+  return nms_dense(h, ar, row_scores, row_boxes, B, k, 1, out, st);
+}
+
+template <class F>
+int with_arena(void* ws, size_t ws_bytes, F body) {
+  Arena dry{nullptr, 0, true};
+  int rc = body(dry);
+  if (rc) return rc;
+  if (dry.off > ws_bytes) return fail(RPP_EWORKSPACE, "workspace: need %zu bytes, got %zu", dry.off, ws_bytes);
+  if (!ws && dry.off) return fail(RPP_EINVAL, "null workspace");
+  Arena real{(char*)ws, 0, false};
+  return body(real);
 }
 
 }  // namespace
@@ -358,7 +560,9 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     delete h;
     return fail(RPP_ECUDA, "create kernels: %s", cudaGetErrorString(e));
   }
-  cudaFuncSetAttribute(col_hard_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -435,12 +639,28 @@ int rpp_anchors(void* handle, float* d_out, void* stream) {
 size_t rpp_workspace_bytes(void* handle, int B, long n) {
   Handle* h = (Handle*)handle;
   if (!h || B <= 0) return 0;
-  if (n <= 0) n = h->N;
-  const int C = h->cfg.num_classes;
-  const SamplePlan plan = make_plan(n, C, kTarget);
-  const Workspace w = layout_cols(nullptr, (size_t)B * C, h->cfg.max_detections, plan.CAP,
-                                  plan.on ? (size_t)B * plan.G * C : 0);
-  return w.bytes + 4096;
+  const Outputs none{};
+  size_t need = 0;
+  // the handle's role is not known here (rpp_detect, rpp_nms or rpp_topk): size for the largest of those that are
+  // valid for this config
+  {
+    Arena a{nullptr, 0, true};
+    if (n <= 0 && detect_pipeline(h, a, nullptr, nullptr, B, none, nullptr) == RPP_OK) need = std::max(need, a.off);
+  }
+  if (n > 0) {
+    const bool per_class = is_per_class_mode(h->cfg.mode);
+    for (int q = 1; q <= (per_class ? 2 : 1); ++q) {
+      Arena a{nullptr, 0, true};
+      if (nms_dense(h, a, nullptr, nullptr, B, n, q == 1 ? 1 : h->cfg.num_classes, none, nullptr) == RPP_OK)
+        need = std::max(need, a.off);
+    }
+    if (h->cfg.pre_nms_top_k > 0) {
+      Arena a{nullptr, 0, true};
+      if (topk_dense(h, a, nullptr, nullptr, B, n, nullptr, nullptr, nullptr, nullptr) == RPP_OK)
+        need = std::max(need, a.off);
+    }
+  }
+  return need + 4096;
 }
 
 int rpp_decode(void* handle, const float* d_logits, const float* d_deltas, int B, float* d_scores, float* d_boxes,
@@ -472,10 +692,15 @@ int rpp_decode(void* handle, const float* d_logits, const float* d_deltas, int B
 
 int rpp_topk(void* handle, const float* d_scores, const float* d_boxes, int B, long n, float* d_scores_out,
              float* d_boxes_out, int* d_index_out, void* ws, size_t ws_bytes, void* stream) {
-  (void)handle; (void)d_scores; (void)d_boxes; (void)B; (void)n; (void)d_scores_out; (void)d_boxes_out;
-  (void)d_index_out; (void)ws; (void)ws_bytes; (void)stream;
+  Handle* h = (Handle*)handle;
   g_launches = 0;
-  return fail(RPP_EINVAL, "rpp_topk: not implemented yet");
+  if (!h || !d_scores || !d_boxes || !d_scores_out || !d_boxes_out || B <= 0 || n <= 0)
+    return fail(RPP_EINVAL, "bad argument");
+  if (h->cfg.pre_nms_top_k <= 0) return fail(RPP_EINVAL, "pre_nms_top_k must be positive for rpp_topk");
+  return with_arena(ws, ws_bytes, [&](Arena& ar) {
+    return topk_dense(h, ar, d_scores, (const float4*)d_boxes, B, n, d_scores_out, (float4*)d_boxes_out, d_index_out,
+                      (cudaStream_t)stream);
+  });
 }
 
 int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, long n, int q, float* d_boxes_out,
@@ -485,34 +710,22 @@ int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, lo
   if (!h || !d_scores || !d_boxes || B <= 0 || n <= 0) return fail(RPP_EINVAL, "bad argument");
   const rpp_config& c = h->cfg;
   if (q != 1 && q != c.num_classes) return fail(RPP_EINVAL, "boxes must be [B,n,4] or [B,n,num_classes,4]");
-  if (!is_per_class_mode(c.mode)) {
-    if (q != 1) return fail(RPP_ECOMBO, "Global* NMS modes need class-agnostic [B,n,4] boxes "
-                                        "(inference.filter_per_class=false)");
-    return fail(RPP_EINVAL, "Global* modes: not implemented yet");
-  }
-  return run_per_class(h, d_scores, 0, nullptr, (const float4*)d_boxes, q, B, n, n, 0, (float4*)d_boxes_out,
-                       d_scores_out, d_classes_out, d_valid_out, ws, ws_bytes, (cudaStream_t)stream);
+  if (!is_per_class_mode(c.mode) && q != 1)
+    return fail(RPP_ECOMBO, "Global* NMS modes need class-agnostic [B,n,4] boxes (inference.filter_per_class=false)");
+  const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
+  return with_arena(ws, ws_bytes, [&](Arena& ar) {
+    return nms_dense(h, ar, d_scores, (const float4*)d_boxes, B, n, q, out, (cudaStream_t)stream);
+  });
 }
 
 static int detect_impl(Handle* h, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,
                        float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes,
                        void* stream) {
   if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
-  const rpp_config& c = h->cfg;
-  const bool filtered = c.pre_nms_top_k > 0;
-  if (is_per_class_mode(c.mode)) {
-    if (!filtered || c.filter_per_class) {
-      const long k_lim = filtered ? std::min<long>(c.pre_nms_top_k, h->N) : h->N;
-      return run_per_class(h, d_logits, 1, (const float4*)d_deltas, nullptr, 1, B, h->N, k_lim, filtered ? 1 : 0,
-                           (float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out, ws, ws_bytes,
-                           (cudaStream_t)stream);
-    }
-    return fail(RPP_EINVAL, "global pre-NMS filter: not implemented yet");
-  }
-  if (filtered && c.filter_per_class)
-    return fail(RPP_ECOMBO, "Global* NMS modes need inference.filter_per_class=false (per-class filtered boxes are "
-                            "4-D; the reference fails with a rank error)");
-  return fail(RPP_EINVAL, "Global* modes: not implemented yet");
+  const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
+  return with_arena(ws, ws_bytes, [&](Arena& ar) {
+    return detect_pipeline(h, ar, (const float4*)d_deltas, d_logits, B, out, (cudaStream_t)stream);
+  });
 }
 
 int rpp_detect(void* handle, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,

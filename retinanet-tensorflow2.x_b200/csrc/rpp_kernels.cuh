@@ -286,9 +286,19 @@ struct ColProblemParams {
   int CAP;
   int force_scan;          // debug: ignore the lists, use the exact column scan only
   // outputs per problem
-  u64* sel_key;            // [P][M]  (score bits | ~row index)
+  u64* sel_key;            // [P][M]  (final score bits | ~row index)
   float4* sel_box;         // [P][M]  kept boxes as they leave NMS (clipped iff clip_before)
   int* sel_cnt;            // [P]
+  // soft NMS (NonMaxSuppressionV5 with soft_nms_sigma > 0)
+  float soft_scale;        // -0.5 / soft_nms_sigma (soft_nms_sigma = config sigma / 2)
+  int soft_ignores_iou;    // TF >= 2.3 weight form
+  int tie_is_rank;         // NMS index of a candidate = its rank in the filtered list (per-class top-k ran first)
+  u64* r_key;              // [P][r_cap] spill of the re-scored queue beyond shared memory
+  uint2* r_meta;
+  float4* r_box;
+  long r_cap;
+  // top-k emission (FilterTopKDetections): sorted keys of the k_lim best rows
+  u64* emit_key;           // [P][k_lim]
 };
 
 struct NmsShared {
@@ -306,7 +316,7 @@ __device__ __forceinline__ float4* nms_kbox(NmsShared* sh) { return reinterpret_
 __device__ __forceinline__ float* nms_karea(NmsShared* sh, int M_lim) {
   return reinterpret_cast<float*>(nms_kbox(sh) + M_lim);
 }
-static inline size_t nms_shared_bytes(int M_lim) { return sizeof(NmsShared) + (size_t)M_lim * 20 + 16; }
+__host__ __device__ static inline size_t nms_shared_bytes(int M_lim) { return sizeof(NmsShared) + (size_t)M_lim * 20 + 16; }
 
 __device__ __forceinline__ float col_score(const ColProblemParams& P, float raw) {
   return P.is_logit ? sigmoid_f32(raw) : raw;
@@ -417,16 +427,233 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
   }
 }
 
-__global__ void __launch_bounds__(RPP_NMS_NT) col_hard_nms_kernel(ColProblemParams P) {
+// ---------------------------------------------------------------------------------------------------------------
+// Soft NMS consumer: NonMaxSuppressionV5 with soft_nms_sigma > 0, lazily re-scored exactly as the
+// TF kernel does it.  The priority queue is split in two: candidates never popped yet are the not-yet-consumed part
+// of the sorted stream (their order is static), and candidates popped, decayed and pushed back live in R (shared
+// memory, spilling to global).  Each step pops the larger of (stream head, max of R); a popped candidate multiplies
+// its score by the weights of the boxes selected since its last visit, newest first, in fp32 in exactly that order,
+// stopping when it falls to the score threshold; it is selected iff the score did not change.
+// expf_glibc reproduces libm's expf bit for bit (checked against glibc on 4.5e8 inputs): TF's kernel calls
+// Eigen::numext::exp<float> = expf.
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ u64 c_exp2f_tab[32] = {
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL,
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL,
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL,
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL,
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
+
+__device__ __forceinline__ float expf_glibc(float x) {
+  if (!(x > -87.0f && x < 88.0f)) return (float)exp((double)x);  // under/overflow tails: correctly rounded exp
+  const double N = 32.0;
+  const double InvLn2N = 0x1.71547652b82fep+0 * N, SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5 / N / N / N, C1 = 0x1.ebfce50fac4f3p-3 / N / N, C2 = 0x1.62e42ff0c52d6p-1 / N;
+  const double z = __dmul_rn(InvLn2N, (double)x);
+  double kd = __dadd_rn(z, SHIFT);
+  const u64 ki = (u64)__double_as_longlong(kd);
+  kd = __dsub_rn(kd, SHIFT);
+  const double r = __dsub_rn(z, kd);
+  const u64 t = c_exp2f_tab[ki & 31u] + (ki << 47);
+  const double sc = __longlong_as_double((long long)t);
+  const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
+  const double r2 = __dmul_rn(r, r);
+  double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+  y = __dadd_rn(__dmul_rn(zz, r2), y);
+  y = __dmul_rn(y, sc);
+  return __double2float_rn(y);
+}
+
+#define RPP_SOFT_RS 512
+
+struct SoftShared {
+  u64 rkey[RPP_SOFT_RS];
+  uint2 rmeta[RPP_SOFT_RS];   // {suppress_begin_index, row}
+  float4 rbox[RPP_SOFT_RS];   // canonical box (the empty box when degenerate)
+  int rcount;
+};
+
+struct RStore {
+  SoftShared* s;
+  u64* gk; uint2* gm; float4* gb;
+  __device__ __forceinline__ u64 key(int i) const { return i < RPP_SOFT_RS ? s->rkey[i] : gk[i - RPP_SOFT_RS]; }
+  __device__ __forceinline__ uint2 meta(int i) const { return i < RPP_SOFT_RS ? s->rmeta[i] : gm[i - RPP_SOFT_RS]; }
+  __device__ __forceinline__ float4 box(int i) const { return i < RPP_SOFT_RS ? s->rbox[i] : gb[i - RPP_SOFT_RS]; }
+  __device__ __forceinline__ void set(int i, u64 k, uint2 m, float4 b) {
+    if (i < RPP_SOFT_RS) { s->rkey[i] = k; s->rmeta[i] = m; s->rbox[i] = b; }
+    else { gk[i - RPP_SOFT_RS] = k; gm[i - RPP_SOFT_RS] = m; gb[i - RPP_SOFT_RS] = b; }
+  }
+};
+
+__device__ __forceinline__ float iou_val(float4 a, float area_a, float4 b, float area_b) {
+  const float h0 = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float h1 = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  const float inter = __fmul_rn(h0, h1);
+  if (!(inter > 0.0f)) return 0.0f;
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+}
+
+// m > 0: consume a sorted chunk of the stream (returns when it is exhausted or the problem is done);
+// m == 0 && final: the stream is over, drain R.
+__device__ void soft_nms_consume(const ColProblemParams& P, NmsShared* sh, SoftShared* ss, int b, int c, size_t p,
+                                 int m, long& consumed, bool final) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4* kbox = nms_kbox(sh);
+  float* karea = nms_karea(sh, P.M_lim);
+  RStore R{ss, P.r_key + p * (size_t)P.r_cap, P.r_meta + p * (size_t)P.r_cap, P.r_box + p * (size_t)P.r_cap};
+  const long room = P.k_lim - consumed;
+  const int m_eff = (long)m < room ? m : (int)room;
+  const float thr = P.score_threshold;
+  const int ngroups = final ? 1 : (m_eff + RPP_NMS_NT - 1) / RPP_NMS_NT;
+  for (int g = 0; g < ngroups; ++g) {
+    const int g0 = g * RPP_NMS_NT;
+    const int gcount = final ? 0 : (m_eff - g0 < RPP_NMS_NT ? m_eff - g0 : RPP_NMS_NT);
+    if (tid < gcount) {
+      float4 orig = col_box(P, b, c, key_tie(sh->chunk[g0 + tid]));
+      if (P.clip_before) orig = clip01(orig);
+      float area;
+      const float4 cb = canon_box(orig, area);
+      sh->corig[tid] = orig;
+      sh->cbox[tid] = area > 0.0f ? cb : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+      sh->carea[tid] = area > 0.0f ? area : 0.0f;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int nsel = sh->nkept;
+      int rcount = ss->rcount;
+      int pos = 0;
+      for (;;) {
+        if (nsel >= P.M_lim) { if (lane == 0) sh->done = 1; break; }
+        // stream head
+        u64 head = 0ull, head_cmp = 0ull;
+        if (pos < gcount) {
+          head = sh->chunk[g0 + pos];
+          head_cmp = P.tie_is_rank ? make_key(key_score(head), (u32)(consumed + g0 + pos)) : head;
+        }
+        // max of R
+        u64 best = 0ull;
+        int best_i = -1;
+        for (int i = lane; i < rcount; i += 32) {
+          const u64 k = R.key(i);
+          if (k > best) { best = k; best_i = i; }
+        }
+        u64 wbest = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const u64 other = __shfl_xor_sync(RPP_FULL_MASK, wbest, o);
+          wbest = other > wbest ? other : wbest;
+        }
+        const u32 owner = __ballot_sync(RPP_FULL_MASK, best == wbest && best != 0ull);
+        const int r_i = owner ? __shfl_sync(RPP_FULL_MASK, best_i, __ffs(owner) - 1) : -1;
+        if (head == 0ull && (!final || wbest == 0ull)) break;  // need more stream / everything drained
+        const bool from_stream = head != 0ull && head_cmp > wbest;
+        float score, area;
+        float4 box;
+        u32 row, tie;
+        int begin;
+        if (from_stream) {
+          score = key_score(head); row = key_tie(head); tie = key_tie(head_cmp); begin = 0;
+          box = sh->cbox[pos]; area = sh->carea[pos];
+        } else {
+          score = key_score(wbest); tie = key_tie(wbest);
+          const uint2 mt = R.meta(r_i);
+          begin = (int)mt.x; row = mt.y;
+          box = R.box(r_i);
+          area = box.z > box.x ? __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y)) : 0.0f;
+        }
+        const float original = score;
+        bool dropped = false;
+        for (int j = nsel - 1; j >= begin && !dropped; j -= 32) {
+          const int jj = j - lane;
+          float w = 1.0f;
+          if (jj >= begin) {
+            const float sim = iou_val(box, area, kbox[jj], karea[jj]);
+            w = expf_glibc(__fmul_rn(__fmul_rn(P.soft_scale, sim), sim));
+            if (!P.soft_ignores_iou && sim > P.iou_threshold) w = 0.0f;
+          }
+          const int cnt = j - begin + 1 < 32 ? j - begin + 1 : 32;
+          for (int t = 0; t < cnt; ++t) {
+            score = __fmul_rn(score, __shfl_sync(RPP_FULL_MASK, w, t));
+            if (score <= thr) { dropped = true; break; }
+          }
+        }
+        if (from_stream) ++pos;
+        if (score == original) {  // select
+          if (lane == 0) {
+            kbox[nsel] = box;
+            karea[nsel] = area;
+            P.sel_key[p * P.M + nsel] = make_key(score, row);
+            float4 ob;
+            if (from_stream) ob = sh->corig[pos - 1];
+            else { ob = col_box(P, b, c, row); if (P.clip_before) ob = clip01(ob); }
+            P.sel_box[p * P.M + nsel] = ob;
+          }
+          ++nsel;
+          if (!from_stream) {  // remove from R (swap with last)
+            --rcount;
+            if (lane == 0 && r_i != rcount) R.set(r_i, R.key(rcount), R.meta(rcount), R.box(rcount));
+          }
+        } else if (!dropped && score > thr) {  // push back, re-scored
+          const int slot = from_stream ? rcount : r_i;
+          if (lane == 0) R.set(slot, make_key(score, tie), make_uint2((u32)nsel, row), box);
+          if (from_stream) ++rcount;
+        } else if (!from_stream) {  // fell to the threshold: gone
+          --rcount;
+          if (lane == 0 && r_i != rcount) R.set(r_i, R.key(rcount), R.meta(rcount), R.box(rcount));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) { sh->nkept = nsel; ss->rcount = rcount; }
+    }
+    __syncthreads();
+    if (sh->done) break;
+  }
+  if (!final) consumed += m_eff;  // at k_lim the caller stops the stream and drains R
+}
+
+// Top-k emission consumer (FilterTopKDetections): the stream IS the sorted top-k.
+__device__ void emit_consume(const ColProblemParams& P, NmsShared* sh, size_t p, int m, long& consumed) {
+  const long room = P.k_lim - consumed;
+  const int m_eff = (long)m < room ? m : (int)room;
+  for (int i = threadIdx.x; i < m_eff; i += RPP_NMS_NT) P.emit_key[p * (size_t)P.k_lim + consumed + i] = sh->chunk[i];
+  consumed += m_eff;
+  if (consumed >= P.k_lim) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh->done = 1;
+    __syncthreads();
+  }
+}
+
+#define RPP_CONSUME_HARD 0
+#define RPP_CONSUME_SOFT 1
+#define RPP_CONSUME_EMIT 2
+
+template <int MODE>
+__global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NmsShared* sh = reinterpret_cast<NmsShared*>(smem_raw);
+  SoftShared* ss = reinterpret_cast<SoftShared*>(smem_raw + ((nms_shared_bytes(P.M_lim) + 15) & ~(size_t)15));
   const int tid = threadIdx.x;
   const size_t p = blockIdx.x;
   const int b = (int)(p / P.C), c = (int)(p % P.C);
-  if (tid == 0) { sh->nkept = 0; sh->done = 0; }
+  if (tid == 0) {
+    sh->nkept = 0;
+    sh->done = 0;
+    if (MODE == RPP_CONSUME_SOFT) ss->rcount = 0;
+  }
   __syncthreads();
 
   long consumed = 0;
+  auto consume = [&](int m) {
+    if (MODE == RPP_CONSUME_HARD) hard_nms_consume(P, sh, b, c, p, m, consumed);
+    else if (MODE == RPP_CONSUME_SOFT) soft_nms_consume(P, sh, ss, b, c, p, m, consumed, false);
+    else emit_consume(P, sh, p, m, consumed);
+  };
+  const int want0 = MODE == RPP_CONSUME_EMIT ? RPP_NMS_CHUNK : 256;
+
   const float T = P.T[p];
   u32 n_raw = P.cand_count[p];
   const bool overflow = n_raw > (u32)P.CAP;
@@ -450,17 +677,17 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_hard_nms_kernel(ColProblemPara
     }
     __syncthreads();
     u64 KB = ~0ull;
-    int want = 256;
-    while (!sh->done) {
+    int want = want0;
+    while (!sh->done && consumed < P.k_lim) {
       const int m = select_chunk<RPP_NMS_NT>([&](int i) { return keys[i]; }, n_list, KB, want, sh->chunk,
                                              RPP_NMS_CHUNK, &sh->sel);
       if (m == 0) break;
-      hard_nms_consume(P, sh, b, c, p, m, consumed);
+      consume(m);
       want = RPP_NMS_CHUNK;
     }
   }
   // ---- phase B: exact scan of the column for everything at or below the edge ---------------------------------
-  if (!sh->done && (!list_complete || overflow || P.force_scan)) {
+  if (!sh->done && consumed < P.k_lim && (!list_complete || overflow || P.force_scan)) {
     u64 KB = (s_edge == INFINITY) ? ~0ull : ((u64)(ord_f32(s_edge) + 1u) << 32);
     const float* col = P.x + (size_t)b * P.N * P.C + c;
     auto keyfn = [&](int i) -> u64 {
@@ -469,15 +696,18 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_hard_nms_kernel(ColProblemPara
       const float s = col_score(P, raw);
       return s > P.score_threshold ? make_key(s, (u32)i) : 0ull;
     };
-    int want = 256;
-    while (!sh->done) {
+    int want = want0;
+    while (!sh->done && consumed < P.k_lim) {
       const int m = select_chunk<RPP_NMS_NT>(keyfn, (int)P.N, KB, want, sh->chunk, RPP_NMS_CHUNK, &sh->sel);
       if (m == 0) break;
-      hard_nms_consume(P, sh, b, c, p, m, consumed);
+      consume(m);
       want = RPP_NMS_CHUNK;
     }
   }
-  if (tid == 0) P.sel_cnt[p] = sh->nkept;
+  if (MODE == RPP_CONSUME_SOFT) {
+    if (!sh->done) soft_nms_consume(P, sh, ss, b, c, p, 0, consumed, true);  // stream over: drain the queue
+  }
+  if (MODE != RPP_CONSUME_EMIT && tid == 0) P.sel_cnt[p] = sh->nkept;
 }
 
 // ===============================================================================================================
@@ -625,5 +855,133 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
       last_c = c;
     }
     if (tid == 0) ob[i] = last_box;
+  }
+}
+
+// ===============================================================================================================
+// K5  Global* modes (GenerateDetections._global_nms, postprocessing_ops.py:244-286): NonMaxSuppressionV5 runs on
+// the per-row maximum over classes.  rowmax_kernel reduces [B,n,C] -> [B,n] (max raw value per row; the score is
+// monotone in the raw value so max score = score(max raw)); the problem kernel then runs with C = 1;
+// global_out_kernel gathers boxes / classes and applies the reference's padding (score -1, class -1, box =
+// boxes[0]).  The class (tf.argmax: first maximum, by SCORE) is only needed for the <= M selected
+// rows, so it is resolved there.
+// ===============================================================================================================
+__global__ void rowmax_kernel(const float* __restrict__ x, size_t rows, int C, float* __restrict__ out) {
+  // one warp per row: coalesced reads of the row's C values
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t r = warp; r < rows; r += nwarps) {
+    float m = -INFINITY;
+    bool any_nan = false;
+    for (int c = lane; c < C; c += 32) {
+      const float v = __ldg(x + r * C + c);
+      any_nan |= v != v;
+      m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(RPP_FULL_MASK, m, o));
+    if (lane == 0) out[r] = m;
+  }
+}
+
+struct GlobalOutParams {
+  int M;
+  const u64* sel_key;     // [B][M]  (score | ~row)
+  const float4* sel_box;  // [B][M]
+  const int* sel_cnt;     // [B]
+  const float* x;         // [B,n,C] logits or scores
+  int is_logit; long n; int C;
+  const float4* deltas; const float4* anchors; const float4* boxes; DecodeParams dp;
+  float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
+};
+
+__global__ void global_out_kernel(GlobalOutParams P) {
+  const int b = blockIdx.x;
+  const int valid = P.sel_cnt[b];
+  if (threadIdx.x == 0) P.out_valid[b] = valid;
+  for (int i = threadIdx.x; i < P.M; i += blockDim.x) {
+    const size_t o = (size_t)b * P.M + i;
+    if (i < valid) {
+      const u64 k = P.sel_key[o];
+      const u32 row = key_tie(k);
+      const float* xr = P.x + ((size_t)b * P.n + row) * P.C;
+      // tf.argmax over scores: first class whose SCORE equals the row maximum
+      float best = -INFINITY;
+      for (int c = 0; c < P.C; ++c) best = fmaxf(best, xr[c]);
+      const float s_best = P.is_logit ? sigmoid_f32(best) : best;
+      int cls = 0;
+      for (int c = 0; c < P.C; ++c) {
+        const float s = P.is_logit ? (xr[c] == best ? s_best : sigmoid_f32(xr[c])) : xr[c];
+        if (s == s_best) { cls = c; break; }
+      }
+      P.out_boxes[o] = P.sel_box[o];
+      P.out_scores[o] = key_score(k);
+      P.out_classes[o] = cls;
+    } else {
+      // padded selected index 0 -> boxes[0] (clipped), score -1, class -1 (:258-268)
+      float4 bx = P.boxes ? P.boxes[(size_t)b * P.n] : decode_box(P.deltas[(size_t)b * P.n], P.anchors[0], P.dp);
+      P.out_boxes[o] = clip01(bx);
+      P.out_scores[o] = -1.0f;
+      P.out_classes[o] = -1;
+    }
+  }
+}
+
+// ===============================================================================================================
+// K6  FilterTopKDetections outputs (postprocessing_ops.py:128-161) from the emitted sorted keys.
+// ===============================================================================================================
+// per class: scores_out [B,k,C], boxes_out [B,k,C,4], idx_out [B,C,k]
+__global__ void topk_gather_per_class_kernel(const u64* __restrict__ emit_key /*[B*C][k]*/, const float4* __restrict__ boxes,
+                                             int B, long n, int C, long k, float* __restrict__ scores_out,
+                                             float4* __restrict__ boxes_out, int* __restrict__ idx_out) {
+  const size_t tot = (size_t)B * k * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t bj = e / C;
+    const long j = (long)(bj % k);
+    const int b = (int)(bj / k);
+    const u64 key = emit_key[((size_t)b * C + c) * k + j];
+    const u32 row = key_tie(key);
+    scores_out[e] = key_score(key);
+    boxes_out[e] = boxes[(size_t)b * n + row];
+    if (idx_out) idx_out[((size_t)b * C + c) * k + j] = (int)row;
+  }
+}
+
+// global: emitted keys over the flat [n*C] axis; scores_out [B,k,C] = whole rows, boxes_out [B,k,4]
+__global__ void topk_gather_global_kernel(const u64* __restrict__ emit_key /*[B][k]*/, const float* __restrict__ scores,
+                                          const float4* __restrict__ boxes, int B, long n, int C, long k,
+                                          float* __restrict__ scores_out, float4* __restrict__ boxes_out,
+                                          int* __restrict__ idx_out) {
+  const size_t tot = (size_t)B * k * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t bj = e / C;
+    const int b = (int)(bj / k);
+    const u32 flat = key_tie(emit_key[bj]);
+    const u32 a = flat / (u32)C;  // indices // num_classes (:156)
+    scores_out[e] = scores[((size_t)b * n + a) * C + c];
+    if (c == 0) {
+      boxes_out[bj] = boxes[(size_t)b * n + a];
+      if (idx_out) idx_out[bj] = (int)flat;
+    }
+  }
+}
+
+// fused global filter: rows selected on raw logits -> materialise the reference's intermediates
+// scores [B,k,C] = sigmoid(logit rows), boxes [B,k,4] = decoded anchors (TransformBoxesAndScores on k rows only)
+__global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][k]*/, const float* __restrict__ logits,
+                                         const float4* __restrict__ deltas, const float4* __restrict__ anchors,
+                                         DecodeParams dp, int B, long N, int C, long k, float* __restrict__ scores_out,
+                                         float4* __restrict__ boxes_out) {
+  const size_t tot = (size_t)B * k * C;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C);
+    const size_t bj = e / C;
+    const int b = (int)(bj / k);
+    const u32 a = key_tie(emit_key[bj]) / (u32)C;
+    scores_out[e] = sigmoid_f32(logits[((size_t)b * N + a) * C + c]);
+    if (c == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
   }
 }

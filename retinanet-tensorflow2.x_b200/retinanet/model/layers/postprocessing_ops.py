@@ -357,7 +357,7 @@ class FusedPostProcessing(Layer):
             raise ValueError('expected class_logits [B,{0},C] and encoded_boxes [B,{0},4], got {1} and {2}'.format(
                 h.num_anchors, tuple(class_logits.shape), tuple(encoded_boxes.shape)))
         out = h.outputs(B, class_logits.device)
-        ws = h.workspace(B, N, class_logits.device)
+        ws = h.workspace(B, 0, class_logits.device)   # n = 0: sized for rpp_detect
         _native.check(_native.lib().rpp_detect(h.ptr, encoded_boxes.data_ptr(), class_logits.data_ptr(), B,
                                                out['boxes'].data_ptr(), out['scores'].data_ptr(),
                                                out['classes'].data_ptr(), out['valid_detections'].data_ptr(),

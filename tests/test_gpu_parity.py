@@ -61,6 +61,24 @@ CASES = [
     (320, 8, 2, 'CombinedNMS', 5000, True, 'sparse'),
     (320, 12, 2, 'PerClassHardNMS', 5000, True, 'quantized'),
     (320, 5, 2, 'PerClassHardNMS', 1000, True, 'dense'),     # C % 4 != 0: scalar collect kernel
+    # soft NMS (lazy re-scoring, bit-exact expf)
+    (64, 6, 3, 'PerClassSoftNMS', 50, True, 'dense'),
+    (64, 6, 3, 'PerClassSoftNMS', -1, True, 'sparse'),
+    (320, 8, 2, 'PerClassSoftNMS', 5000, True, 'dense'),
+    (320, 8, 2, 'PerClassSoftNMS', 300, True, 'quantized'),
+    # global filter (top-k over anchors x classes) feeding the per-class modes
+    (64, 6, 3, 'PerClassHardNMS', 80, False, 'dense'),
+    (320, 8, 2, 'CombinedNMS', 5000, False, 'dense'),
+    (320, 8, 2, 'PerClassSoftNMS', 2000, False, 'sparse'),
+    # Global* modes: no filter, or the global filter
+    (64, 6, 3, 'GlobalHardNMS', -1, True, 'dense'),
+    (64, 6, 3, 'GlobalSoftNMS', -1, False, 'dense'),
+    (64, 6, 3, 'GlobalSoftNMS', 80, False, 'dense'),
+    (320, 8, 2, 'GlobalHardNMS', 5000, False, 'dense'),
+    (320, 8, 2, 'GlobalSoftNMS', 5000, False, 'dense'),
+    (320, 8, 2, 'GlobalSoftNMS', -1, False, 'sparse'),
+    (320, 5, 2, 'GlobalHardNMS', 5000, False, 'sparse'),
+    (320, 8, 2, 'GlobalSoftNMS', 5000, False, 'quantized'),
 ]
 
 
@@ -73,6 +91,65 @@ def test_fused_detect_vs_oracle(ref, H, C, B, mode, k, fpc, dist):
     got = to_numpy(layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}))
     exp = oracle_detect(ref, p, logits, deltas)
     assert image_mismatches(got, exp) == []
+
+
+def test_global_mode_with_per_class_filter_is_rejected():
+    # the reference fails with a rank error; we raise ValueError
+    p = make_params(64, num_classes=4, mode='GlobalSoftNMS', pre_nms_top_k=50, filter_per_class=True)
+    layer = _fused(p)
+    N = layer.handle(4).num_anchors
+    logits, deltas = synth_inputs(1, N, 4)
+    with pytest.raises(ValueError):
+        layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)})
+
+
+def test_unsupported_mode_raises_assertion():
+    from retinanet.model.layers import GenerateDetections
+    with pytest.raises(AssertionError):
+        GenerateDetections(mode='FancyNMS')
+
+
+STAGE_CASES = [
+    ('PerClassHardNMS', 300, True), ('CombinedNMS', 300, True), ('PerClassSoftNMS', 300, True),
+    ('PerClassHardNMS', 400, False), ('GlobalSoftNMS', 400, False), ('GlobalHardNMS', 400, False),
+    ('CombinedNMS', -1, True), ('GlobalSoftNMS', -1, False),
+]
+
+
+@pytest.mark.parametrize('mode,k,fpc', STAGE_CASES)
+def test_stagewise_layers_vs_oracle(ref, mode, k, fpc):
+    """The reference's layer-by-layer graph (fused=False): every stage output is checked against the oracle's
+    stage; NMS runs on IDENTICAL inputs (the oracle's own decoded tensors) and must be bit-exact."""
+    from retinanet.model.builder import ModelBuilder
+    from retinanet.model.layers import FilterTopKDetections, GenerateDetections
+    H, C, B = 320, 8, 2
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=k, filter_per_class=fpc, max_detections=60)
+    model = ModelBuilder(p, run_mode='export').add_post_processing_stage(None, fused=False)
+    anchors, _ = ref.anchors(H, H, 3, 7, p.anchor_params.areas, p.anchor_params.aspect_ratios,
+                             p.anchor_params.scales)
+    N = len(anchors)
+    logits, deltas = synth_inputs(B, N, C, seed=11)
+    # whole chain through the layers
+    x = {'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}
+    for layer in model.layers[1:]:
+        x = layer(x)
+    exp = oracle_detect(ref, p, logits, deltas)
+    assert image_mismatches(to_numpy(x), exp) == []
+    # stage 2 on identical inputs: oracle's scores/boxes in, bit-exact out
+    es, eb = ref.sigmoid(logits), ref.decode_boxes(deltas, anchors, H, H)
+    if k > 0:
+        got = to_numpy(FilterTopKDetections(k, fpc)({'scores': _gpu(es), 'boxes': _gpu(eb)}))
+        fs, fb, _ = (ref.filter_per_class if fpc else ref.filter_global)(es, eb, k)
+        assert np.array_equal(got['scores'], fs) and np.array_equal(got['boxes'], fb)
+    else:
+        fs, fb = es, eb
+    inf = p.inference
+    gd = GenerateDetections(inf.iou_threshold, inf.score_threshold, inf.max_detections, inf.soft_nms_sigma, C, mode)
+    got = to_numpy(gd({'scores': _gpu(fs), 'boxes': _gpu(fb)}))
+    e2 = ref.generate_detections(mode, fs, fb, max_detections=inf.max_detections)
+    for key in e2:
+        assert got[key].dtype == e2[key].dtype
+        assert np.array_equal(got[key], e2[key]), key
 
 
 @pytest.mark.parametrize('mode', ['PerClassHardNMS', 'CombinedNMS'])
