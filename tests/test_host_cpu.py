@@ -1,0 +1,170 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/retinapost.h declares (no compute
+without a GPU), host-side config / builder logic, and image sharding over a world_size-2 gloo group."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from conftest import PKG, REFERENCE_CONFIG, ROOT
+
+
+def test_abi_exports_every_declared_symbol():
+    from retinanet import _native
+    header = open(os.path.join(ROOT, 'include', 'retinapost.h')).read()
+    declared = sorted(set(re.findall(r'\b(rpp_[a-z0-9_]+)\s*\(', header)))
+    assert len(declared) >= 16
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert missing == []
+    assert sorted(_native.EXPORTS) == declared
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without CUDA the product must fail loudly instead of computing somewhere else."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from retinanet import _native
+    from retinanet.model.layers import GenerateDetections
+    cfg = _native.RppConfig()
+    h = ctypes.c_void_p()
+    assert _native.lib().rpp_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    layer = GenerateDetections(mode='PerClassHardNMS', num_classes=2)
+    with pytest.raises(RuntimeError):
+        layer({'scores': torch.zeros(1, 4, 2), 'boxes': torch.zeros(1, 4, 4)})
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b|retinapost_ref|rpp_ref_', text, re.M):
+                    bad.append(f)
+    assert bad == []
+
+
+def test_attrdict_and_reference_json(tmp_path):
+    from retinanet.cfg.config import AttrDict, Config
+    path = tmp_path / 'cfg.json'
+    path.write_text(json.dumps(REFERENCE_CONFIG))
+    p = Config(str(path)).params
+    assert p.inference.mode == 'PerClassHardNMS' and p['inference']['max_detections'] == 100
+    assert p.architecture.feature_fusion.min_level == 3
+    p.inference.pre_nms_top_k = -1
+    assert p['inference']['pre_nms_top_k'] == -1
+    assert json.loads(json.dumps(p.inference))['iou_threshold'] == 0.5     # still a plain dict for json.dumps
+    with pytest.raises(AttributeError):
+        p.inference.nope
+    assert isinstance(AttrDict({'a': [{'b': 1}]}).a[0], AttrDict)
+    ref_json = '/root/reference/configs/v3-32/mscoco-retinanet-resnet50-640x640-30x-256.json'
+    if os.path.exists(ref_json):   # only in the build container
+        q = Config(ref_json).params
+        assert q.inference == REFERENCE_CONFIG['inference']
+        assert q.anchor_params == REFERENCE_CONFIG['anchor_params']
+
+
+def test_builder_stage_gating():
+    from retinanet.cfg.config import AttrDict
+    from retinanet.model.builder import ModelBuilder
+    from retinanet.model.layers import (FilterTopKDetections, FuseDetections, FusedPostProcessing,
+                                        GenerateDetections, TransformBoxesAndScores)
+    names = lambda m: [type(layer) for layer in m.layers]   # noqa: E731
+    p = AttrDict(REFERENCE_CONFIG)
+    b = ModelBuilder(p, run_mode='export')
+    assert names(b.add_post_processing_stage(None)) == [FuseDetections, FusedPostProcessing]
+    assert names(b.add_post_processing_stage(None, fused=False)) == [
+        FuseDetections, TransformBoxesAndScores, FilterTopKDetections, GenerateDetections]
+    assert names(b.add_post_processing_stage(None, skip_decoding=True, skip_nms=True)) == [FuseDetections]
+    assert names(b.prepare_model_for_export(None, mode='onnx_tensorrt')) == [FuseDetections]
+    # tf_tensorrt / onnx force pre_nms_top_k = -1 (builder.py:133-138)
+    b2 = ModelBuilder(AttrDict(REFERENCE_CONFIG))
+    m = b2.prepare_model_for_export(None, mode='onnx')
+    assert b2.params.inference.pre_nms_top_k == -1 and m.fused
+    assert names(b2.add_post_processing_stage(None, fused=False)) == [
+        FuseDetections, TransformBoxesAndScores, GenerateDetections]
+    with pytest.raises(ValueError):
+        b.prepare_model_for_export(None, mode='bogus')
+    with pytest.raises(AssertionError):
+        GenerateDetections(mode='NotAMode')
+    bad = AttrDict(REFERENCE_CONFIG)
+    bad.inference.mode = 'NotAMode'
+    with pytest.raises(AssertionError):
+        ModelBuilder(bad).add_post_processing_stage(None)
+
+
+def test_fuse_detections_layout():
+    """FuseDetections on CPU tensors (pure reshapes): anchor order (level, y, x, a), class fastest."""
+    import torch
+    from retinanet.model.layers import FuseDetections
+    B, A, C = 2, 9, 3
+    cls, box = {}, {}
+    for level, f in zip(range(3, 8), [8, 4, 2, 1, 1]):
+        cls[str(level)] = torch.arange(B * f * f * A * C, dtype=torch.float32).reshape(B, f, f, A * C) + level * 1e5
+        box[str(level)] = torch.arange(B * f * f * A * 4, dtype=torch.float32).reshape(B, f, f, A * 4) + level * 1e5
+    out = FuseDetections(3, 7)({'class-predictions': cls, 'box-predictions': box})
+    N = (64 + 16 + 4 + 1 + 1) * A
+    assert out['class_logits'].shape == (B, N, C) and out['encoded_boxes'].shape == (B, N, 4)
+    assert out['class_logits'][1, 0, 1] == cls['3'][1, 0, 0, 1]
+    assert out['class_logits'][0, 64 * A + 10, 2] == cls['4'][0, 0, 1, 1 * C + 2]   # level 4, x=1, anchor 1
+    assert out['encoded_boxes'][1, N - 1, 3] == box['7'][1, 0, 0, A * 4 - 1]
+
+
+def test_shard_range():
+    from retinanet.distributed import shard_range
+    for n in (0, 1, 7, 8, 64, 65):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from retinanet.distributed import shard_batch, shard_range, gather_detections
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:' + os.environ['PORT'], rank=rank, world_size=world)
+B, M = 5, 3                                   # ragged: ranks get 3 and 2 images
+full = {'boxes': torch.arange(B * M * 4, dtype=torch.float32).reshape(B, M, 4),
+        'scores': torch.arange(B * M, dtype=torch.float32).reshape(B, M),
+        'classes': torch.arange(B * M, dtype=torch.int32).reshape(B, M),
+        'valid_detections': torch.arange(B, dtype=torch.int32)}
+mine = shard_batch(full, rank, world)
+lo, hi = shard_range(B, rank, world)
+assert mine['scores'].shape[0] == hi - lo
+got = gather_detections(mine, num_images=B)
+for k in full:
+    assert got[k].dtype == full[k].dtype and torch.equal(got[k], full[k]), k
+dist.barrier()
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_gather_detections_gloo_world2(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER)
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE='2', PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), PKG], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
