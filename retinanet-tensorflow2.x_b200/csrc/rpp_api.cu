@@ -102,7 +102,9 @@ SamplePlan make_plan(long n, int C, int target) {
   int lanes = 1024 / C;
   if (lanes > 12) lanes = 12;
   const int G = lanes * RPP_GPT;
-  int S = (int)std::floor(target / (0.916 * G));
+  // group size chosen so that the wanted logit sits near the 70th percentile of the group maxima:
+  // rows per group g = -ln(0.7) * n / target, i.e. one sampled row every S = target / (0.357 * G) rows (~3 %)
+  int S = (int)std::floor(target / (0.357 * G));
   if (S < 1) S = 1;
   const long g = n / ((long)S * G);
   if (g < 8) return s;
@@ -195,8 +197,9 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st) {
     const int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
     sample_max_kernel<<<dim3(B, split), threads, 0, st>>>(ps.x, n, C, plan.stride, plan.lanes, plan.rows_per_group, gm);
     LAUNCHED();
-    const size_t smem = (size_t)plan.G * C * sizeof(u32);
-    sample_rank_kernel<<<B, 1024, smem, st>>>(gm, C, plan.G, plan.rank, ps.T_min, T);
+    const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
+    sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
+                                                                                        ps.T_min, T);
     LAUNCHED();
   } else {
     fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(T, P, ps.T_min);
@@ -218,7 +221,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st) {
       const long n_tiles = (long)B * tiles_per_image;
       long grid = (long)h->sm_count * MINB;
       if (grid > n_tiles) grid = n_tiles;
-      const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(u32) + 2 * (size_t)C * sizeof(u32);
+      const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
 #define RPP_LAUNCH_COLLECT(U, MB)                                                                               \
       collect_cols4_kernel<U, MB><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(                                \
           (const float4*)ps.x, T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,              \
@@ -318,7 +321,10 @@ int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const
   mp.deltas = deltas; mp.anchors = h->d_anchors; mp.boxes = boxes; mp.q = q; mp.dp = h->dp;
   mp.row0_mode = row0_mode;
   mp.out_boxes = out.boxes; mp.out_scores = out.scores; mp.out_classes = out.classes; mp.out_valid = out.valid;
-  merge_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mp);
+  size_t merge_smem = sizeof(MergeShared) + (size_t)C * M * sizeof(u64);
+  mp.keys_in_smem = merge_smem <= 200 * 1024;
+  if (!mp.keys_in_smem) merge_smem = sizeof(MergeShared);
+  merge_kernel<<<B, RPP_MERGE_NT, merge_smem, st>>>(mp);
   LAUNCHED();
   stage_mark(h, 4, st);
   return RPP_OK;
@@ -563,7 +569,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

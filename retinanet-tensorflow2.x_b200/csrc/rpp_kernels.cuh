@@ -109,22 +109,27 @@ __global__ void sample_max_kernel(const float* __restrict__ x /*[B,N,C]*/, long 
     atomicMax(&gm[((size_t)b * G + rl + i * lanes) * C + c], ord_f32(m[i]));
 }
 
+#define RPP_RANK_CPB 8   // classes per block
 __global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int rank, float T_min,
                                    float* __restrict__ T) {
-  extern __shared__ u32 s_gm[];  // [G][C]
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < G * C; i += blockDim.x) s_gm[i] = gm[(size_t)b * G * C + i];
+  extern __shared__ u32 s_gm[];  // [G][RPP_RANK_CPB]
+  const int b = blockIdx.x, c0 = blockIdx.y * RPP_RANK_CPB;
+  const int nc = C - c0 < RPP_RANK_CPB ? C - c0 : RPP_RANK_CPB;
+  for (int i = threadIdx.x; i < G * nc; i += blockDim.x) {
+    const int g = i / nc, cc = i - g * nc;
+    s_gm[g * RPP_RANK_CPB + cc] = gm[((size_t)b * G + g) * C + c0 + cc];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < G * C; i += blockDim.x) {
-    const int cc = i % C;
-    const u32 v = s_gm[i];
+  for (int i = threadIdx.x; i < G * nc; i += blockDim.x) {
+    const int g0 = i / nc, cc = i - g0 * nc;
+    const u32 v = s_gm[g0 * RPP_RANK_CPB + cc];
     int less = 0, eq = 0;
     for (int g = 0; g < G; ++g) {
-      const u32 o = s_gm[g * C + cc];
+      const u32 o = s_gm[g * RPP_RANK_CPB + cc];
       less += o < v;
       eq += o == v;
     }
-    if (less <= rank && rank < less + eq) T[(size_t)b * C + cc] = fmaxf(unord_f32(v), T_min);
+    if (less <= rank && rank < less + eq) T[(size_t)b * C + c0 + cc] = fmaxf(unord_f32(v), T_min);
   }
 }
 
@@ -143,7 +148,7 @@ __global__ void fill_kernel(float* p, size_t n, float v) {
 // ===============================================================================================================
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
@@ -164,8 +169,8 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
                      u32* __restrict__ tile_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = C4 * 4;
-  u32* s_rows = reinterpret_cast<u32*>(smem_raw);        // [C][RPP_STAGE_CAP] staged row indices
-  u32* s_cnt = s_rows + (size_t)C * RPP_STAGE_CAP;       // [C]
+  uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);   // [C][RPP_STAGE_CAP] staged (logit bits, row)
+  u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);  // [C]
   u32* s_base = s_cnt + C;                               // [C]
   __shared__ long s_tile;
   const int tid = threadIdx.x;
@@ -203,15 +208,17 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
           if (row + (long)u * lanes >= r1) m = 0u;
           mask |= m << (4 * u);
         }
-        // rare path (~1 % of elements): stage the ROW INDEX only; the value is re-read from L2 at the flush
+        // rare path (~1 % of elements).  The value is re-read by address (an L1 hit: the line was just loaded by
+        // this warp) instead of being selected out of 16 registers by a run-time index.
         while (mask) {
           const int bit = __ffs(mask) - 1;
           mask &= mask - 1u;
           const int c = cq * 4 + (bit & 3);
           const u32 r = (u32)(row + (long)(bit >> 2) * lanes);
+          const float val = __ldg(xb + (size_t)r * C + c);
           const u32 slot = atomicAdd(&s_cnt[c], 1u);
-          if (slot < RPP_STAGE_CAP) s_rows[c * RPP_STAGE_CAP + slot] = r;
-          else append_cand(cand_count, cand, CAP, pbase + c, __ldg(xb + (size_t)r * C + c), r);
+          if (slot < RPP_STAGE_CAP) s_stage[c * RPP_STAGE_CAP + slot] = make_uint2(__float_as_uint(val), r);
+          else append_cand(cand_count, cand, CAP, pbase + c, val, r);
         }
       }
     }
@@ -227,9 +234,7 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       if ((u32)r < n) {
         const u32 slot = s_base[c] + (u32)r;
-        const u32 rowi = s_rows[e];
-        if (slot < (u32)CAP)
-          cand[(pbase + c) * (size_t)CAP + slot] = make_uint2(__float_as_uint(__ldg(xb + (size_t)rowi * C + c)), rowi);
+        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[e];
       }
     }
     __syncthreads();
@@ -372,6 +377,19 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       sh->carea[tid] = area;
     }
     __syncthreads();
+    // every warp builds the suppression mask of its own tile now (pairwise IoU does not depend on what is kept):
+    // bit j of `row` = candidate j < lane of my tile overlaps me.  All warps are busy; the serial part of a round
+    // is then only the bit-chain.
+    u32 row = 0u;
+    {
+      const int tbase = warp * 32;
+      const int tcount = gcount - tbase < 32 ? gcount - tbase : 32;
+      for (int j = 0; j < tcount - 1; ++j) {
+        const float4 ob = sh->cbox[tbase + j];
+        const float oa = sh->carea[tbase + j];
+        if (j < lane && lane < tcount && iou_gt(bx, area, ob, oa, thr)) row |= 1u << j;
+      }
+    }
     int tested = 0;
     const int ntiles = (gcount + 31) >> 5;
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -383,13 +401,6 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       tested = nk;
       if (warp == tile) {
         const u32 cand_bits = __ballot_sync(RPP_FULL_MASK, alive);
-        u32 row = 0u;  // bit j: alive candidate j < lane of this tile overlaps me
-        for (int j = 0; j < 31; ++j) {
-          if (!((cand_bits >> j) & 1u)) continue;  // uniform
-          const float4 ob = sh->cbox[tile * 32 + j];
-          const float oa = sh->carea[tile * 32 + j];
-          if (alive && j < lane && iou_gt(bx, area, ob, oa, thr)) row |= 1u << j;
-        }
         u32 kept_bits = 0u;
 #pragma unroll
         for (int l = 0; l < 32; ++l) {
@@ -652,7 +663,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
     else if (MODE == RPP_CONSUME_SOFT) soft_nms_consume(P, sh, ss, b, c, p, m, consumed, false);
     else emit_consume(P, sh, p, m, consumed);
   };
-  const int want0 = MODE == RPP_CONSUME_EMIT ? RPP_NMS_CHUNK : 256;
+  const int want0 = MODE == RPP_CONSUME_EMIT ? RPP_NMS_CHUNK : 248;  // ~250 keys: a 256-wide bitonic sort
 
   const float T = P.T[p];
   u32 n_raw = P.cand_count[p];
@@ -726,6 +737,7 @@ struct MergeParams {
   const float* x; int is_logit; long N;
   const float4* deltas; const float4* anchors; const float4* boxes; int q; DecodeParams dp;
   int row0_mode;           // 0: row 0 = index 0 of the source; 1: row 0 = best of the column (per-class top-k ran)
+  int keys_in_smem;        // the C*M merge keys fit in dynamic shared memory
   float4* out_boxes;       // [B][M]
   float* out_scores;       // [B][M]
   void* out_classes;       // [B][M] f32 (combined) / i32
@@ -753,10 +765,19 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
     if (slot < scnt[c]) return make_key(key_score(sk[i]), (u32)i);
     return P.combined ? 0ull : make_key(0.0f, (u32)i);  // NMSV5 pads scores with 0.0 (A.2)
   };
+  // stage the C*M keys in shared memory once (coalesced, loads in flight), then select over them
+  u64* skeys = reinterpret_cast<u64*>(sh + 1);
+  if (P.keys_in_smem) {
+    for (int i = tid; i < C * M; i += RPP_MERGE_NT) skeys[i] = keyfn(i);
+    __syncthreads();
+  }
   u64 KB = ~0ull;
   int got = 0;
   while (got < M) {
-    const int m = select_chunk<RPP_MERGE_NT>(keyfn, C * M, KB, M - got, sh->chunk, RPP_CHUNK_CAP, &sh->sel);
+    const int m = P.keys_in_smem
+        ? select_chunk<RPP_MERGE_NT>([&](int i) { return skeys[i]; }, C * M, KB, M - got, sh->chunk, RPP_CHUNK_CAP,
+                                     &sh->sel)
+        : select_chunk<RPP_MERGE_NT>(keyfn, C * M, KB, M - got, sh->chunk, RPP_CHUNK_CAP, &sh->sel);
     if (m == 0) break;
     const int take = m < M - got ? m : M - got;
     for (int i = tid; i < take; i += RPP_MERGE_NT) sh->top[got + i] = sh->chunk[i];
