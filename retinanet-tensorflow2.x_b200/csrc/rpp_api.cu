@@ -56,6 +56,13 @@ struct Handle {
   int device;
   int sm_count;
   int force_scan;
+  int collect_ctas;      // env RPP_COLLECT_CTAS: CTAs per SM of the collect kernel (0 = automatic)
+  int overlap_hint;
+  int overlap;           // run NMS of image chunk i on a side stream under the collect stream of chunk i+1
+  int target;            // candidates per problem the sampled pre-threshold aims at (env RPP_TARGET)
+  cudaStream_t side;
+  cudaEvent_t ev_chunk[8];
+  cudaEvent_t ev_join;
   int collect_variant;   // tuning knob (env RPP_COLLECT_VARIANT): 0 = unroll 4 / 3 CTAs per SM, 1 = 4/2, 2 = 8/2
   DecodeParams dp;
   // optional per-stage timing (bench.py roofline): 5 events per call = boundaries of sample|collect|nms|merge
@@ -123,7 +130,7 @@ SamplePlan make_plan(long n, int C, int target) {
   return s;
 }
 
-const int kTarget = 1024;
+const int kTarget = 768;
 
 // Bump allocator over the caller's workspace.  Every pipeline below is written once and run twice: a dry pass
 // (no launches) sizes the workspace — rpp_workspace_bytes and the capacity check share it — then the real pass.
@@ -155,12 +162,13 @@ struct ProblemSet {
   u64* sel_key; float4* sel_box; int* sel_cnt; u64* emit_key;
 };
 
-int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st) {
+int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaStream_t st2 = nullptr,
+                    cudaEvent_t ev = nullptr) {
   const int B = ps.B, C = ps.C;
   const long n = ps.n;
   const size_t P = (size_t)B * C;
   const bool emit = ps.consumer == RPP_CONSUME_EMIT;
-  const int target = emit ? (int)std::min<long>(ps.k_lim + std::max<long>(256, ps.k_lim / 8), 1 << 30) : kTarget;
+  const int target = emit ? (int)std::min<long>(ps.k_lim + std::max<long>(256, ps.k_lim / 8), 1 << 30) : h->target;
   SamplePlan plan = make_plan(n, C, target);
   if (plan.on && emit) plan.CAP = 2 * target;
   const size_t gm_elems = plan.on ? (size_t)B * plan.G * C : 0;
@@ -219,7 +227,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st) {
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
       const int tiles_per_image = (int)((n + rows_per_tile - 1) / rows_per_tile);
       const long n_tiles = (long)B * tiles_per_image;
-      long grid = (long)h->sm_count * MINB;
+      // resident CTAs per SM: 3 fill the register file; when NMS blocks of the previous image chunk share the SMs
+      // (overlap), 2 leave them room
+      int ctas = h->collect_ctas > 0 ? h->collect_ctas : ((ev || h->overlap_hint) ? 2 : MINB);
+      if (ctas > MINB) ctas = MINB;
+      long grid = (long)h->sm_count * ctas;
       if (grid > n_tiles) grid = n_tiles;
       const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
 #define RPP_LAUNCH_COLLECT(U, MB)                                                                               \
@@ -240,6 +252,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st) {
     }
   }
   stage_mark(h, 2, st);
+  if (ev) {  // the problems (and what follows) run on the side stream, ordered after this collect
+    CUDA_OK(cudaEventRecord(ev, st));
+    CUDA_OK(cudaStreamWaitEvent(st2, ev, 0));
+    st = st2;
+  }
   // ---- stage 3: problems -------------------------------------------------------------------------------------
   ColProblemParams pp{};
   pp.x = ps.x; pp.is_logit = ps.is_logit; pp.N = n; pp.C = C;
@@ -285,9 +302,9 @@ void nms_v5_args(const rpp_config& c, float* iou_thr, float* sigma_tf) {
 }
 
 // CombinedNMS / PerClass*: per-(image, class) problems over the columns of x [B,n,C], then the per-image merge.
-int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
-                       int q, int B, long n, long k_lim, int row0_mode, int tie_is_rank, const Outputs& out,
-                       cudaStream_t st) {
+int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
+                    int q, int B, long n, long k_lim, int row0_mode, int tie_is_rank, const Outputs& out,
+                    cudaStream_t st, cudaStream_t st2, cudaEvent_t ev) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
   ProblemSet ps{};
@@ -311,8 +328,9 @@ int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const
     ps.soft_sigma_tf = sigma_tf;
     ps.M_lim = M;
   }
-  int rc = run_problem_set(h, ar, ps, st);
+  int rc = run_problem_set(h, ar, ps, st, st2, ev);
   if (rc || ar.dry) return rc;
+  if (ev) st = st2;
 
   MergeParams mp{};
   mp.C = C; mp.M = M; mp.combined = c.mode == RPP_COMBINED_NMS;
@@ -327,6 +345,41 @@ int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const
   merge_kernel<<<B, RPP_MERGE_NT, merge_smem, st>>>(mp);
   LAUNCHED();
   stage_mark(h, 4, st);
+  return RPP_OK;
+}
+
+// Splits the batch into up to 4 image chunks: the HBM-bound collect of chunk i+1 (caller's stream) runs over the
+// issue-bound NMS + merge of chunk i (the handle's side stream).  Fork/join with events only: the caller's stream
+// is ordered after everything, there is no host synchronisation.
+int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
+                       int q, int B, long n, long k_lim, int row0_mode, int tie_is_rank, const Outputs& out,
+                       cudaStream_t st) {
+  const int C = h->cfg.num_classes, M = h->cfg.max_detections;
+  int nchunks = 1;
+  if (h->overlap && !h->timing && B >= 16) nchunks = B >= 32 ? 4 : 2;
+  if (nchunks == 1) return per_class_chunk(h, ar, x, is_logit, deltas, boxes, q, B, n, k_lim, row0_mode, tie_is_rank,
+                                           out, st, nullptr, nullptr);
+  int b0 = 0;
+  for (int i = 0; i < nchunks; ++i) {
+    const int bc = (B - b0) / (nchunks - i);
+    Outputs o{};
+    if (!ar.dry) {
+      o.boxes = out.boxes + (size_t)b0 * M;
+      o.scores = out.scores + (size_t)b0 * M;
+      o.classes = (char*)out.classes + (size_t)b0 * M * 4;   // f32 / i32 classes in the per-class modes
+      o.valid = out.valid + b0;
+    }
+    int rc = per_class_chunk(h, ar, x ? x + (size_t)b0 * n * C : nullptr, is_logit,
+                             deltas ? deltas + (size_t)b0 * n : nullptr,
+                             boxes ? boxes + (size_t)b0 * n * q : nullptr, q, bc, n, k_lim, row0_mode, tie_is_rank, o,
+                             st, h->side, h->ev_chunk[i]);
+    if (rc) return rc;
+    b0 += bc;
+  }
+  if (!ar.dry) {
+    CUDA_OK(cudaEventRecord(h->ev_join, h->side));
+    CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
+  }
   return RPP_OK;
 }
 
@@ -523,6 +576,23 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   }
   h->timing = 0;
   h->timed_calls = 0;
+  {
+    const char* v = getenv("RPP_OVERLAP");
+    h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_COLLECT_CTAS");
+    h->collect_ctas = v ? atoi(v) : 0;
+    h->overlap_hint = 0;
+    v = getenv("RPP_TARGET");
+    h->target = v ? atoi(v) : kTarget;
+    if (h->target < 64) h->target = 64;
+    if (h->target > 3072) h->target = 3072;
+  }
+  h->side = nullptr;
+  h->ev_join = nullptr;
+  for (int i = 0; i < 8; ++i) h->ev_chunk[i] = nullptr;
+  CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) CUDA_OK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
   CUDA_OK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
 
   AnchorParams& ap = h->ap;
@@ -584,6 +654,9 @@ int rpp_destroy(void* handle) {
   cudaFree(h->d_anchors);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   host_path_free(h);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int i = 0; i < 8; ++i) if (h->ev_chunk[i]) cudaEventDestroy(h->ev_chunk[i]);
   delete h;
   return RPP_OK;
 }
