@@ -258,7 +258,10 @@ class GenerateDetections(Layer):
                  soft_nms_sigma=None,
                  num_classes=None,
                  mode='CombinedNMS',
+                 soft_ignores_iou_threshold=True,
                  **kwargs):
+        # soft_ignores_iou_threshold (not in the reference): True = NonMaxSuppressionV5 of TF >= 2.3, where the IoU
+        # threshold is ignored when soft_nms_sigma > 0; False = the older kernel form.
 
         if mode not in GenerateDetections._SUPPORTED_NMS_MODES:
             raise AssertionError(
@@ -275,6 +278,7 @@ class GenerateDetections(Layer):
         self.soft_nms_sigma = soft_nms_sigma
         self.num_classes = num_classes
         self.mode = mode
+        self.soft_ignores_iou_threshold = soft_ignores_iou_threshold
         self._handles = {}
 
     def _handle(self, num_classes):
@@ -286,7 +290,8 @@ class GenerateDetections(Layer):
                                 "(soft NMS modes need soft_nms_sigma)")
             h = _Handle(num_classes=num_classes, mode=self.mode, iou_threshold=self.iou_threshold,
                         score_threshold=self.score_threshold, soft_nms_sigma=self.soft_nms_sigma or 0.0,
-                        max_detections=self.max_detections)
+                        max_detections=self.max_detections,
+                        soft_ignores_iou_threshold=self.soft_ignores_iou_threshold)
             self._handles[num_classes] = h
         return h
 

@@ -1,0 +1,207 @@
+"""GPU parity at BASELINE.json's other configurations (reduced batch so the oracle finishes in seconds) and over the
+edge of the parameter space.  Everything goes through the C ABI via the reference-shaped layers."""
+import numpy as np
+import pytest
+
+from _util import image_mismatches, make_params, oracle_detect, synth_inputs, to_numpy
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+def _gpu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _fused(params):
+    from retinanet.model.builder import ModelBuilder
+    return ModelBuilder(params, run_mode='export').add_post_processing_stage(None).layers[-1]
+
+
+def _run(ref, p, B, seed=0, dist='dense', logits=None):
+    C = p.architecture.head.num_classes
+    layer = _fused(p)
+    N = layer.handle(C).num_anchors
+    lg, deltas = synth_inputs(B, N, C, seed=seed, dist=dist)
+    if logits is not None:
+        lg = logits(lg)
+    got = to_numpy(layer({'class_logits': _gpu(lg), 'encoded_boxes': _gpu(deltas)}))
+    exp = oracle_detect(ref, p, lg, deltas, threads=16)
+    return got, exp
+
+
+# ---- BASELINE.json configs --------------------------------------------------------------------------------------
+def test_config1_combined_640(ref):
+    p = make_params(640, num_classes=80, mode='CombinedNMS', pre_nms_top_k=5000, filter_per_class=True)
+    got, exp = _run(ref, p, 1, seed=1)
+    assert image_mismatches(got, exp) == []
+
+
+def test_config1_random_init_head_has_no_detections(ref):
+    """configs[0]: random-init weights -> logits ~ -log(99) + N(0, 0.01^2) -> p ~ 0.01 < 0.05."""
+    p = make_params(640, num_classes=80, mode='CombinedNMS')
+    got, exp = _run(ref, p, 1, seed=2, logits=lambda x: (x * 0.01 - 4.59512).astype(np.float32))
+    assert image_mismatches(got, exp) == [] and got['valid_detections'].tolist() == [0]
+
+
+def test_config3_global_soft_640(ref):
+    p = make_params(640, num_classes=80, mode='GlobalSoftNMS', pre_nms_top_k=5000, filter_per_class=False,
+                    soft_nms_sigma=0.5)
+    for dist in ('dense', 'sparse'):
+        got, exp = _run(ref, p, 2, seed=3, dist=dist)
+        assert image_mismatches(got, exp) == [], dist
+
+
+def test_config4_combined_1024(ref):
+    p = make_params(1024, num_classes=80, mode='CombinedNMS', pre_nms_top_k=5000, filter_per_class=True)
+    got, exp = _run(ref, p, 2, seed=4)
+    assert image_mismatches(got, exp) == []
+
+
+def test_config5_global_hard_320_c5(ref):
+    p = make_params(320, num_classes=5, mode='GlobalHardNMS', pre_nms_top_k=5000, filter_per_class=False)
+    for dist in ('dense', 'sparse'):
+        got, exp = _run(ref, p, 16, seed=5, dist=dist)
+        assert image_mismatches(got, exp) == [], dist
+
+
+def test_per_class_soft_640(ref):
+    p = make_params(640, num_classes=80, mode='PerClassSoftNMS', pre_nms_top_k=5000, filter_per_class=True)
+    got, exp = _run(ref, p, 2, seed=6)
+    assert image_mismatches(got, exp) == []
+
+
+# ---- parameter edges ----------------------------------------------------------------------------------------------
+EDGE = [
+    dict(mode='PerClassHardNMS', max_detections=1),
+    dict(mode='PerClassHardNMS', max_detections=300),
+    dict(mode='CombinedNMS', max_detections=7, pre_nms_top_k=3),
+    dict(mode='PerClassHardNMS', pre_nms_top_k=1),
+    dict(mode='PerClassSoftNMS', pre_nms_top_k=2, max_detections=5),
+    dict(mode='PerClassHardNMS', score_threshold=0.0),
+    dict(mode='CombinedNMS', score_threshold=0.9),
+    dict(mode='PerClassHardNMS', score_threshold=0.9999),
+    dict(mode='PerClassHardNMS', iou_threshold=0.0),
+    dict(mode='CombinedNMS', iou_threshold=1.0),
+    dict(mode='PerClassSoftNMS', soft_nms_sigma=0.1),
+    dict(mode='PerClassSoftNMS', soft_nms_sigma=4.0, max_detections=40),
+    dict(mode='GlobalSoftNMS', soft_nms_sigma=0.05, filter_per_class=False),
+    dict(mode='GlobalSoftNMS', soft_nms_sigma=0.0, filter_per_class=False),     # sigma 0 -> hard with IoU 1.0
+    dict(mode='PerClassSoftNMS', soft_nms_sigma=0.0),                           # sigma 0 -> plain hard NMS
+    dict(mode='GlobalHardNMS', filter_per_class=False, max_detections=250, pre_nms_top_k=120),   # k < M
+    dict(mode='GlobalHardNMS', pre_nms_top_k=-1, score_threshold=0.7),
+]
+
+
+@pytest.mark.parametrize('inf', EDGE, ids=lambda d: ','.join('{}={}'.format(k, v) for k, v in d.items()))
+def test_parameter_edges(ref, inf):
+    kw = dict(pre_nms_top_k=200, filter_per_class=True, max_detections=30)
+    kw.update(inf)
+    p = make_params(96, num_classes=4, **kw)
+    got, exp = _run(ref, p, 3, seed=21)
+    assert image_mismatches(got, exp) == []
+
+
+@pytest.mark.parametrize('H,W,lo,hi,C', [(96, 160, 3, 7, 3), (224, 224, 3, 6, 2), (64, 64, 4, 5, 1), (40, 72, 3, 7, 7)])
+def test_shapes_and_levels(ref, H, W, lo, hi, C):
+    for mode, fpc in [('PerClassHardNMS', True), ('GlobalSoftNMS', False)]:
+        p = make_params(H, W, num_classes=C, mode=mode, pre_nms_top_k=150, filter_per_class=fpc, max_detections=25)
+        p.architecture.feature_fusion.min_level = lo
+        p.architecture.feature_fusion.max_level = hi
+        layer = _fused(p)
+        N = layer.handle(C).num_anchors
+        logits, deltas = synth_inputs(2, N, C, seed=H + W)
+        got = to_numpy(layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}))
+        ap = p.anchor_params
+        anchors, _ = ref.anchors(H, W, lo, hi, ap.areas, ap.aspect_ratios, ap.scales)
+        assert len(anchors) == N
+        exp = ref.detect(logits, deltas, anchors, H, W, mode, pre_nms_top_k=150, filter_per_class=fpc,
+                         max_detections=25, threads=4)
+        assert image_mismatches(got, exp) == [], mode
+
+
+def test_scale_box_targets_and_huge_deltas(ref):
+    """box_variance scaling on; deltas large enough to push boxes far outside [0,1] and to overflow exp()."""
+    p = make_params(96, num_classes=3, mode='CombinedNMS', pre_nms_top_k=100, max_detections=20)
+    p.encoder_params.scale_box_targets = True
+    layer = _fused(p)
+    N = layer.handle(3).num_anchors
+    rng = np.random.default_rng(8)
+    logits = rng.standard_normal((2, N, 3)).astype(np.float32)
+    deltas = (rng.standard_normal((2, N, 4)) * 20).astype(np.float32)
+    deltas[0, :50, 2:] = 500.0      # exp(0.2 * 500) overflows fp32 -> inf sized boxes
+    got = to_numpy(layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}))
+    exp = oracle_detect(ref, p, logits, deltas)
+    assert np.array_equal(got['valid_detections'], exp['valid_detections'])
+    assert np.array_equal(got['classes'], exp['classes']) and np.array_equal(got['scores'], exp['scores'])
+    assert np.array_equal(np.nan_to_num(got['boxes'], nan=-7.0), np.nan_to_num(exp['boxes'], nan=-7.0))
+
+
+def test_old_tf_soft_kernel_form(ref):
+    """soft_ignores_iou_threshold=False: the pre-2.3 NonMaxSuppressionV5 also hard-drops IoU > threshold."""
+    from retinanet.model.layers import GenerateDetections
+    rng = np.random.default_rng(9)
+    ctr, wh = rng.uniform(0.2, 0.8, (2, 300, 2)), rng.uniform(0.05, 0.4, (2, 300, 2))
+    boxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(np.float32)
+    scores = (rng.uniform(0, 1, (2, 300, 3)) ** 2).astype(np.float32)
+    for mode in ('GlobalSoftNMS', 'PerClassSoftNMS'):
+        gd = GenerateDetections(0.5, 0.05, 250, 0.5, 3, mode, soft_ignores_iou_threshold=False)
+        got = to_numpy(gd({'scores': _gpu(scores), 'boxes': _gpu(boxes)}))
+        exp = ref.generate_detections(mode, scores, boxes, max_detections=250, soft_ignores_iou_threshold=False)
+        new = ref.generate_detections(mode, scores, boxes, max_detections=250, soft_ignores_iou_threshold=True)
+        for key in exp:
+            assert np.array_equal(got[key], exp[key]), (mode, key)
+        if mode == 'GlobalSoftNMS':   # the two kernel forms really differ on this input (threshold 0.5 is live)
+            assert not np.array_equal(exp['scores'], new['scores'])
+
+
+def test_dense_nms_flipped_and_degenerate_boxes(ref):
+    """GenerateDetections on arbitrary dense boxes: flipped corners are canonicalised for IoU but emitted as given;
+    zero-area boxes never suppress or get suppressed."""
+    from retinanet.model.layers import GenerateDetections
+    rng = np.random.default_rng(10)
+    n = 500
+    ctr, wh = rng.uniform(0.2, 0.8, (1, n, 2)), rng.uniform(0.05, 0.3, (1, n, 2))
+    boxes = np.concatenate([ctr - wh / 2, ctr + wh / 2], -1).astype(np.float32)
+    boxes[0, ::7] = boxes[0, ::7][:, [2, 3, 0, 1]]          # flipped
+    boxes[0, ::11, 2] = boxes[0, ::11, 0]                   # zero width
+    scores = rng.uniform(0, 1, (1, n, 2)).astype(np.float32)
+    for mode in ('CombinedNMS', 'PerClassHardNMS', 'PerClassSoftNMS', 'GlobalSoftNMS', 'GlobalHardNMS'):
+        gd = GenerateDetections(0.4, 0.1, 60, 0.5, 2, mode)
+        got = to_numpy(gd({'scores': _gpu(scores), 'boxes': _gpu(boxes)}))
+        exp = ref.generate_detections(mode, scores, boxes, iou_threshold=0.4, score_threshold=0.1, max_detections=60)
+        for key in exp:
+            assert np.array_equal(got[key], exp[key]), (mode, key)
+
+
+def test_host_entry_matches_device_entry():
+    """rpp_detect_host (pinned host buffers, chunked H2D) == rpp_detect."""
+    import ctypes
+    from retinanet import _native
+    p = make_params(320, num_classes=8, mode='PerClassHardNMS', pre_nms_top_k=1000, max_detections=50)
+    layer = _fused(p)
+    h = layer.handle(8)
+    B, N, M = 5, h.num_anchors, 50
+    logits, deltas = synth_inputs(B, N, 8, seed=12)
+    dev = to_numpy(layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}))
+    hl, hd = torch.from_numpy(logits).pin_memory(), torch.from_numpy(deltas).pin_memory()
+    ob, os_ = torch.empty((B, M, 4)).pin_memory(), torch.empty((B, M)).pin_memory()
+    oc, ov = torch.empty((B, M), dtype=torch.int32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory()
+    _native.check(_native.lib().rpp_detect_host(h.ptr, 0, hd.data_ptr(), hl.data_ptr(), B, ob.data_ptr(),
+                                                os_.data_ptr(), oc.data_ptr(), ov.data_ptr()))
+    assert np.array_equal(ob.numpy(), dev['boxes']) and np.array_equal(os_.numpy(), dev['scores'])
+    assert np.array_equal(oc.numpy(), dev['classes']) and np.array_equal(ov.numpy(), dev['valid_detections'])
+
+
+def test_determinism_and_input_immutability():
+    p = make_params(320, num_classes=8, mode='PerClassHardNMS')
+    layer = _fused(p)
+    N = layer.handle(8).num_anchors
+    logits, deltas = synth_inputs(3, N, 8, seed=13)
+    lg, dl = _gpu(logits), _gpu(deltas)
+    a = to_numpy(layer({'class_logits': lg, 'encoded_boxes': dl}))
+    for _ in range(3):
+        b = to_numpy(layer({'class_logits': lg, 'encoded_boxes': dl}))
+        for key in a:
+            assert np.array_equal(a[key], b[key])
+    assert np.array_equal(lg.cpu().numpy(), logits) and np.array_equal(dl.cpu().numpy(), deltas)
