@@ -113,13 +113,17 @@ SamplePlan make_plan(long n, int C, int target) {
   // rows per group g = -ln(0.7) * n / target, i.e. one sampled row every S = target / (0.357 * G) rows (~3 %)
   int S = (int)std::floor(target / (0.357 * G));
   if (S < 1) S = 1;
-  const long g = n / ((long)S * G);
-  if (g < 8) return s;
+  long g = n / ((long)S * G);
+  if (g < 8) {   // the target is a large fraction of the column: sample denser, accept a lower quantile
+    g = 8;
+    S = (int)(n / (g * G));
+    if (S < 1) return s;
+  }
   const double q = std::pow(1.0 - (double)target / (double)n, (double)g);
+  if (q < 0.05 || q > 0.97 || G < 8) return s;
   int rank = (int)std::floor(q * G);
   if (rank < 2) rank = 2;
   if (rank > G - 3) rank = G - 3;
-  if (G < 8) return s;
   s.on = true;
   s.stride = S;
   s.G = G;
@@ -168,7 +172,9 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   const long n = ps.n;
   const size_t P = (size_t)B * C;
   const bool emit = ps.consumer == RPP_CONSUME_EMIT;
-  const int target = emit ? (int)std::min<long>(ps.k_lim + std::max<long>(256, ps.k_lim / 8), 1 << 30) : h->target;
+  // emission must reach k_lim from the list (falling short means an exact scan of the whole column): aim well
+  // above k_lim; the estimate's 1-sigma error is ~20 %
+  const int target = emit ? (int)std::min<long>(ps.k_lim + ps.k_lim / 2 + 512, 1 << 28) : h->target;
   SamplePlan plan = make_plan(n, C, target);
   if (plan.on && emit) plan.CAP = 2 * target;
   const size_t gm_elems = plan.on ? (size_t)B * plan.G * C : 0;
@@ -242,6 +248,22 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       else if (h->collect_variant == 1) RPP_LAUNCH_COLLECT(4, 2);
       else RPP_LAUNCH_COLLECT(8, 2);
 #undef RPP_LAUNCH_COLLECT
+      LAUNCHED();
+    } else if (C == 1 && n % 4 == 0 && ((uintptr_t)ps.x % 16) == 0) {
+      const long n4 = n / 4;
+      const int UNROLL = 4;
+      long f4_per_tile = (long)RPP_COLLECT_NT * UNROLL * 4;   // 32 K elements per tile
+      if (plan.on) {   // keep ~128 expected hits per tile (queue capacity 1024)
+        const long want = (long)(128.0 * n / target / 4);
+        f4_per_tile = std::max<long>((long)RPP_COLLECT_NT * UNROLL,
+                                     std::min<long>(want, (long)RPP_COLLECT_NT * UNROLL * 16));
+        f4_per_tile = f4_per_tile / ((long)RPP_COLLECT_NT * UNROLL) * ((long)RPP_COLLECT_NT * UNROLL);
+      }
+      const int tiles_per_image = (int)((n4 + f4_per_tile - 1) / f4_per_tile);
+      long grid = std::min<long>((long)h->sm_count * 3, (long)B * tiles_per_image);
+      collect_flat4_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>((const float4*)ps.x, T, cand_count, cand,
+                                                                        plan.CAP, B, n4, (int)f4_per_tile,
+                                                                        tiles_per_image, tile_counter);
       LAUNCHED();
     } else {
       const size_t tot = (size_t)B * n * C;

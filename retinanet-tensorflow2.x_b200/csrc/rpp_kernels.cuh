@@ -241,6 +241,65 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
   }
 }
 
+// Single-column variant (C == 1: the flat anchors x classes axis of the global filter, or the row maxima of the
+// Global* modes): x [B, n], n % 4 == 0, one threshold per image.  Same structure: streaming LDG.128, hits queued in
+// shared memory, one global atomic per tile.
+#define RPP_FLAT_QCAP 1024
+template <int UNROLL>
+__global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
+collect_flat4_kernel(const float4* __restrict__ x4 /*[B, n/4]*/, const float* __restrict__ T /*[B]*/,
+                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long n4,
+                     int f4_per_tile, int tiles_per_image, u32* __restrict__ tile_counter) {
+  __shared__ uint2 s_q[RPP_FLAT_QCAP];
+  __shared__ u32 s_qn, s_base;
+  __shared__ long s_tile;
+  const int tid = threadIdx.x;
+  const long n_tiles = (long)B * tiles_per_image;
+  for (;;) {
+    if (tid == 0) { s_tile = (long)atomicAdd(tile_counter, 1u); s_qn = 0u; }
+    __syncthreads();
+    const long tile = s_tile;
+    if (tile >= n_tiles) break;
+    const int b = (int)(tile / tiles_per_image);
+    const long f0 = (long)(tile % tiles_per_image) * f4_per_tile;
+    const long f1 = f0 + f4_per_tile < n4 ? f0 + f4_per_tile : n4;
+    const float t = __ldg(T + b);
+    const float4* src = x4 + (size_t)b * n4;
+    for (long f = f0 + tid; f < f1; f += (long)RPP_COLLECT_NT * UNROLL) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long ff = f + (long)u * RPP_COLLECT_NT;
+        v[u] = ff < f1 ? ld_stream_f4(src + ff) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const long ff = f + (long)u * RPP_COLLECT_NT;
+        if (ff >= f1) continue;
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (e[i] >= t) {
+            const u32 idx = (u32)(ff * 4 + i);
+            const u32 slot = atomicAdd(&s_qn, 1u);
+            if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(e[i]), idx);
+            else append_cand(cand_count, cand, CAP, (size_t)b, e[i], idx);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const u32 nq = s_qn < RPP_FLAT_QCAP ? s_qn : RPP_FLAT_QCAP;
+    if (tid == 0) s_base = nq ? atomicAdd(&cand_count[b], nq) : 0u;
+    __syncthreads();
+    for (u32 i = tid; i < nq; i += RPP_COLLECT_NT) {
+      const u32 slot = s_base + i;
+      if (slot < (u32)CAP) cand[(size_t)b * CAP + slot] = s_q[i];
+    }
+    __syncthreads();
+  }
+}
+
 // generic C (C % 4 != 0, or unaligned base): one element per thread step
 __global__ void collect_cols1_kernel(const float* __restrict__ x, const float* __restrict__ T,
                                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N,

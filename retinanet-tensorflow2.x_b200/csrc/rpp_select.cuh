@@ -32,9 +32,15 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
   // pass 1: population below the bound
   u32 cnt = 0;
   u64 mx = 0ull, mn = ~0ull;
-  for (int i = tid; i < n; i += NT) {
-    const u64 k = key(i);
-    if (k != 0ull && k < KB) { ++cnt; mx = k > mx ? k : mx; mn = k < mn ? k : mn; }
+  for (int i0 = tid; i0 < n; i0 += 4 * NT) {   // 4 independent key loads in flight per thread
+    u64 k4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const u64 k = k4[u];
+      if (k != 0ull && k < KB) { ++cnt; mx = k > mx ? k : mx; mn = k < mn ? k : mn; }
+    }
   }
   block_cnt_max_min<NT>(cnt, mx, mn, &sc->bs);
   if (cnt == 0) return 0;
@@ -56,10 +62,16 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
       const int nb = 1 << bits;
       for (int i = tid; i < nb; i += NT) sc->hist[i] = 0;
       __syncthreads();
-      for (int i = tid; i < n; i += NT) {
-        const u64 k = key(i);
-        if (k != 0ull && k < KB && k >= base && (top_shift >= 64 || ((k - base) >> top_shift) == 0ull))
-          atomicAdd(&sc->hist[(u32)((k - base) >> shift)], 1u);
+      for (int i0 = tid; i0 < n; i0 += 4 * NT) {
+        u64 k4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const u64 k = k4[u];
+          if (k != 0ull && k < KB && k >= base && (top_shift >= 64 || ((k - base) >> top_shift) == 0ull))
+            atomicAdd(&sc->hist[(u32)((k - base) >> shift)], 1u);
+        }
       }
       __syncthreads();
       // find d* = the highest bin whose suffix count reaches w_eff
@@ -99,11 +111,17 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
   // pass 3: compaction of {lo <= key < KB}
   if (tid == 0) sc->m = 0;
   __syncthreads();
-  for (int i = tid; i < n; i += NT) {
-    const u64 k = key(i);
-    if (k != 0ull && k < KB && k >= lo) {
-      const u32 slot = atomicAdd(&sc->m, 1u);
-      if (slot < (u32)CC) chunk[slot] = k;
+  for (int i0 = tid; i0 < n; i0 += 4 * NT) {
+    u64 k4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const u64 k = k4[u];
+      if (k != 0ull && k < KB && k >= lo) {
+        const u32 slot = atomicAdd(&sc->m, 1u);
+        if (slot < (u32)CC) chunk[slot] = k;
+      }
     }
   }
   __syncthreads();
