@@ -56,6 +56,7 @@ struct Handle {
   int device;
   int sm_count;
   int force_scan;
+  int two_pass;          // env RPP_TWO_PASS (default 1): probe / bound / finish scheme of the per-class modes
   int collect_ctas;      // env RPP_COLLECT_CTAS: CTAs per SM of the collect kernel (0 = automatic)
   int overlap_hint;
   int overlap;           // run NMS of image chunk i on a side stream under the collect stream of chunk i+1
@@ -162,6 +163,7 @@ struct ProblemSet {
   long k_lim; int M_lim; int M;
   int clip_before; float iou_threshold; float score_threshold; float T_min;
   float soft_sigma_tf; int tie_is_rank;
+  int two_pass_m1;         // > 0: probe with this many kept per class, bound per image, finish (per-class modes)
   // out (workspace)
   u64* sel_key; float4* sel_box; int* sel_cnt; u64* emit_key;
 };
@@ -200,6 +202,12 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       r_meta = ar.take<uint2>(P * (size_t)r_cap);
       r_box = ar.take<float4>(P * (size_t)r_cap);
     }
+  }
+  float* bound = nullptr;
+  float* stop_L = nullptr;
+  if (ps.two_pass_m1 > 0) {
+    bound = ar.take<float>(P);
+    stop_L = ar.take<float>((size_t)B);
   }
   if (ar.dry) return RPP_OK;
 
@@ -297,12 +305,27 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   pp.r_key = r_key; pp.r_meta = r_meta; pp.r_box = r_box; pp.r_cap = r_cap;
   pp.emit_key = ps.emit_key;
   const size_t smem_nms = align_up(nms_shared_bytes(pp.M_lim), 16);
-  if (ps.consumer == RPP_CONSUME_HARD)
-    col_problem_kernel<RPP_CONSUME_HARD><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
-  else if (ps.consumer == RPP_CONSUME_SOFT)
-    col_problem_kernel<RPP_CONSUME_SOFT><<<(unsigned)P, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
-  else
-    col_problem_kernel<RPP_CONSUME_EMIT><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+  auto launch = [&](void) {
+    if (ps.consumer == RPP_CONSUME_HARD)
+      col_problem_kernel<RPP_CONSUME_HARD><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+    else if (ps.consumer == RPP_CONSUME_SOFT)
+      col_problem_kernel<RPP_CONSUME_SOFT><<<(unsigned)P, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
+    else
+      col_problem_kernel<RPP_CONSUME_EMIT><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+  };
+  pp.pass = 0; pp.M_cap = pp.M_lim; pp.want0 = 248;   // ~250 keys: a 256-wide bitonic sort
+  pp.bound = bound; pp.stop_L = stop_L;
+  if (ps.two_pass_m1 > 0) {
+    const int m1 = ps.two_pass_m1;
+    pp.pass = 1; pp.M_cap = m1; pp.want0 = std::max(24, 6 * m1);
+    launch();
+    LAUNCHED();
+    perclass_bound_kernel<<<B, 256, (size_t)C * m1 * sizeof(float), st>>>(ps.sel_key, ps.sel_cnt, C, ps.M, m1, ps.M,
+                                                                         stop_L);
+    LAUNCHED();
+    pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 248;
+  }
+  launch();
   LAUNCHED();
   stage_mark(h, 3, st);
   return RPP_OK;
@@ -349,6 +372,11 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
     ps.iou_threshold = iou_thr;
     ps.soft_sigma_tf = sigma_tf;
     ps.M_lim = M;
+  }
+  // cross-class bound: the merge keeps only the M best of C * M_lim boxes, so a class rarely needs more than a few
+  {
+    const int m1 = std::min(ps.M_lim, (M + C - 1) / C + 3);
+    ps.two_pass_m1 = (h->two_pass && C > 1 && 2 * m1 < ps.M_lim && (long)C * m1 <= 8192) ? m1 : 0;
   }
   int rc = run_problem_set(h, ar, ps, st, st2, ev);
   if (rc || ar.dry) return rc;
@@ -601,6 +629,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_TWO_PASS");
+    h->two_pass = v ? atoi(v) : 1;
     v = getenv("RPP_COLLECT_CTAS");
     h->collect_ctas = v ? atoi(v) : 0;
     h->overlap_hint = 0;

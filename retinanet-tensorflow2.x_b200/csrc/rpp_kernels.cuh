@@ -340,12 +340,21 @@ struct ColProblemParams {
   float iou_threshold;
   float score_threshold;
   float T_min;             // raw pre-image of the score threshold (candidates have raw >= T_min)
-  int M_lim;               // max kept per problem
+  int M_lim;               // max kept per problem (also sizes the kept arrays in shared memory)
+  // Two-pass scheme of the per-class modes (DESIGN.md "cross-class bound"): pass 1 (probe) keeps at most M_cap = m1
+  // boxes per class and records `bound` = score of its last kept box (-inf when the class is exhausted); a tiny
+  // kernel turns the probes of an image into stop_L = a lower bound of the image's M-th best final score; pass 2
+  // re-runs only the classes whose bound >= stop_L, stopping at the first candidate below stop_L.
+  int pass;                // 0 single pass, 1 probe, 2 finish
+  int M_cap;               // kept limit of this pass
+  int want0;               // size of the first chunk
+  float* bound;            // [P]
+  const float* stop_L;     // [B] or nullptr
   long k_lim;              // max candidates consumed (pre_nms_top_k after clamping; N when unfiltered)
   int M;                   // stride of the sel_* arrays
   // candidate lists
   const float* T;          // [P] thresholds used by the collect pass
-  const u32* cand_count;   // [P]
+  u32* cand_count;         // [P]; bit 31 = the list was already converted to keys in place (long lists)
   uint2* cand;             // [P][CAP]
   int CAP;
   int force_scan;          // debug: ignore the lists, use the exact column scan only
@@ -419,8 +428,17 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
   float4* kbox = nms_kbox(sh);
   float* karea = nms_karea(sh, P.M_lim);
   const long room = P.k_lim - consumed;
-  const int m_eff = (long)m < room ? m : (int)room;
+  int m_eff = (long)m < room ? m : (int)room;
   const float thr = P.iou_threshold;
+  bool cut = false;
+  if (P.pass == 2) {  // candidates below the image's bound can never reach the final top-M: stop there
+    const float L = P.stop_L[b];
+    int ok = 0;
+    for (int i0 = 0; i0 < m_eff; i0 += RPP_NMS_NT)
+      ok += __syncthreads_count(i0 + tid < m_eff && key_score(sh->chunk[i0 + tid]) >= L);
+    cut = ok < m_eff;
+    m_eff = ok;
+  }
   for (int g0 = 0; g0 < m_eff; g0 += RPP_NMS_NT) {
     const int gcount = m_eff - g0 < RPP_NMS_NT ? m_eff - g0 : RPP_NMS_NT;
     bool alive = tid < gcount;
@@ -467,7 +485,7 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
           if (((cand_bits >> l) & 1u) && (r & kept_bits) == 0u) kept_bits |= 1u << l;
         }
         int nnew = __popc(kept_bits);
-        const int room_k = P.M_lim - nk;
+        const int room_k = P.M_cap - nk;
         while (nnew > room_k) {  // keep only the first room_k
           kept_bits &= ~(1u << (31 - __clz(kept_bits)));
           --nnew;
@@ -481,7 +499,7 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
         }
         if (lane == 0) {
           sh->nkept = nk + nnew;
-          if (nk + nnew >= P.M_lim) sh->done = 1;
+          if (nk + nnew >= P.M_cap) sh->done = 1;
         }
       }
       __syncthreads();
@@ -490,7 +508,7 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
     if (sh->done) break;
   }
   consumed += m_eff;
-  if (consumed >= P.k_lim) {
+  if (consumed >= P.k_lim || cut) {
     __syncthreads();
     if (tid == 0) sh->done = 1;
     __syncthreads();
@@ -596,7 +614,7 @@ __device__ void soft_nms_consume(const ColProblemParams& P, NmsShared* sh, SoftS
       int rcount = ss->rcount;
       int pos = 0;
       for (;;) {
-        if (nsel >= P.M_lim) { if (lane == 0) sh->done = 1; break; }
+        if (nsel >= P.M_cap) { if (lane == 0) sh->done = 1; break; }
         // stream head
         u64 head = 0ull, head_cmp = 0ull;
         if (pos < gcount) {
@@ -620,6 +638,11 @@ __device__ void soft_nms_consume(const ColProblemParams& P, NmsShared* sh, SoftS
         const int r_i = owner ? __shfl_sync(RPP_FULL_MASK, best_i, __ffs(owner) - 1) : -1;
         if (head == 0ull && (!final || wbest == 0ull)) break;  // need more stream / everything drained
         const bool from_stream = head != 0ull && head_cmp > wbest;
+        if (P.pass == 2 && key_score(from_stream ? head_cmp : wbest) < P.stop_L[b]) {
+          // the queue maximum is below the image's bound: nothing this class selects from now on can matter
+          if (lane == 0) sh->done = 1;
+          break;
+        }
         float score, area;
         float4 box;
         u32 row, tie;
@@ -709,6 +732,10 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   const int tid = threadIdx.x;
   const size_t p = blockIdx.x;
   const int b = (int)(p / P.C), c = (int)(p % P.C);
+  if (MODE != RPP_CONSUME_EMIT && P.pass == 2) {
+    const float bd = P.bound[p];
+    if (bd == -INFINITY || bd < P.stop_L[b]) return;   // the probe already holds everything that can matter
+  }
   if (tid == 0) {
     sh->nkept = 0;
     sh->done = 0;
@@ -722,10 +749,12 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
     else if (MODE == RPP_CONSUME_SOFT) soft_nms_consume(P, sh, ss, b, c, p, m, consumed, false);
     else emit_consume(P, sh, p, m, consumed);
   };
-  const int want0 = MODE == RPP_CONSUME_EMIT ? RPP_NMS_CHUNK : 248;  // ~250 keys: a 256-wide bitonic sort
+  const int want0 = MODE == RPP_CONSUME_EMIT ? RPP_NMS_CHUNK : P.want0;
 
   const float T = P.T[p];
   u32 n_raw = P.cand_count[p];
+  const bool converted = (n_raw & 0x80000000u) != 0u;   // a previous pass left u64 keys in the list
+  n_raw &= 0x7fffffffu;
   const bool overflow = n_raw > (u32)P.CAP;
   int n_list = (overflow || P.force_scan) ? 0 : (int)n_raw;
   const bool list_complete = !(T > P.T_min);  // the list holds every element above the score threshold
@@ -738,12 +767,16 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
     uint2* lst = P.cand + p * (size_t)P.CAP;
     u64* gkeys = reinterpret_cast<u64*>(lst);
     u64* keys = n_list <= RPP_LIST_SMEM ? sh->lkeys : gkeys;
-    for (int i = tid; i < n_list; i += RPP_NMS_NT) {
-      const uint2 e = lst[i];
-      const float s = col_score(P, __uint_as_float(e.x));
-      // consumable now: strictly above everything that was NOT collected (those score <= s_edge)
-      const bool ok = s > P.score_threshold && (list_complete || s > s_edge);
-      keys[i] = ok ? make_key(s, e.y) : 0ull;
+    if (!converted) {
+      for (int i = tid; i < n_list; i += RPP_NMS_NT) {
+        const uint2 e = lst[i];
+        const float s = col_score(P, __uint_as_float(e.x));
+        // consumable now: strictly above everything that was NOT collected (those score <= s_edge)
+        const bool ok = s > P.score_threshold && (list_complete || s > s_edge);
+        keys[i] = ok ? make_key(s, e.y) : 0ull;
+      }
+      // long lists are converted in place (global memory): remember it for the finish pass
+      if (keys == gkeys && tid == 0) P.cand_count[p] = n_raw | 0x80000000u;
     }
     __syncthreads();
     u64 KB = ~0ull;
@@ -777,7 +810,43 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   if (MODE == RPP_CONSUME_SOFT) {
     if (!sh->done) soft_nms_consume(P, sh, ss, b, c, p, 0, consumed, true);  // stream over: drain the queue
   }
-  if (MODE != RPP_CONSUME_EMIT && tid == 0) P.sel_cnt[p] = sh->nkept;
+  if (MODE != RPP_CONSUME_EMIT && tid == 0) {
+    const int nk = sh->nkept;
+    P.sel_cnt[p] = nk;
+    if (P.pass == 1)   // stopped by the probe cap: later boxes of this class score <= the last kept one
+      P.bound[p] = (nk >= P.M_cap && nk > 0) ? key_score(P.sel_key[p * P.M + nk - 1]) : -INFINITY;
+  }
+}
+
+// Per image: stop_L = the Mtop-th best score among the boxes the probes kept (-inf if there are fewer): every one of
+// them is a real final candidate, so the image's Mtop-th best FINAL score is >= stop_L.
+__global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int* __restrict__ sel_cnt, int C, int M,
+                                      int m1, int Mtop, float* __restrict__ stop_L) {
+  extern __shared__ float s_sc[];  // [C * m1]
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  const int n_all = C * m1;
+  for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+    const int c = i / m1, slot = i - c * m1;
+    s_sc[i] = slot < sel_cnt[(size_t)b * C + c] ? key_score(sel_key[((size_t)b * C + c) * M + slot]) : -INFINITY;
+  }
+  if (threadIdx.x == 0) { s_n = 0; stop_L[b] = -INFINITY; }
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < n_all; i += blockDim.x) local += s_sc[i] > -INFINITY;
+  if (local) atomicAdd(&s_n, local);
+  __syncthreads();
+  if (s_n < Mtop) return;
+  for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+    const float v = s_sc[i];
+    if (!(v > -INFINITY)) continue;
+    int rank = 0;
+    for (int j = 0; j < n_all; ++j) {
+      const float o = s_sc[j];
+      rank += (o > v) || (o == v && j < i);
+    }
+    if (rank == Mtop - 1) stop_L[b] = v;
+  }
 }
 
 // ===============================================================================================================

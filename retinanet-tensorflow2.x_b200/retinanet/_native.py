@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libretinapost.so')
+LIB_PATH = os.environ.get('RPP_LIB') or os.path.join(os.path.dirname(_HERE), 'libretinapost.so')   # RPP_LIB: tuning builds
 
 MODES = ['CombinedNMS', 'GlobalSoftNMS', 'GlobalHardNMS', 'PerClassSoftNMS', 'PerClassHardNMS']
 
