@@ -56,6 +56,7 @@ struct Handle {
   int device;
   int sm_count;
   int force_scan;
+  int probe_extra;       // env RPP_PROBE_EXTRA: boxes per class kept by the probe beyond ceil(M / C)
   int two_pass;          // env RPP_TWO_PASS (default 1): probe / bound / finish scheme of the per-class modes
   int collect_ctas;      // env RPP_COLLECT_CTAS: CTAs per SM of the collect kernel (0 = automatic)
   int overlap_hint;
@@ -375,7 +376,7 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   }
   // cross-class bound: the merge keeps only the M best of C * M_lim boxes, so a class rarely needs more than a few
   {
-    const int m1 = std::min(ps.M_lim, (M + C - 1) / C + 3);
+    const int m1 = std::min(ps.M_lim, (M + C - 1) / C + h->probe_extra);
     ps.two_pass_m1 = (h->two_pass && C > 1 && 2 * m1 < ps.M_lim && (long)C * m1 <= 8192) ? m1 : 0;
   }
   int rc = run_problem_set(h, ar, ps, st, st2, ev);
@@ -388,6 +389,7 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   mp.x = x; mp.is_logit = is_logit; mp.N = n;
   mp.deltas = deltas; mp.anchors = h->d_anchors; mp.boxes = boxes; mp.q = q; mp.dp = h->dp;
   mp.row0_mode = row0_mode;
+  mp.score_nonneg = c.score_threshold >= 0.0f;
   mp.out_boxes = out.boxes; mp.out_scores = out.scores; mp.out_classes = out.classes; mp.out_valid = out.valid;
   size_t merge_smem = sizeof(MergeShared) + (size_t)C * M * sizeof(u64);
   mp.keys_in_smem = merge_smem <= 200 * 1024;
@@ -629,6 +631,9 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_PROBE_EXTRA");
+    h->probe_extra = v ? atoi(v) : 3;
+    if (h->probe_extra < 1) h->probe_extra = 1;
     v = getenv("RPP_TWO_PASS");
     h->two_pass = v ? atoi(v) : 1;
     v = getenv("RPP_COLLECT_CTAS");

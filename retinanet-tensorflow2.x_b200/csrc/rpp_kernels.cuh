@@ -319,7 +319,9 @@ __global__ void collect_cols1_kernel(const float* __restrict__ x, const float* _
 // K3  per-(image, class) problem kernel: lazy exact selection + greedy hard NMS
 //     (CombinedNMS per-class stage;  PerClassHardNMS = NonMaxSuppressionV5 hard, A.2).
 // ===============================================================================================================
+#ifndef RPP_NMS_NT
 #define RPP_NMS_NT 128
+#endif
 #define RPP_CHUNK_CAP 1024   // merge kernel
 #define RPP_NMS_CHUNK 512
 #define RPP_LIST_SMEM 1536
@@ -674,6 +676,7 @@ __device__ void soft_nms_consume(const ColProblemParams& P, NmsShared* sh, SoftS
           }
         }
         if (from_stream) ++pos;
+        __syncwarp();             // every lane has read its R entry before lane 0 rewrites R below
         if (score == original) {  // select
           if (lane == 0) {
             kbox[nsel] = box;
@@ -762,8 +765,50 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   if (!list_complete) s_edge = col_score(P, T);
   if (overflow || P.force_scan) s_edge = INFINITY;
 
-  // ---- phase A: the collected list -------------------------------------------------------------------------
-  if (n_list > 0) {
+  // ---- phase A0: the head of the list, selected on RAW logits ------------------------------------------------
+  // The consumer usually wants a few dozen candidates, so evaluating the binary64 sigmoid for the whole list is
+  // wasted work.  The score is monotone in the logit: the top-`want` of the list by (logit desc, index asc) is a
+  // complete prefix of the score order for every score strictly above S(lowest selected logit) =: e0 (the same
+  // "edge rule" as for the collect threshold, one level down).  Only those are scored, re-keyed by (score, index),
+  // sorted and consumed here; if the consumer wants more, phase A continues below the bound e0 with the full list.
+  u64 KB_A = ~0ull;          // phase A consumes keys below this bound
+  bool skip_A = false;
+  if (MODE != RPP_CONSUME_EMIT && P.is_logit && n_list > 0 && n_list <= RPP_LIST_SMEM && !converted) {
+    const uint2* lst = P.cand + p * (size_t)P.CAP;
+    for (int i = tid; i < n_list; i += RPP_NMS_NT) {
+      const uint2 e = lst[i];
+      sh->lkeys[i] = ((u64)ord_f32(__uint_as_float(e.x)) << 32) | (u64)(0xffffffffu - e.y);
+    }
+    __syncthreads();
+    u64 KBr = ~0ull;
+    const int m = select_chunk<RPP_NMS_NT>([&](int i) { return sh->lkeys[i]; }, n_list, KBr, want0, sh->chunk,
+                                           RPP_NMS_CHUNK, &sh->sel, /*sort=*/false);
+    // m >= 1 (the list is not empty).  Everything outside the chunk has a raw key < KBr (the cut), i.e. a logit <=
+    // the float encoded in the cut's upper half.
+    const bool whole = m == n_list;
+    float e0;
+    if (whole) e0 = list_complete ? -INFINITY : s_edge;
+    else e0 = sigmoid_f32(unord_f32((u32)(KBr >> 32)));
+    const int P2 = next_pow2(m < 2 ? 2 : m);
+    for (int i = tid; i < P2; i += RPP_NMS_NT) {
+      u64 k = 0ull;
+      if (i < m) {
+        const u64 rk = sh->chunk[i];
+        const float sc = sigmoid_f32(unord_f32((u32)(rk >> 32)));
+        if (sc > P.score_threshold && sc > e0) k = make_key(sc, key_tie(rk));
+      }
+      sh->chunk[i] = k;
+    }
+    __syncthreads();
+    bitonic_sort_desc<RPP_NMS_NT>(sh->chunk, P2);   // true order: (score desc, index asc); invalid keys sink
+    int mv = 0;
+    for (int i0 = 0; i0 < m; i0 += RPP_NMS_NT) mv += __syncthreads_count(i0 + tid < m && sh->chunk[i0 + tid] != 0ull);
+    if (mv > 0) consume(mv);
+    if (whole) skip_A = true;                       // nothing of the list is left that phase A may consume
+    else KB_A = (u64)(ord_f32(e0) + 1u) << 32;      // phase A: scores <= e0
+  }
+  // ---- phase A: the collected list, keyed by score ----------------------------------------------------------
+  if (n_list > 0 && !skip_A && !sh->done && consumed < P.k_lim) {
     uint2* lst = P.cand + p * (size_t)P.CAP;
     u64* gkeys = reinterpret_cast<u64*>(lst);
     u64* keys = n_list <= RPP_LIST_SMEM ? sh->lkeys : gkeys;
@@ -779,7 +824,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
       if (keys == gkeys && tid == 0) P.cand_count[p] = n_raw | 0x80000000u;
     }
     __syncthreads();
-    u64 KB = ~0ull;
+    u64 KB = KB_A;
     int want = want0;
     while (!sh->done && consumed < P.k_lim) {
       const int m = select_chunk<RPP_NMS_NT>([&](int i) { return keys[i]; }, n_list, KB, want, sh->chunk,
@@ -866,6 +911,7 @@ struct MergeParams {
   const float4* deltas; const float4* anchors; const float4* boxes; int q; DecodeParams dp;
   int row0_mode;           // 0: row 0 = index 0 of the source; 1: row 0 = best of the column (per-class top-k ran)
   int keys_in_smem;        // the C*M merge keys fit in dynamic shared memory
+  int score_nonneg;        // score_threshold >= 0: every kept score is positive
   float4* out_boxes;       // [B][M]
   float* out_scores;       // [B][M]
   void* out_classes;       // [B][M] f32 (combined) / i32
@@ -893,10 +939,21 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
     if (slot < scnt[c]) return make_key(key_score(sk[i]), (u32)i);
     return P.combined ? 0ull : make_key(0.0f, (u32)i);  // NMSV5 pads scores with 0.0 (A.2)
   };
-  // stage the C*M keys in shared memory once (coalesced, loads in flight), then select over them
+  // stage the C*M keys in shared memory once, then select over them.  The per-class counts go to shared memory
+  // first so that only filled slots cost a global load (after the cross-class bound most classes hold a few boxes).
   u64* skeys = reinterpret_cast<u64*>(sh + 1);
   if (P.keys_in_smem) {
-    for (int i = tid; i < C * M; i += RPP_MERGE_NT) skeys[i] = keyfn(i);
+    int* s_cnt = reinterpret_cast<int*>(sh->top);   // top[] is not live yet: C <= 2048 ints fit
+    const bool cnt_smem = C <= 2048;
+    if (cnt_smem) {
+      for (int c = tid; c < C; c += RPP_MERGE_NT) s_cnt[c] = scnt[c];
+      __syncthreads();
+    }
+    for (int i = tid; i < C * M; i += RPP_MERGE_NT) {
+      const int c = i / M, slot = i - c * M;
+      const int n = cnt_smem ? s_cnt[c] : scnt[c];
+      skeys[i] = slot < n ? make_key(key_score(sk[i]), (u32)i) : (P.combined ? 0ull : make_key(0.0f, (u32)i));
+    }
     __syncthreads();
   }
   u64 KB = ~0ull;
@@ -954,7 +1011,10 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
   // of the column when the per-class top-k ran first and the class kept nothing (row0_mode 1).
   int last_c = -1;
   float4 last_box = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = 0; i < M; ++i) {
+  // pads have score 0 and sort after every positive score: they can only sit at positions >= valid (for a
+  // negative score threshold a 0-score pad may precede a negative kept score, hence min(valid, first pad))
+  const int first = P.score_nonneg ? valid : 0;
+  for (int i = first; i < M; ++i) {
     const int c = sh->need[i];  // uniform across the block
     if (c < 0) continue;
     if (c != last_c) {

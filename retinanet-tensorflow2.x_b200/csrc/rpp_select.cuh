@@ -11,7 +11,9 @@
 #pragma once
 #include "rpp_common.cuh"
 
+#ifndef RPP_RADIX_BITS
 #define RPP_RADIX_BITS 10
+#endif
 #define RPP_RADIX_BINS (1 << RPP_RADIX_BITS)
 
 template <int NT>
@@ -27,7 +29,8 @@ struct SelectScratch {
 // lowered to the smallest key returned.  m == 0 <=> the domain holds no key below KB.  m >= min(want/4, remaining).
 // All threads of the block must call; chunk must hold next_pow2(CC) keys.
 template <int NT, class KeyFn>
-__device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int CC, SelectScratch<NT>* sc) {
+__device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int CC, SelectScratch<NT>* sc,
+                            bool sort = true) {
   const int tid = threadIdx.x;
   // pass 1: population below the bound
   u32 cnt = 0;
@@ -82,11 +85,22 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
       u32 local = 0;
       for (int j = 0; j < bpt; ++j)
         if (b0 + j < nb) local += sc->hist[b0 + j];
-      sc->part[tid] = local;
-      __syncthreads();
-      // suffix over threads (NT <= 1024: a serial walk by warp 0 lanes is cheap enough: each lane sums a slice)
+      // suffix over threads
       u32 above = 0;  // sum of bins owned by higher threads
-      for (int t = tid + 1; t < NT; ++t) above += sc->part[t];
+      {
+        // inclusive suffix sum inside the warp, then add the totals of the higher warps
+        u32 v = local;
+        const int lane = tid & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const u32 t = __shfl_down_sync(RPP_FULL_MASK, v, o);
+          if (lane + o < 32) v += t;
+        }
+        if (lane == 0) sc->part[tid >> 5] = v;   // warp total (part[] is reused: NT/32 <= NT)
+        __syncthreads();
+        for (int w = (tid >> 5) + 1; w < NT / 32; ++w) above += sc->part[w];
+        above += v - local;
+      }
       if (above < w_eff && above + local >= w_eff) {
         u32 run = above;
         for (int j = bpt - 1; j >= 0; --j) {
@@ -130,7 +144,7 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
   const int P2 = next_pow2(m < 2 ? 2 : m);
   for (int i = m + tid; i < P2; i += NT) chunk[i] = 0ull;
   __syncthreads();
-  bitonic_sort_desc<NT>(chunk, P2);
+  if (sort) bitonic_sort_desc<NT>(chunk, P2);
   KB = lo;
   return m;
 }
