@@ -111,6 +111,15 @@ int rpp_detect(void* handle, const float* d_deltas_BN4, const float* d_logits_BN
                float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
                void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The fused path reading the model's PER-LEVEL head outputs in place: FuseDetections (postprocessing_ops.py:15-56)
+ * only reshapes each level's NHWC tensor [B,H_l,W_l,A*C] / [B,H_l,W_l,A*4] to [B,n_l,C] / [B,n_l,4] and concatenates
+ * them; here the levels (min_level..max_level, in order) are consumed where they lie, which saves that copy.
+ * Covers CombinedNMS / PerClass*NMS with the per-class filter or no filter, num_classes % 4 == 0, 16-byte aligned
+ * level tensors; returns RPP_EINVAL otherwise (fuse and call rpp_detect). */
+int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const float* const* d_logits_levels, int B,
+                      float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Same, from HOST buffers (the serving call of export.py:233-253 / evaluate_saved_model.py: tensors arrive from
  * the host and detections are consumed on the host).  Copies H2D in image chunks overlapped with the kernels,
  * then D2H of the four outputs; synchronises before returning.  Pinned host memory is recommended.

@@ -158,8 +158,9 @@ bool is_per_class_mode(int mode) {
 // One set of P = B * C "column problems": columns of x [B, n, C] -> lazily sorted candidates -> consumer.
 struct ProblemSet {
   // in
-  const float* x; int is_logit; int B; long n; int C;
+  const float* x; int is_logit; int B; long n; int C;   // fused tensors ...
   const float4* deltas; const float4* boxes; int q;
+  const Levels* levels;    // ... or the per-level pieces (x / deltas then unused)
   int consumer;            // RPP_CONSUME_*
   long k_lim; int M_lim; int M;
   int clip_before; float iou_threshold; float score_threshold; float T_min;
@@ -212,13 +213,25 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   if (ar.dry) return RPP_OK;
 
+  Levels lv;
+  memset(&lv, 0, sizeof(lv));
+  if (ps.levels) lv = *ps.levels;
+  else { lv.L = 1; lv.off[0] = 0; lv.off[1] = n; lv.x[0] = ps.x; lv.d[0] = ps.deltas; }
+  bool aligned = true;
+  for (int l = 0; l < lv.L; ++l) aligned = aligned && ((uintptr_t)lv.x[l] % 16) == 0;
+
   // ---- stage 0/1: thresholds ---------------------------------------------------------------------------------
   CUDA_OK(cudaMemsetAsync(cand_count, 0, zero_bytes, st));
   stage_mark(h, 0, st);
   if (plan.on && !h->force_scan) {
     const int threads = (int)align_up((size_t)plan.lanes * C, 32);
     const int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
-    sample_max_kernel<<<dim3(B, split), threads, 0, st>>>(ps.x, n, C, plan.stride, plan.lanes, plan.rows_per_group, gm);
+    if (lv.L > 1)
+      sample_max_kernel<true><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
+                                                                  plan.rows_per_group, gm);
+    else
+      sample_max_kernel<false><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
+                                                                   plan.rows_per_group, gm);
     LAUNCHED();
     const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
     sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
@@ -231,7 +244,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   stage_mark(h, 1, st);
   // ---- stage 2: collect --------------------------------------------------------------------------------------
   if (!h->force_scan) {
-    if (C % 4 == 0 && ((uintptr_t)ps.x % 16) == 0 && C / 4 <= RPP_COLLECT_NT) {
+    if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT) {
       const int C4 = C / 4;
       const int lanes = RPP_COLLECT_NT / C4;
       const int UNROLL = h->collect_variant == 2 ? 8 : 4;
@@ -240,7 +253,12 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
-      const int tiles_per_image = (int)((n + rows_per_tile - 1) / rows_per_tile);
+      int tiles_per_image = 0;
+      for (int l = 0; l < lv.L; ++l) {
+        lv.tile_off[l] = tiles_per_image;
+        tiles_per_image += (int)((lv.off[l + 1] - lv.off[l] + rows_per_tile - 1) / rows_per_tile);
+      }
+      lv.tile_off[lv.L] = tiles_per_image;
       const long n_tiles = (long)B * tiles_per_image;
       // resident CTAs per SM: 3 fill the register file; when NMS blocks of the previous image chunk share the SMs
       // (overlap), 2 leave them room
@@ -251,13 +269,18 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
 #define RPP_LAUNCH_COLLECT(U, MB)                                                                               \
       collect_cols4_kernel<U, MB><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(                                \
-          (const float4*)ps.x, T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,              \
+          (const float4*)lv.x[0], T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,           \
           tiles_per_image, tile_counter)
-      if (h->collect_variant == 0) RPP_LAUNCH_COLLECT(4, 3);
+      if (lv.L > 1)
+        collect_cols4_levels_kernel<4, 3><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(
+            lv, T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile, tiles_per_image, tile_counter);
+      else if (h->collect_variant == 0) RPP_LAUNCH_COLLECT(4, 3);
       else if (h->collect_variant == 1) RPP_LAUNCH_COLLECT(4, 2);
       else RPP_LAUNCH_COLLECT(8, 2);
 #undef RPP_LAUNCH_COLLECT
       LAUNCHED();
+    } else if (lv.L > 1) {
+      return fail(RPP_EINVAL, "per-level inputs need num_classes % 4 == 0 and 16-byte aligned level tensors");
     } else if (C == 1 && n % 4 == 0 && ((uintptr_t)ps.x % 16) == 0) {
       const long n4 = n / 4;
       const int UNROLL = 4;
@@ -290,8 +313,8 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   // ---- stage 3: problems -------------------------------------------------------------------------------------
   ColProblemParams pp{};
-  pp.x = ps.x; pp.is_logit = ps.is_logit; pp.N = n; pp.C = C;
-  pp.deltas = ps.deltas; pp.anchors = h->d_anchors; pp.boxes = ps.boxes; pp.q = ps.q; pp.dp = h->dp;
+  pp.lv = lv; pp.is_logit = ps.is_logit; pp.N = n; pp.C = C;
+  pp.anchors = h->d_anchors; pp.boxes = ps.boxes; pp.q = ps.q; pp.dp = h->dp;
   pp.clip_before = ps.clip_before;
   pp.iou_threshold = ps.iou_threshold;
   pp.score_threshold = ps.score_threshold;
@@ -350,12 +373,13 @@ void nms_v5_args(const rpp_config& c, float* iou_thr, float* sigma_tf) {
 // CombinedNMS / PerClass*: per-(image, class) problems over the columns of x [B,n,C], then the per-image merge.
 int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
                     int q, int B, long n, long k_lim, int row0_mode, int tie_is_rank, const Outputs& out,
-                    cudaStream_t st, cudaStream_t st2, cudaEvent_t ev) {
+                    cudaStream_t st, cudaStream_t st2, cudaEvent_t ev, const Levels* levels = nullptr) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
   ProblemSet ps{};
   ps.x = x; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = C;
   ps.deltas = deltas; ps.boxes = boxes; ps.q = q;
+  ps.levels = levels;
   ps.k_lim = k_lim; ps.M = M;
   ps.score_threshold = c.score_threshold;
   ps.T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
@@ -386,8 +410,11 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   MergeParams mp{};
   mp.C = C; mp.M = M; mp.combined = c.mode == RPP_COMBINED_NMS;
   mp.sel_key = ps.sel_key; mp.sel_box = ps.sel_box; mp.sel_cnt = ps.sel_cnt;
-  mp.x = x; mp.is_logit = is_logit; mp.N = n;
-  mp.deltas = deltas; mp.anchors = h->d_anchors; mp.boxes = boxes; mp.q = q; mp.dp = h->dp;
+  memset(&mp.lv, 0, sizeof(mp.lv));
+  if (levels) mp.lv = *levels;
+  else { mp.lv.L = 1; mp.lv.off[1] = n; mp.lv.x[0] = x; mp.lv.d[0] = deltas; }
+  mp.is_logit = is_logit; mp.N = n;
+  mp.anchors = h->d_anchors; mp.boxes = boxes; mp.q = q; mp.dp = h->dp;
   mp.row0_mode = row0_mode;
   mp.score_nonneg = c.score_threshold >= 0.0f;
   mp.out_boxes = out.boxes; mp.out_scores = out.scores; mp.out_classes = out.classes; mp.out_valid = out.valid;
@@ -405,12 +432,12 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
 // is ordered after everything, there is no host synchronisation.
 int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
                        int q, int B, long n, long k_lim, int row0_mode, int tie_is_rank, const Outputs& out,
-                       cudaStream_t st) {
+                       cudaStream_t st, const Levels* levels = nullptr) {
   const int C = h->cfg.num_classes, M = h->cfg.max_detections;
   int nchunks = 1;
-  if (h->overlap && !h->timing && B >= 16) nchunks = B >= 32 ? 4 : 2;
+  if (h->overlap && !h->timing && B >= 16 && !levels) nchunks = B >= 32 ? 4 : 2;
   if (nchunks == 1) return per_class_chunk(h, ar, x, is_logit, deltas, boxes, q, B, n, k_lim, row0_mode, tie_is_rank,
-                                           out, st, nullptr, nullptr);
+                                           out, st, nullptr, nullptr, levels);
   int b0 = 0;
   for (int i = 0; i < nchunks; ++i) {
     const int bc = (B - b0) / (nchunks - i);
@@ -528,12 +555,20 @@ int topk_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, i
 
 // add_post_processing_stage fused: logits + deltas -> detections
 int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* logits, int B, const Outputs& out,
-                    cudaStream_t st) {
+                    cudaStream_t st, const Levels* levels = nullptr) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes;
   const long N = h->N;
   const bool filtered = c.pre_nms_top_k > 0;
   const bool per_class = is_per_class_mode(c.mode);
+  if (levels) {
+    if (!per_class || (filtered && !c.filter_per_class) || C % 4 != 0)
+      return fail(RPP_EINVAL, "rpp_detect_levels covers CombinedNMS / PerClass*NMS with the per-class filter or no "
+                              "filter and num_classes % 4 == 0; fuse the levels and call rpp_detect otherwise");
+    const long k = filtered ? std::min<long>(c.pre_nms_top_k, N) : N;
+    return per_class_pipeline(h, ar, nullptr, 1, nullptr, nullptr, 1, B, N, k, filtered ? 1 : 0, filtered ? 1 : 0, out,
+                              st, levels);
+  }
   if (!per_class && filtered && c.filter_per_class)
     return fail(RPP_ECOMBO, "Global* NMS modes need inference.filter_per_class=false (per-class filtered boxes are "
                             "4-D; the reference fails with a rank error)");
@@ -699,6 +734,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols4_levels_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   *handle = h;
@@ -861,6 +897,31 @@ static int detect_impl(Handle* h, const float* d_deltas, const float* d_logits, 
   const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     return detect_pipeline(h, ar, (const float4*)d_deltas, d_logits, B, out, (cudaStream_t)stream);
+  });
+}
+
+int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const float* const* d_logits_levels, int B,
+                      float* d_boxes_out, float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws,
+                      size_t ws_bytes, void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !d_deltas_levels || !d_logits_levels || B <= 0) return fail(RPP_EINVAL, "bad argument");
+  if (h->levels > RPP_MAX_LEVELS) return fail(RPP_EINVAL, "too many levels");
+  Levels lv;
+  memset(&lv, 0, sizeof(lv));
+  lv.L = h->levels;
+  for (int l = 0; l < h->levels; ++l) {
+    if (!d_deltas_levels[l] || !d_logits_levels[l]) return fail(RPP_EINVAL, "null level pointer");
+    if (((uintptr_t)d_deltas_levels[l] % 16) || ((uintptr_t)d_logits_levels[l] % 16))
+      return fail(RPP_EINVAL, "level tensors must be 16-byte aligned");
+    lv.off[l] = h->ap.bounds[l];
+    lv.x[l] = d_logits_levels[l];
+    lv.d[l] = (const float4*)d_deltas_levels[l];
+  }
+  lv.off[h->levels] = h->ap.bounds[h->levels];
+  const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
+  return with_arena(ws, ws_bytes, [&](Arena& ar) {
+    return detect_pipeline(h, ar, nullptr, nullptr, B, out, (cudaStream_t)stream, &lv);
   });
 }
 

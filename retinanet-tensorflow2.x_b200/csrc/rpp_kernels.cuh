@@ -5,6 +5,33 @@
 #include "rpp_select.cuh"
 
 // ===============================================================================================================
+// The [B, N, C] logit tensor and the [B, N, 4] delta tensor, either fused (L = 1) or as the per-level head outputs
+// the model produces ([B, H_l, W_l, A*C] NHWC = [B, n_l, C]; FuseDetections, postprocessing_ops.py:15-56, only
+// concatenates them).  Reading the levels in place saves the 1.65 GB concat copy per batch.
+// ===============================================================================================================
+#define RPP_MAX_LEVELS 8
+struct Levels {
+  int L;
+  long off[RPP_MAX_LEVELS + 1];        // cumulative rows: level l holds rows [off[l], off[l+1])
+  const float* x[RPP_MAX_LEVELS];      // [B, n_l, C]
+  const float4* d[RPP_MAX_LEVELS];     // [B, n_l] float4 (may be null for score tensors)
+  int tile_off[RPP_MAX_LEVELS + 1];    // collect kernel: cumulative tiles per image
+};
+__device__ __forceinline__ int lv_find(const Levels& lv, long r) {
+  int l = 0;
+  while (l + 1 < lv.L && r >= lv.off[l + 1]) ++l;
+  return l;
+}
+__device__ __forceinline__ const float* lv_row(const Levels& lv, int b, long r, int C) {
+  const int l = lv_find(lv, r);
+  return lv.x[l] + ((size_t)b * (lv.off[l + 1] - lv.off[l]) + (r - lv.off[l])) * C;
+}
+__device__ __forceinline__ float4 lv_delta(const Levels& lv, int b, long r) {
+  const int l = lv_find(lv, r);
+  return lv.d[l][(size_t)b * (lv.off[l + 1] - lv.off[l]) + (r - lv.off[l])];
+}
+
+// ===============================================================================================================
 // K0a  anchors — AnchorBoxGenerator (dataloader/anchor_generator.py:24-104).  One thread per anchor.
 // ===============================================================================================================
 struct AnchorParams {
@@ -84,7 +111,8 @@ __global__ void decode_kernel(const float4* __restrict__ deltas, const float4* _
 // ===============================================================================================================
 #define RPP_GPT 8   // groups per thread; G = lanes * RPP_GPT
 
-__global__ void sample_max_kernel(const float* __restrict__ x /*[B,N,C]*/, long N, int C, int stride, int lanes,
+template <bool LEVELS>
+__global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stride, int lanes,
                                   int rounds, u32* __restrict__ gm /*[B][G][C]*/) {
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
   const int c = threadIdx.x % C, rl = threadIdx.x / C;
@@ -93,13 +121,13 @@ __global__ void sample_max_kernel(const float* __restrict__ x /*[B,N,C]*/, long 
   float m[RPP_GPT];
 #pragma unroll
   for (int i = 0; i < RPP_GPT; ++i) m[i] = -INFINITY;
-  const float* base = x + (size_t)b * N * C + c;
+  const float* base = lv.x[0] + (size_t)b * N * C + c;   // fused tensor (LEVELS == false)
   for (int r = split; r < rounds; r += nsplit) {
     float v[RPP_GPT];
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) {
       const long s = (long)r * G + rl + i * lanes;  // sampled row index; group = rl + i * lanes
-      v[i] = __ldg(base + (size_t)(s * stride) * C);
+      v[i] = LEVELS ? __ldg(lv_row(lv, b, s * stride, C) + c) : __ldg(base + (size_t)(s * stride) * C);
     }
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) m[i] = fmaxf(m[i], v[i]);
@@ -241,6 +269,96 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
   }
 }
 
+// Per-level variant (rpp_detect_levels): same kernel, tiles are (image, level, row range).
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(RPP_COLLECT_NT, MINB)
+collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const float* __restrict__ T /*[B*C]*/,
+                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C4,
+                     int lanes /*row lanes per block*/, int rows_per_tile, int tiles_per_image,
+                     u32* __restrict__ tile_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = C4 * 4;
+  uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);   // [C][RPP_STAGE_CAP] staged (logit bits, row)
+  u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);  // [C]
+  u32* s_base = s_cnt + C;                               // [C]
+  __shared__ long s_tile;
+  const int tid = threadIdx.x;
+  const int cq = tid % C4, rl = tid / C4;
+  const bool active = rl < lanes;
+  const long n_tiles = (long)B * tiles_per_image;
+  for (;;) {
+    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    __syncthreads();
+    const long tile = s_tile;
+    if (tile >= n_tiles) break;
+    const int b = (int)(tile / tiles_per_image);
+    const int t_img = (int)(tile % tiles_per_image);
+    // rows are LOCAL to the level inside the loop; `goff` turns them into fused row indices when staged
+    long n_l, goff, r0;
+    const float* __restrict__ xb;
+    {
+      int l = 0;
+      while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
+      n_l = lv.off[l + 1] - lv.off[l];
+      goff = lv.off[l];
+      r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
+      xb = lv.x[l] + (size_t)b * n_l * C;
+    }
+    const long r1 = r0 + rows_per_tile < n_l ? r0 + rows_per_tile : n_l;
+    const size_t pbase = (size_t)b * C;
+    if (active) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(T + (size_t)b * C) + cq);
+      const float4* __restrict__ src = reinterpret_cast<const float4*>(xb) + cq;
+      for (long row = r0 + rl; row < r1; row += (long)lanes * UNROLL) {
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const long r = row + (long)u * lanes;
+          v[u] = r < r1 ? ld_stream_f4(src + (size_t)r * C4)
+                        : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        u32 mask = 0u;  // bit 4u+i: component i of load u passes its class threshold (NaN never passes >=)
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          u32 m = (v[u].x >= t4.x ? 1u : 0u) | (v[u].y >= t4.y ? 2u : 0u) | (v[u].z >= t4.z ? 4u : 0u) |
+                  (v[u].w >= t4.w ? 8u : 0u);
+          if (row + (long)u * lanes >= r1) m = 0u;
+          mask |= m << (4 * u);
+        }
+        // rare path (~1 % of elements).  The value is re-read by address (an L1 hit: the line was just loaded by
+        // this warp) instead of being selected out of 16 registers by a run-time index.
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const int c = cq * 4 + (bit & 3);
+          const u32 r = (u32)(row + (long)(bit >> 2) * lanes);
+          const float val = __ldg(xb + (size_t)r * C + c);
+          const u32 slot = atomicAdd(&s_cnt[c], 1u);
+          if (slot < RPP_STAGE_CAP) s_stage[c * RPP_STAGE_CAP + slot] = make_uint2(__float_as_uint(val), (u32)goff + r);
+          else append_cand(cand_count, cand, CAP, pbase + c, val, (u32)goff + r);
+        }
+      }
+    }
+    __syncthreads();
+    // flush: one global atomic per class that staged anything
+    for (int c = tid; c < C; c += RPP_COLLECT_NT) {
+      const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+      s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+    }
+    __syncthreads();
+    for (int e = tid; e < C * RPP_STAGE_CAP; e += RPP_COLLECT_NT) {
+      const int c = e / RPP_STAGE_CAP, r = e - c * RPP_STAGE_CAP;
+      const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+      if ((u32)r < n) {
+        const u32 slot = s_base[c] + (u32)r;
+        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Single-column variant (C == 1: the flat anchors x classes axis of the global filter, or the row maxima of the
 // Global* modes): x [B, n], n % 4 == 0, one threshold per image.  Same structure: streaming LDG.128, hits queued in
 // shared memory, one global atomic per tile.
@@ -328,12 +446,11 @@ __global__ void collect_cols1_kernel(const float* __restrict__ x, const float* _
 
 struct ColProblemParams {
   // source: columns of a [B, N, C] tensor
-  const float* x;          // logits (is_logit = 1) or scores (is_logit = 0)
+  Levels lv;               // x: logits (is_logit = 1) or scores (is_logit = 0); d: box deltas (fused path)
   int is_logit;
   long N;                  // rows per image
   int C;
   // boxes: decoded on demand (deltas + anchors) or gathered from a dense [B, N, q, 4] tensor
-  const float4* deltas;    // [B,N] (fused) or nullptr
   const float4* anchors;   // [N]
   const float4* boxes;     // dense boxes (stage-wise) or nullptr
   int q;
@@ -402,7 +519,7 @@ __device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int 
     const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;  // boxes[:, min(q-1, c)] (:440)
     return P.boxes[((size_t)b * P.N + row) * P.q + qi];
   }
-  return decode_box(P.deltas[(size_t)b * P.N + row], P.anchors[row], P.dp);
+  return decode_box(lv_delta(P.lv, b, row), P.anchors[row], P.dp);
 }
 
 // Greedy hard NMS over one sorted chunk (m keys in sh->chunk).  The chunk is walked in groups of RPP_NMS_NT
@@ -837,9 +954,8 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   // ---- phase B: exact scan of the column for everything at or below the edge ---------------------------------
   if (!sh->done && consumed < P.k_lim && (!list_complete || overflow || P.force_scan)) {
     u64 KB = (s_edge == INFINITY) ? ~0ull : ((u64)(ord_f32(s_edge) + 1u) << 32);
-    const float* col = P.x + (size_t)b * P.N * P.C + c;
     auto keyfn = [&](int i) -> u64 {
-      const float raw = __ldg(col + (size_t)i * P.C);
+      const float raw = __ldg(lv_row(P.lv, b, i, P.C) + c);
       if (!(raw >= P.T_min)) return 0ull;
       const float s = col_score(P, raw);
       return s > P.score_threshold ? make_key(s, (u32)i) : 0ull;
@@ -907,8 +1023,8 @@ struct MergeParams {
   const float4* sel_box;   // [B*C][M]
   const int* sel_cnt;      // [B*C]
   // pad box of a class with no candidates = its row 0 (:453 gather of index 0): needs the column argmax
-  const float* x; int is_logit; long N;
-  const float4* deltas; const float4* anchors; const float4* boxes; int q; DecodeParams dp;
+  Levels lv; int is_logit; long N;
+  const float4* anchors; const float4* boxes; int q; DecodeParams dp;
   int row0_mode;           // 0: row 0 = index 0 of the source; 1: row 0 = best of the column (per-class top-k ran)
   int keys_in_smem;        // the C*M merge keys fit in dynamic shared memory
   int score_nonneg;        // score_threshold >= 0: every kept score is positive
@@ -1021,10 +1137,9 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
       u32 row = 0;
       if (P.row0_mode == 1) {
         // argmax of the column under (score desc, index asc)
-        const float* col = P.x + (size_t)b * P.N * P.C + c;
         u64 best = 0ull;
         for (long r = tid; r < P.N; r += RPP_MERGE_NT) {
-          const float raw = __ldg(col + (size_t)r * P.C);
+          const float raw = __ldg(lv_row(P.lv, b, r, P.C) + c);
           const u64 k = ((u64)ord_f32(raw) << 32) | (u64)(0xffffffffu - (u32)r);
           best = k > best ? k : best;
         }
@@ -1045,7 +1160,7 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
           const float raw_lo = unord_f32(hi_o);
           u64 best2 = 0ull;
           for (long r = tid; r < P.N; r += RPP_MERGE_NT) {
-            const float raw = __ldg(col + (size_t)r * P.C);
+            const float raw = __ldg(lv_row(P.lv, b, r, P.C) + c);
             if (raw >= raw_lo) { const u64 k = (u64)(0xffffffffu - (u32)r); best2 = k > best2 ? k : best2; }
           }
           cnt = 0; mn = ~0ull;
@@ -1058,7 +1173,7 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
         const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;
         bx = P.boxes[((size_t)b * P.N + row) * P.q + qi];
       } else {
-        bx = decode_box(P.deltas[(size_t)b * P.N + row], P.anchors[row], P.dp);
+        bx = decode_box(lv_delta(P.lv, b, row), P.anchors[row], P.dp);
       }
       last_box = clip01(bx);
       last_c = c;

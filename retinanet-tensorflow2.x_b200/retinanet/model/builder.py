@@ -69,6 +69,7 @@ class ModelBuilder:
                                  max_level=params.architecture.feature_fusion.max_level)]
 
         if fused and not skip_decoding and not skip_nms:
+            stages[0].lazy = True     # hand the per-level tensors over; the concat happens only if it is needed
             stages.append(FusedPostProcessing(params=params))
             return InferenceModel(model, stages, fused=True)
 

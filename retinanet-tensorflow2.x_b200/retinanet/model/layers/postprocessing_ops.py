@@ -118,6 +118,25 @@ class _Handle:
             pass
 
 
+class _LazyFused(dict):
+    """FuseDetections' output with the concat deferred: behaves like {'class_logits', 'encoded_boxes'} (the tensors
+    are concatenated on first access) and carries the per-level views for rpp_detect_levels."""
+
+    def __init__(self, class_levels, box_levels):
+        super().__init__()
+        self.class_levels = class_levels
+        self.box_levels = box_levels
+
+    def __missing__(self, key):
+        if key == 'class_logits':
+            self[key] = torch.cat(self.class_levels, dim=1)
+        elif key == 'encoded_boxes':
+            self[key] = torch.cat(self.box_levels, dim=1)
+        else:
+            raise KeyError(key)
+        return dict.__getitem__(self, key)
+
+
 class Layer:
     """Stand-in for tf.keras.layers.Layer: `layer(x)` dispatches to `layer.call(x)`; accepts `name=`."""
 
@@ -132,11 +151,14 @@ class FuseDetections(Layer):
     """postprocessing_ops.py:7-56 — reshape each level's NHWC head output to [B, H*W*A, C] / [B, H*W*A, 4] and
     concatenate the levels.  Pure data movement (torch views + one concat)."""
 
-    def __init__(self, min_level, max_level, **kwargs):
+    def __init__(self, min_level, max_level, lazy=False, **kwargs):
         super(FuseDetections, self).__init__(**kwargs)
 
         self.min_level = min_level
         self.max_level = max_level
+        # lazy (not in the reference; set by the builder in front of FusedPostProcessing): also hand over the
+        # per-level [B, n_l, C] / [B, n_l, 4] views and defer the concat, which rpp_detect_levels makes unnecessary
+        self.lazy = lazy
 
     def call(self, predictions):
         class_predictions = predictions['class-predictions']
@@ -156,6 +178,8 @@ class FuseDetections(Layer):
             class_logits.append(class_predictions[level].reshape(batch_size, -1, num_classes))
             encoded_boxes.append(box_predictions[level].reshape(batch_size, -1, 4))
 
+        if self.lazy:
+            return _LazyFused(class_logits, encoded_boxes)
         return {
             'class_logits': torch.cat(class_logits, dim=1),
             'encoded_boxes': torch.cat(encoded_boxes, dim=1)
@@ -353,7 +377,40 @@ class FusedPostProcessing(Layer):
             self._handles[num_classes] = h
         return h
 
+    def _levels_supported(self, num_classes):
+        inf = self._params.inference
+        return (num_classes % 4 == 0 and not self.mode.startswith('Global')
+                and (inf.pre_nms_top_k <= 0 or inf.filter_per_class))
+
+    def _call_levels(self, lazy):
+        """Per-level head outputs in place (rpp_detect_levels): no FuseDetections concat."""
+        cls = [_as_f32(t) for t in lazy.class_levels]
+        box = [_as_f32(t) for t in lazy.box_levels]
+        B, C = cls[0].shape[0], cls[0].shape[2]
+        h = self.handle(C)
+        if sum(t.shape[1] for t in cls) != h.num_anchors or any(b.shape[1] != c.shape[1] for b, c in zip(box, cls)):
+            raise ValueError('per-level head outputs do not add up to the {} anchors of the configured input shape'
+                             .format(h.num_anchors))
+        out = h.outputs(B, cls[0].device)
+        ws = h.workspace(B, 0, cls[0].device)
+        n = len(cls)
+        cls_p = (ctypes.c_void_p * n)(*[t.data_ptr() for t in cls])
+        box_p = (ctypes.c_void_p * n)(*[t.data_ptr() for t in box])
+        _native.check(_native.lib().rpp_detect_levels(h.ptr, box_p, cls_p, B, out['boxes'].data_ptr(),
+                                                      out['scores'].data_ptr(), out['classes'].data_ptr(),
+                                                      out['valid_detections'].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                      _stream()))
+        return {
+            'scores': out['scores'],
+            'boxes': out['boxes'],
+            'classes': out['classes'],
+            'valid_detections': out['valid_detections'],
+        }
+
     def call(self, predictions):
+        if isinstance(predictions, _LazyFused) and self._levels_supported(predictions.class_levels[0].shape[2]) \
+                and all(t.data_ptr() % 16 == 0 for t in predictions.class_levels + predictions.box_levels):
+            return self._call_levels(predictions)
         class_logits = _as_f32(predictions['class_logits'])
         encoded_boxes = _as_f32(predictions['encoded_boxes'])
         B, N, C = class_logits.shape

@@ -234,3 +234,39 @@ def test_two_pass_equals_single_pass(monkeypatch):
     b = to_numpy(_fused(p)(x))
     for key in a:
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize('mode,k', [('PerClassHardNMS', 5000), ('CombinedNMS', -1), ('PerClassSoftNMS', 300),
+                                    ('GlobalSoftNMS', -1)])
+def test_per_level_head_outputs_in_place(ref, mode, k):
+    """The model-side input of the path: per-level NHWC head outputs.  The fused builder consumes them in place
+    (rpp_detect_levels) when the mode allows it and must equal the concat + rpp_detect route and the oracle."""
+    from retinanet.model.builder import ModelBuilder
+    H, C, B, A = 320, 8, 3, 9
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=k, filter_per_class=not mode.startswith('Global'),
+                    max_detections=50)
+    rng = np.random.default_rng(41)
+    cls, box = {}, {}
+    for level in range(3, 8):
+        f = int(np.ceil(H / 2 ** level))
+        cls[str(level)] = rng.standard_normal((B, f, f, A * C)).astype(np.float32)
+        box[str(level)] = np.clip(rng.standard_normal((B, f, f, A * 4)) * 0.5, -4, 4).astype(np.float32)
+    heads = {'class-predictions': {k_: _gpu(v) for k_, v in cls.items()},
+             'box-predictions': {k_: _gpu(v) for k_, v in box.items()}}
+    model = ModelBuilder(p).add_post_processing_stage(None)
+    got = to_numpy(model(heads))
+    logits = np.concatenate([cls[str(l)].reshape(B, -1, C) for l in range(3, 8)], 1)
+    deltas = np.concatenate([box[str(l)].reshape(B, -1, 4) for l in range(3, 8)], 1)
+    exp = oracle_detect(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
+    via_concat = to_numpy(model.layers[-1]({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}))
+    for key in got:
+        assert np.array_equal(got[key], via_concat[key]), key
+    # and the exact slow path through the level table
+    from retinanet import _native
+    h = model.layers[-1].handle(C)
+    _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 1))
+    slow = to_numpy(model(heads))
+    _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 0))
+    for key in got:
+        assert np.array_equal(got[key], slow[key]), key
