@@ -230,6 +230,34 @@ def run_ours(args, rank, local_rank, world):
     _native.check(L.rpp_debug_stage_ms(h.ptr, stage, ctypes.byref(ncalls)))
     _native.check(L.rpp_debug_stage_timing(h.ptr, 0))
 
+    # the same step fed with the model-side input of the path, the per-level NHWC head outputs (views of the same
+    # memory layout a detector emits): consumed in place (rpp_detect_levels) vs the reference's FuseDetections concat
+    from retinanet.model.builder import ModelBuilder
+    bounds = [0, 57600, 72000, 75600, 76500, 76725]
+    heads = {'class-predictions': {}, 'box-predictions': {}}
+    for li, level in enumerate(range(3, 8)):
+        f = -(-H // 2 ** level)
+        heads['class-predictions'][str(level)] = logits[:, bounds[li]:bounds[li + 1]].contiguous().view(B, f, f, 9 * C)
+        heads['box-predictions'][str(level)] = deltas[:, bounds[li]:bounds[li + 1]].contiguous().view(B, f, f, 36)
+    levels_ms = {}
+    for name, fused in (('in_place', True), ('concat_then_detect', False)):
+        model = ModelBuilder(params).add_post_processing_stage(None)
+        model.layers[0].lazy = fused
+        for _ in range(3):
+            o2 = model(heads)
+        torch.cuda.synchronize()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            o2 = model(heads)
+        e2.record()
+        torch.cuda.synchronize()
+        levels_ms[name] = s2.elapsed_time(e2) / args.steps
+        assert bool((o2['scores'] == out['scores']).all().item())
+        del model
+    del heads
+    torch.cuda.empty_cache()
+
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,6 +333,9 @@ def run_ours(args, rank, local_rank, world):
                      'note': 'separate K-step pass, stages serialised (in the timed region collect of image chunk '
                              'i+1 overlaps NMS+merge of chunk i on a side stream)'},
         'mean_valid_detections': valid_mean,
+        'from_head_levels': {'ms_per_step': levels_ms, 'images_per_s': {k: B / v * 1e3 for k, v in levels_ms.items()},
+                             'note': 'per-level NHWC head outputs as input (rank 0): rpp_detect_levels in place vs '
+                                     'FuseDetections concat + rpp_detect'},
     }
     if world == 1 and not args.no_cpu_baseline:
         from oracle import ref
