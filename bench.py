@@ -205,17 +205,30 @@ def run_ours(args, rank, local_rank, world):
     launches_per_step = int(L.rpp_last_launch_count())
     barrier()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # eager calls (one ctypes call + 8 launches per step) ...
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if sampler:
-        sampler.start()
     start.record()
     for _ in range(args.steps):
         out = layer(inputs)
     end.record()
     barrier()
+    ms_eager = start.elapsed_time(end) / args.steps
+    # ... and the same step captured once in a CUDA graph (public API: FusedPostProcessing.capture) — the timed region
+    replay, out_g = layer.capture(inputs)
+    for _ in range(3):
+        replay()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    start.record()
+    for _ in range(args.steps):
+        replay()
+    end.record()
+    barrier()
     clocks = sampler.stop() if sampler else None
     ms_total = start.elapsed_time(end)
+    assert bool((out_g['scores'] == out['scores']).all().item())
     valid_mean = float(out['valid_detections'].float().mean().item())
 
     # second pass, same K steps, with CUDA events at the stage boundaries on the launch stream: per-kernel durations
@@ -333,6 +346,9 @@ def run_ours(args, rank, local_rank, world):
                      'note': 'separate K-step pass, stages serialised (in the timed region collect of image chunk '
                              'i+1 overlaps NMS+merge of chunk i on a side stream)'},
         'mean_valid_detections': valid_mean,
+        'ms_per_step_eager': ms_eager,
+        'launch': 'timed region replays a CUDA graph of one step (FusedPostProcessing.capture); ms_per_step_eager = '
+                  'plain calls',
         'from_head_levels': {'ms_per_step': levels_ms, 'images_per_s': {k: B / v * 1e3 for k, v in levels_ms.items()},
                              'note': 'per-level NHWC head outputs as input (rank 0): rpp_detect_levels in place vs '
                                      'FuseDetections concat + rpp_detect'},

@@ -253,6 +253,12 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
+      {   // small batches: shrink the tiles until every resident CTA has work
+        const long want_tiles = (long)h->sm_count * MINB;
+        const long unit = (long)lanes * UNROLL;
+        while (rows_per_tile > unit && (long)B * ((n + rows_per_tile - 1) / rows_per_tile) < want_tiles)
+          rows_per_tile = std::max(unit, (rows_per_tile / 2 + unit - 1) / unit * unit);
+      }
       int tiles_per_image = 0;
       for (int l = 0; l < lv.L; ++l) {
         lv.tile_off[l] = tiles_per_image;

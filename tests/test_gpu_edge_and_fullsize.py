@@ -270,3 +270,19 @@ def test_per_level_head_outputs_in_place(ref, mode, k):
     _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 0))
     for key in got:
         assert np.array_equal(got[key], slow[key]), key
+
+
+def test_cuda_graph_capture(ref):
+    """The fused call is capturable (no host sync, no allocation inside the library); replays follow the inputs."""
+    p = make_params(320, num_classes=8, mode='PerClassHardNMS', pre_nms_top_k=1000, max_detections=50)
+    layer = _fused(p)
+    N = layer.handle(8).num_anchors
+    logits, deltas = synth_inputs(3, N, 8, seed=51)
+    lg, dl = _gpu(logits), _gpu(deltas)
+    replay, out = layer.capture({'class_logits': lg, 'encoded_boxes': dl})
+    replay()
+    assert image_mismatches(to_numpy(out), oracle_detect(ref, p, logits, deltas)) == []
+    logits2, deltas2 = synth_inputs(3, N, 8, seed=52, dist='sparse')
+    lg.copy_(_gpu(logits2)); dl.copy_(_gpu(deltas2))
+    replay()
+    assert image_mismatches(to_numpy(out), oracle_detect(ref, p, logits2, deltas2)) == []
