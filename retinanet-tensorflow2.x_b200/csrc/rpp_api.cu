@@ -192,8 +192,10 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   ps.sel_cnt = nullptr; ps.sel_key = nullptr; ps.sel_box = nullptr; ps.emit_key = nullptr;
   u64* r_key = nullptr; uint2* r_meta = nullptr; float4* r_box = nullptr;
   long r_cap = 0;
+  int* emit_done = nullptr;
   if (emit) {
     ps.emit_key = ar.take<u64>(P * (size_t)ps.k_lim);
+    emit_done = ar.take<int>(P);
   } else {
     ps.sel_cnt = ar.take<int>(P);
     ps.sel_key = ar.take<u64>(P * (size_t)ps.M);
@@ -243,7 +245,10 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   stage_mark(h, 1, st);
   // ---- stage 2: collect --------------------------------------------------------------------------------------
-  if (!h->force_scan) {
+  // Unsampled SCORE columns (dense stage inputs of a few thousand rows): a list would just be a copy of the column,
+  // so the problem kernel scans the column itself (its "exact scan" phase costs no sigmoid on scores).
+  const bool scan_only = h->force_scan || (!plan.on && !ps.is_logit && !emit);
+  if (!scan_only) {
     if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT) {
       const int C4 = C / 4;
       const int lanes = RPP_COLLECT_NT / C4;
@@ -303,6 +308,10 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
                                                                         plan.CAP, B, n4, (int)f4_per_tile,
                                                                         tiles_per_image, tile_counter);
       LAUNCHED();
+    } else if (C == 1) {
+      long chunks = std::max<long>(1, std::min<long>((n + 1023) / 1024, (long)h->sm_count * 16 / std::max(1, B) + 1));
+      collect_flat1_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, st>>>(ps.x, T, cand_count, cand, plan.CAP, n);
+      LAUNCHED();
     } else {
       const size_t tot = (size_t)B * n * C;
       size_t grid = (tot + 255) / 256;
@@ -327,13 +336,14 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   pp.T_min = ps.T_min;
   pp.M = ps.M; pp.M_lim = ps.M_lim; pp.k_lim = ps.k_lim;
   pp.T = T; pp.cand_count = cand_count; pp.cand = cand; pp.CAP = plan.CAP;
-  pp.force_scan = h->force_scan;
+  pp.force_scan = scan_only;
   pp.sel_key = ps.sel_key; pp.sel_box = ps.sel_box; pp.sel_cnt = ps.sel_cnt;
   pp.soft_scale = ps.soft_sigma_tf > 0.0f ? -0.5f / ps.soft_sigma_tf : 0.0f;
   pp.soft_ignores_iou = h->cfg.soft_ignores_iou_threshold;
   pp.tie_is_rank = ps.tie_is_rank;
   pp.r_key = r_key; pp.r_meta = r_meta; pp.r_box = r_box; pp.r_cap = r_cap;
   pp.emit_key = ps.emit_key;
+  pp.emit_done = emit_done;
   const size_t smem_nms = align_up(nms_shared_bytes(pp.M_lim), 16);
   auto launch = [&](void) {
     if (ps.consumer == RPP_CONSUME_HARD)
@@ -354,6 +364,10 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
                                                                          stop_L);
     LAUNCHED();
     pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 248;
+  }
+  if (emit) {   // whole-list sort in shared memory where it applies; the generic kernel takes the rest
+    emit_sort_kernel<<<(unsigned)P, RPP_EMIT_NT, sizeof(EmitShared), st>>>(pp);
+    LAUNCHED();
   }
   launch();
   LAUNCHED();
@@ -478,7 +492,12 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
     const size_t rows = (size_t)B * n;
     size_t grid = (rows * 32 + 255) / 256;
     if (grid > (size_t)h->sm_count * 16) grid = (size_t)h->sm_count * 16;
-    rowmax_kernel<<<(unsigned)grid, 256, 0, st>>>(x, rows, C, mraw);
+    if (C <= 16) {
+      size_t g2 = std::min<size_t>((rows + 255) / 256, (size_t)h->sm_count * 16);
+      rowmax_small_kernel<<<(unsigned)g2, 256, 0, st>>>(x, rows, C, mraw);
+    } else {
+      rowmax_kernel<<<(unsigned)grid, 256, 0, st>>>(x, rows, C, mraw);
+    }
     LAUNCHED();
   }
   float iou_thr, sigma_tf;
@@ -737,6 +756,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(emit_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -418,6 +418,18 @@ collect_flat4_kernel(const float4* __restrict__ x4 /*[B, n/4]*/, const float* __
   }
 }
 
+// single column, any n / alignment: grid (chunks, B), no index arithmetic beyond the stride
+__global__ void collect_flat1_kernel(const float* __restrict__ x /*[B,n]*/, const float* __restrict__ T,
+                                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, long n) {
+  const int b = blockIdx.y;
+  const float t = __ldg(T + b);
+  const float* xb = x + (size_t)b * n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float v = __ldg(xb + i);
+    if (v >= t) append_cand(cand_count, cand, CAP, (size_t)b, v, (u32)i);
+  }
+}
+
 // generic C (C % 4 != 0, or unaligned base): one element per thread step
 __global__ void collect_cols1_kernel(const float* __restrict__ x, const float* __restrict__ T,
                                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N,
@@ -491,6 +503,7 @@ struct ColProblemParams {
   long r_cap;
   // top-k emission (FilterTopKDetections): sorted keys of the k_lim best rows
   u64* emit_key;           // [P][k_lim]
+  int* emit_done;          // [P] 1 = emit_sort_kernel already wrote this problem's keys
 };
 
 struct NmsShared {
@@ -852,6 +865,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   const int tid = threadIdx.x;
   const size_t p = blockIdx.x;
   const int b = (int)(p / P.C), c = (int)(p % P.C);
+  if (MODE == RPP_CONSUME_EMIT && P.emit_done && P.emit_done[p]) return;   // done by emit_sort_kernel
   if (MODE != RPP_CONSUME_EMIT && P.pass == 2) {
     const float bd = P.bound[p];
     if (bd == -INFINITY || bd < P.stop_L[b]) return;   // the probe already holds everything that can matter
@@ -1008,6 +1022,64 @@ __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int
     }
     if (rank == Mtop - 1) stop_L[b] = v;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Top-k emission fast path (FilterTopKDetections, rpp_topk and the global pre-NMS filter): when a problem's whole
+// candidate list fits in shared memory, one 1024-thread block scores it, sorts it once (bitonic, <= 16 K keys) and
+// writes the k best keys.  Problems it cannot serve exactly (list overflowed, too long, or fewer than k candidates
+// safely above the collect edge) are left to the generic lazy kernel, which skips the ones done here.
+// ---------------------------------------------------------------------------------------------------------------
+#define RPP_EMIT_NT 1024
+#define RPP_EMIT_CAP 16384
+#define RPP_EMIT_CHUNK 8192
+struct EmitShared {
+  SelectScratch<RPP_EMIT_NT> sel;
+  u64 keys[RPP_EMIT_CAP];
+  u64 chunk[RPP_EMIT_CHUNK];
+  int valid;
+};
+__global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const size_t p = blockIdx.x;
+  if (tid == 0) { P.emit_done[p] = 0; sh->valid = 0; }
+  const u32 n_raw = P.cand_count[p];
+  if (P.force_scan || (n_raw & 0x80000000u) || n_raw > (u32)P.CAP || n_raw > RPP_EMIT_CAP || n_raw == 0) return;
+  const int n_list = (int)n_raw;
+  const float T = P.T[p];
+  const bool list_complete = !(T > P.T_min);
+  const float s_edge = list_complete ? P.score_threshold : col_score(P, T);
+  const uint2* lst = P.cand + p * (size_t)P.CAP;
+  int local = 0;
+  for (int i = tid; i < n_list; i += RPP_EMIT_NT) {
+    const uint2 e = lst[i];
+    const float sc = col_score(P, __uint_as_float(e.x));
+    u64 k = 0ull;
+    if (sc > P.score_threshold && (list_complete || sc > s_edge)) { k = make_key(sc, e.y); ++local; }
+    sh->keys[i] = k;
+  }
+  __syncthreads();
+  if (local) atomicAdd(&sh->valid, local);
+  __syncthreads();
+  const int nv = sh->valid;
+  if ((long)nv < P.k_lim) return;   // not enough candidates strictly above the edge: the generic kernel decides
+  // the k best keys, in order: usually ONE exact radix cut to [k, 8192] keys and one bitonic sort of that chunk
+  u64 KB = ~0ull;
+  long emitted = 0;
+  while (emitted < P.k_lim) {
+    const long want = P.k_lim - emitted;
+    const int m = select_chunk<RPP_EMIT_NT>([&](int i) { return sh->keys[i]; }, n_list, KB,
+                                            (int)(want < RPP_EMIT_CHUNK ? want : RPP_EMIT_CHUNK), sh->chunk,
+                                            RPP_EMIT_CHUNK, &sh->sel);
+    if (m == 0) break;
+    const long take = (long)m < want ? m : want;
+    for (long i = tid; i < take; i += RPP_EMIT_NT) P.emit_key[p * (size_t)P.k_lim + emitted + i] = sh->chunk[i];
+    emitted += take;
+    __syncthreads();
+  }
+  if (tid == 0 && emitted == P.k_lim) P.emit_done[p] = 1;
 }
 
 // ===============================================================================================================
@@ -1190,6 +1262,15 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
 // boxes[0]).  The class (tf.argmax: first maximum, by SCORE) is only needed for the <= M selected
 // rows, so it is resolved there.
 // ===============================================================================================================
+// thread-per-row variant for narrow rows (C <= 16): adjacent threads read adjacent rows
+__global__ void rowmax_small_kernel(const float* __restrict__ x, size_t rows, int C, float* __restrict__ out) {
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (size_t)gridDim.x * blockDim.x) {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, __ldg(x + r * C + c));
+    out[r] = m;
+  }
+}
+
 __global__ void rowmax_kernel(const float* __restrict__ x, size_t rows, int C, float* __restrict__ out) {
   // one warp per row: coalesced reads of the row's C values
   const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
