@@ -796,11 +796,16 @@ __device__ void soft_nms_consume(const ColProblemParams& P, NmsShared* sh, SoftS
           float w = 1.0f;
           if (jj >= begin) {
             const float sim = iou_val(box, area, kbox[jj], karea[jj]);
-            w = expf_glibc(__fmul_rn(__fmul_rn(P.soft_scale, sim), sim));
+            // sim == 0 (no overlap, the common case): expf(scale * 0 * 0) = expf(0) = 1 exactly
+            if (sim != 0.0f) w = expf_glibc(__fmul_rn(__fmul_rn(P.soft_scale, sim), sim));
             if (!P.soft_ignores_iou && sim > P.iou_threshold) w = 0.0f;
           }
-          const int cnt = j - begin + 1 < 32 ? j - begin + 1 : 32;
-          for (int t = 0; t < cnt; ++t) {
+          // multiply in the kernel's order (newest selected first = ascending lane); a weight of exactly 1.0 leaves
+          // the score and the threshold test unchanged, so only the lanes that overlap are walked
+          u32 nz = __ballot_sync(RPP_FULL_MASK, w != 1.0f);
+          while (nz) {
+            const int t = __ffs(nz) - 1;
+            nz &= nz - 1u;
             score = __fmul_rn(score, __shfl_sync(RPP_FULL_MASK, w, t));
             if (score <= thr) { dropped = true; break; }
           }
