@@ -286,3 +286,20 @@ def test_cuda_graph_capture(ref):
     lg.copy_(_gpu(logits2)); dl.copy_(_gpu(deltas2))
     replay()
     assert image_mismatches(to_numpy(out), oracle_detect(ref, p, logits2, deltas2)) == []
+
+
+@pytest.mark.parametrize('env', [{'RPP_OVERLAP': '1'}, {'RPP_COLLECT_VARIANT': '1'}, {'RPP_COLLECT_VARIANT': '2'},
+                                 {'RPP_TARGET': '128'}, {'RPP_PROBE_EXTRA': '1'}],
+                         ids=lambda e: ','.join('{}={}'.format(k, v) for k, v in e.items()))
+def test_tuning_knobs_do_not_change_results(monkeypatch, env):
+    """Every tuning knob of DESIGN.md (read at rpp_create) is result-neutral."""
+    p = make_params(320, num_classes=8, mode='PerClassHardNMS', pre_nms_top_k=2000, max_detections=40)
+    N = _fused(p).handle(8).num_anchors
+    logits, deltas = synth_inputs(16, N, 8, seed=61)
+    x = {'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}
+    a = to_numpy(_fused(p)(x))
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    b = to_numpy(_fused(p)(x))
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
