@@ -127,6 +127,17 @@ int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const f
 int rpp_detect_host(void* handle, int device, const float* h_deltas_BN4, const float* h_logits_BNC, int B,
                     float* h_boxes_BM4, float* h_scores_BM, void* h_classes_BM, int* h_valid_B);
 
+/* COCO post-formatting epilogue = the per-image loop of COCOEvaluator.accumulate_results
+ * (eval/coco_evaluator.py:111-134) on the device: rows [0, valid) of every image, boxes divided by
+ * (resize_scale / input_shape) tiled to 4 (skipped when d_resize_scale_B2 is NULL: rescale_detections=False),
+ * truncated to int32 and turned from x1,y1,x2,y2 into x,y,w,h; class ids optionally remapped through
+ * d_class_map[num_classes] (remap_class_ids).  Outputs are COMPACTED in image order: bbox [T,4] i32, category [T] i32,
+ * score [T] f32, image index [T] i32 (position in the batch), and T itself; size the outputs for B * max_detections. */
+int rpp_coco_format(void* handle, const float* d_boxes_BM4, const float* d_scores_BM, const void* d_classes_BM,
+                    const int* d_valid_B, int B, const float* d_resize_scale_B2, const int* d_class_map,
+                    int* d_bbox_out_T4, int* d_category_out_T, float* d_score_out_T, int* d_image_out_T,
+                    int* d_total_out, void* stream);
+
 /* Number of kernels the last rpp_detect / rpp_nms / rpp_topk / rpp_decode call on this thread launched. */
 int rpp_last_launch_count(void);
 

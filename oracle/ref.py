@@ -201,3 +201,25 @@ def detect(class_logits, encoded_boxes, anchor_boxes, H, W, mode, iou_threshold=
     if r != 0:
         raise ValueError('invalid mode / filter combination (Global* modes need filter_per_class=False)')
     return {'boxes': bo, 'scores': so, 'classes': co, 'valid_detections': vo}
+
+
+def coco_format(detections, image_ids, resize_scales, input_shape, rescale_detections=True, class_id_map=None):
+    """COCOEvaluator.accumulate_results (eval/coco_evaluator.py:95-134) restated in numpy, line by line."""
+    out = []
+    f = np.float32
+    for i in range(len(image_ids)):
+        v = int(detections['valid_detections'][i])                      # :113
+        boxes = np.array(detections['boxes'][i][:v], dtype=f)           # :114
+        classes = detections['classes'][i][:v]                          # :115
+        scores = detections['scores'][i][:v]                            # :116
+        if rescale_detections:
+            rs = np.asarray(resize_scales[i], f) / np.asarray(input_shape, f)   # :119
+            boxes = boxes / np.tile(rs[None], (1, 2))                   # :120-123
+        boxes = np.int32(boxes)                                         # :125
+        boxes[:, 2:] = boxes[:, 2:] - boxes[:, :2]                      # :126
+        for box, c, s in zip(boxes, classes, scores):
+            c = int(c)
+            if class_id_map is not None:                                # _maybe_remap_class_ids :89-93
+                c = class_id_map[c]
+            out.append({'image_id': int(image_ids[i]), 'category_id': c, 'bbox': box.tolist(), 'score': float(s)})
+    return out

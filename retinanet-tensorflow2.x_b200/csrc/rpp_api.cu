@@ -926,6 +926,28 @@ static int detect_impl(Handle* h, const float* d_deltas, const float* d_logits, 
   });
 }
 
+int rpp_coco_format(void* handle, const float* d_boxes, const float* d_scores, const void* d_classes,
+                    const int* d_valid, int B, const float* d_resize_scale, const int* d_class_map, int* d_bbox_out,
+                    int* d_category_out, float* d_score_out, int* d_image_out, int* d_total_out, void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !d_boxes || !d_scores || !d_classes || !d_valid || !d_bbox_out || !d_category_out || !d_score_out ||
+      !d_image_out || !d_total_out || B <= 0)
+    return fail(RPP_EINVAL, "bad argument");
+  CocoParams cp{};
+  cp.boxes = (const float4*)d_boxes; cp.scores = d_scores; cp.classes = d_classes; cp.valid = d_valid;
+  cp.class_kind = h->cfg.mode == RPP_COMBINED_NMS ? 0 : (rpp_classes_itemsize(h) == 8 ? 1 : 2);
+  cp.B = B; cp.M = h->cfg.max_detections;
+  cp.resize_scale = d_resize_scale;
+  cp.in_h = (float)h->cfg.H; cp.in_w = (float)h->cfg.W;
+  cp.class_map = d_class_map; cp.num_classes = h->cfg.num_classes;
+  cp.bbox_out = (int4*)d_bbox_out; cp.category_out = d_category_out; cp.score_out = d_score_out;
+  cp.image_out = d_image_out; cp.total_out = d_total_out;
+  coco_format_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(cp);
+  LAUNCHED();
+  return RPP_OK;
+}
+
 int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const float* const* d_logits_levels, int B,
                       float* d_boxes_out, float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws,
                       size_t ws_bytes, void* stream) {

@@ -1395,3 +1395,55 @@ __global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][
     if (c == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
   }
 }
+
+// ===============================================================================================================
+// K7  COCO post-formatting epilogue — COCOEvaluator.accumulate_results (eval/coco_evaluator.py:111-134): slice by
+// valid_detections, boxes /= (resize_scale / input_shape) tiled to 4 (the reference divides [x1,y1,x2,y2] by the
+// [H,W,H,W]-ordered scale), np.int32 truncation, x2y2 -> wh, optional class-id remap; rows are compacted in image
+// order so one small device->host copy replaces the per-image numpy loop.
+// ===============================================================================================================
+struct CocoParams {
+  const float4* boxes; const float* scores; const void* classes; const int* valid;
+  int class_kind;            // 0 f32, 1 i64, 2 i32 (per NMS mode)
+  int B, M;
+  const float* resize_scale; // [B,2] or nullptr (rescale_detections=False)
+  float in_h, in_w;          // input.input_shape
+  const int* class_map;      // [num_classes] or nullptr
+  int num_classes;
+  int4* bbox_out; int* category_out; float* score_out; int* image_out; int* total_out;
+};
+
+__global__ void coco_format_kernel(CocoParams P) {
+  const int b = blockIdx.x;
+  __shared__ int s_off;
+  if (threadIdx.x == 0) {
+    int off = 0;
+    for (int i = 0; i < b; ++i) off += max(0, min(P.valid[i], P.M));
+    s_off = off;
+    if (b == P.B - 1) *P.total_out = off + max(0, min(P.valid[b], P.M));
+  }
+  __syncthreads();
+  const int v = max(0, min(P.valid[b], P.M));
+  float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (P.resize_scale) {
+    const float s0 = __fdiv_rn(P.resize_scale[2 * b + 0], P.in_h), s1 = __fdiv_rn(P.resize_scale[2 * b + 1], P.in_w);
+    sc = make_float4(s0, s1, s0, s1);
+  }
+  for (int i = threadIdx.x; i < v; i += blockDim.x) {
+    const size_t o = (size_t)b * P.M + i;
+    float4 bx = P.boxes[o];
+    if (P.resize_scale)
+      bx = make_float4(__fdiv_rn(bx.x, sc.x), __fdiv_rn(bx.y, sc.y), __fdiv_rn(bx.z, sc.z), __fdiv_rn(bx.w, sc.w));
+    const int x1 = (int)bx.x, y1 = (int)bx.y, x2 = (int)bx.z, y2 = (int)bx.w;   // np.int32: truncation toward zero
+    int cls;
+    if (P.class_kind == 0) cls = (int)((const float*)P.classes)[o];
+    else if (P.class_kind == 1) cls = (int)((const long long*)P.classes)[o];
+    else cls = ((const int*)P.classes)[o];
+    if (P.class_map && cls >= 0 && cls < P.num_classes) cls = P.class_map[cls];
+    const size_t r = (size_t)s_off + i;
+    P.bbox_out[r] = make_int4(x1, y1, x2 - x1, y2 - y1);
+    P.category_out[r] = cls;
+    P.score_out[r] = P.scores[o];
+    P.image_out[r] = b;
+  }
+}

@@ -303,3 +303,25 @@ def test_tuning_knobs_do_not_change_results(monkeypatch, env):
     b = to_numpy(_fused(p)(x))
     for key in a:
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize('mode', ['CombinedNMS', 'PerClassHardNMS', 'GlobalHardNMS'])
+def test_coco_post_format_epilogue(ref, mode):
+    """COCOEvaluator.accumulate_results (eval/coco_evaluator.py:95-134) on the device vs its numpy restatement."""
+    from retinanet.eval import COCOEvaluator
+    H, C, B = 320, 8, 4
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=1000, filter_per_class=not mode.startswith('Global'),
+                    max_detections=30, score_threshold=0.6)
+    layer = _fused(p)
+    N = layer.handle(C).num_anchors
+    logits, deltas = synth_inputs(B, N, C, seed=71, dist='sparse')
+    logits[:, ::50] += 5.0
+    out = layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)})
+    scales = np.array([[0.5, 0.5], [0.8533334, 0.8533334], [1.0, 1.0], [0.3333, 0.3333]], np.float32)
+    ids = [11, 22, 33, 44]
+    cmap = [1, 2, 3, 5, 8, 13, 21, 34]
+    for rescale, remap in [(True, True), (False, False)]:
+        ev = COCOEvaluator([H, H], remap_class_ids=remap, class_id_map=cmap)
+        ev.accumulate_results({'image_id': ids, 'detections': out, 'resize_scale': scales}, rescale_detections=rescale)
+        exp = ref.coco_format(to_numpy(out), ids, scales, [H, H], rescale, cmap if remap else None)
+        assert len(exp) > 0 and ev.processed_detections == exp
