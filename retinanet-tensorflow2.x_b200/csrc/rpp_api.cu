@@ -671,6 +671,11 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   CUDA_OK(cudaGetDevice(&dev));
   Handle* h = new (std::nothrow) Handle();
   if (!h) return fail(RPP_EINVAL, "out of host memory");
+  h->d_anchors = nullptr;
+  h->side = nullptr;
+  h->ev_join = nullptr;
+  for (int i = 0; i < 8; ++i) h->ev_chunk[i] = nullptr;
+  const int rc = [&]() -> int {
   h->cfg = *cfg;
   h->areas.assign(cfg->areas, cfg->areas + cfg->n_areas);
   h->ratios.assign(cfg->aspect_ratios, cfg->aspect_ratios + cfg->n_ratios);
@@ -704,9 +709,6 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     if (h->target < 64) h->target = 64;
     if (h->target > 3072) h->target = 3072;
   }
-  h->side = nullptr;
-  h->ev_join = nullptr;
-  for (int i = 0; i < 8; ++i) h->ev_chunk[i] = nullptr;
   CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i) CUDA_OK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
@@ -730,7 +732,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   for (int i = 0; i < cfg->n_ratios; ++i) ap.ratios[i] = cfg->aspect_ratios[i];
   for (int i = 0; i < cfg->n_scales; ++i) ap.scales[i] = cfg->scales[i];
   h->N = n;
-  if (n <= 0 || n >= 0x7fffffffL) { delete h; return fail(RPP_EINVAL, "anchor count out of range"); }
+  if (n <= 0 || n >= 0x7fffffffL) return fail(RPP_EINVAL, "anchor count out of range");
 
   h->dp.shape[0] = (float)cfg->H; h->dp.shape[1] = (float)cfg->W;
   h->dp.shape[2] = (float)cfg->H; h->dp.shape[3] = (float)cfg->W;
@@ -738,7 +740,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   h->dp.scale = cfg->scale_box_targets;
 
   cudaError_t e = cudaMalloc(&h->d_anchors, (size_t)n * sizeof(float4));
-  if (e != cudaSuccess) { delete h; return fail(RPP_ECUDA, "cudaMalloc anchors: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) return fail(RPP_ECUDA, "cudaMalloc anchors: %s", cudaGetErrorString(e));
   anchors_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ap, n, h->d_anchors);
   float* d_t = nullptr;
   e = cudaMalloc(&d_t, sizeof(float));
@@ -748,11 +750,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     cudaFree(d_t);
   }
   if (e == cudaSuccess) e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    cudaFree(h->d_anchors);
-    delete h;
-    return fail(RPP_ECUDA, "create kernels: %s", cudaGetErrorString(e));
-  }
+  if (e != cudaSuccess) return fail(RPP_ECUDA, "create kernels: %s", cudaGetErrorString(e));
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -763,6 +761,12 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(collect_cols4_levels_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return RPP_OK;
+  }();
+  if (rc != RPP_OK) {   // nothing leaks on a failed create
+    rpp_destroy(h);
+    return rc;
+  }
   *handle = h;
   return RPP_OK;
 }
