@@ -278,6 +278,23 @@ def run_ours(args, rank, local_rank, world):
         del model
     del heads
     torch.cuda.empty_cache()
+    # 16-bit head outputs (what a mixed-precision detector can emit; the reference casts them to fp32 first): the
+    # dominant stream halves.  Informational: the headline `value` stays on fp32 inputs.
+    half_ms = {}
+    for name, tdt in (('bf16', torch.bfloat16), ('f16', torch.float16)):
+        xh = {'class_logits': logits.to(tdt), 'encoded_boxes': deltas.to(tdt)}
+        for _ in range(3):
+            layer(xh)
+        torch.cuda.synchronize()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            layer(xh)
+        e2.record()
+        torch.cuda.synchronize()
+        half_ms[name] = s2.elapsed_time(e2) / args.steps
+        del xh
+    torch.cuda.empty_cache()
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -355,6 +372,9 @@ def run_ours(args, rank, local_rank, world):
                              'i+1 overlaps NMS+merge of chunk i on a side stream)'},
         'mean_valid_detections': valid_mean,
         'ms_per_step_eager': ms_eager,
+        'half_precision_inputs': {'ms_per_step': half_ms, 'images_per_s': {k: B / v * 1e3 for k, v in half_ms.items()},
+                                  'note': 'same workload with f16 / bf16 logits and deltas read in place '
+                                          '(rpp_detect_typed), eager calls'},
         'launch': 'timed region replays a CUDA graph of one step (FusedPostProcessing.capture); ms_per_step_eager = '
                   'plain calls',
         'from_head_levels': {'ms_per_step': levels_ms, 'images_per_s': {k: B / v * 1e3 for k, v in levels_ms.items()},

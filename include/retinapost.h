@@ -120,6 +120,18 @@ int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const f
                       float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Generalisation of the two entries above over the element type of the head outputs.  The reference casts whatever
+ * the heads emit to fp32 before anything else (tf.cast, postprocessing_ops.py:111-112); RPP_F16 / RPP_BF16 inputs
+ * are converted (exactly) as they are loaded, so half-precision heads stream half the bytes.  n_pieces = 1: fused
+ * [B,N,C] / [B,N,4] tensors (d_logits[0], d_deltas[0]); n_pieces = number of levels: per-level head outputs.
+ * Same mode coverage as rpp_detect_levels; 16-bit inputs need num_classes % 8 == 0. */
+#define RPP_F32 0
+#define RPP_F16 1
+#define RPP_BF16 2
+int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, const void* const* d_logits, int dtype,
+                     int B, float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Same, from HOST buffers (the serving call of export.py:233-253 / evaluate_saved_model.py: tensors arrive from
  * the host and detections are consumed on the host).  Copies H2D in image chunks overlapped with the kernels,
  * then D2H of the four outputs; synchronises before returning.  Pinned host memory is recommended.

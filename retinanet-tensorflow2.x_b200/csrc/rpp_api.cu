@@ -229,11 +229,14 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     const int threads = (int)align_up((size_t)plan.lanes * C, 32);
     const int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
     if (lv.L > 1)
-      sample_max_kernel<true><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
-                                                                  plan.rows_per_group, gm);
+      sample_max_kernel<true, false><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
+                                                                         plan.rows_per_group, gm);
+    else if (lv.dtype != RPP_DT_F32)
+      sample_max_kernel<false, true><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
+                                                                         plan.rows_per_group, gm);
     else
-      sample_max_kernel<false><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
-                                                                   plan.rows_per_group, gm);
+      sample_max_kernel<false, false><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
+                                                                          plan.rows_per_group, gm);
     LAUNCHED();
     const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
     sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
@@ -249,7 +252,32 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   // so the problem kernel scans the column itself (its "exact scan" phase costs no sigmoid on scores).
   const bool scan_only = h->force_scan || (!plan.on && !ps.is_logit && !emit);
   if (!scan_only) {
-    if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT) {
+    if (lv.dtype != RPP_DT_F32) {
+      if (C % 8 != 0 || !aligned || C / 8 > RPP_COLLECT_NT)
+        return fail(RPP_EINVAL, "16-bit logits need num_classes % 8 == 0 and 16-byte aligned tensors");
+      const int C8 = C / 8;
+      const int lanes = RPP_COLLECT_NT / C8;
+      const int UNROLL = 4;
+      long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
+      rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
+      if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
+      int tiles_per_image = 0;
+      for (int l = 0; l < lv.L; ++l) {
+        lv.tile_off[l] = tiles_per_image;
+        tiles_per_image += (int)((lv.off[l + 1] - lv.off[l] + rows_per_tile - 1) / rows_per_tile);
+      }
+      lv.tile_off[lv.L] = tiles_per_image;
+      const long n_tiles = (long)B * tiles_per_image;
+      const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
+      const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
+      if (lv.dtype == RPP_DT_F16)
+        collect_cols8_half_kernel<4, RPP_DT_F16><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(
+            lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter);
+      else
+        collect_cols8_half_kernel<4, RPP_DT_BF16><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(
+            lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter);
+      LAUNCHED();
+    } else if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT) {
       const int C4 = C / 4;
       const int lanes = RPP_COLLECT_NT / C4;
       const int UNROLL = h->collect_variant == 2 ? 8 : 4;
@@ -588,8 +616,9 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   const bool per_class = is_per_class_mode(c.mode);
   if (levels) {
     if (!per_class || (filtered && !c.filter_per_class) || C % 4 != 0)
-      return fail(RPP_EINVAL, "rpp_detect_levels covers CombinedNMS / PerClass*NMS with the per-class filter or no "
-                              "filter and num_classes % 4 == 0; fuse the levels and call rpp_detect otherwise");
+      return fail(RPP_EINVAL, "rpp_detect_levels / rpp_detect_typed cover CombinedNMS / PerClass*NMS with the "
+                              "per-class filter or no filter and num_classes % 4 == 0 (% 8 for 16-bit inputs); "
+                              "fuse / convert and call rpp_detect otherwise");
     const long k = filtered ? std::min<long>(c.pre_nms_top_k, N) : N;
     return per_class_pipeline(h, ar, nullptr, 1, nullptr, nullptr, 1, B, N, k, filtered ? 1 : 0, filtered ? 1 : 0, out,
                               st, levels);
@@ -758,6 +787,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols8_half_kernel<4, RPP_DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols8_half_kernel<4, RPP_DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_levels_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -952,29 +983,43 @@ int rpp_coco_format(void* handle, const float* d_boxes, const float* d_scores, c
   return RPP_OK;
 }
 
-int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const float* const* d_logits_levels, int B,
-                      float* d_boxes_out, float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws,
-                      size_t ws_bytes, void* stream) {
+int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, const void* const* d_logits, int dtype,
+                     int B, float* d_boxes_out, float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws,
+                     size_t ws_bytes, void* stream) {
   Handle* h = (Handle*)handle;
   g_launches = 0;
-  if (!h || !d_deltas_levels || !d_logits_levels || B <= 0) return fail(RPP_EINVAL, "bad argument");
-  if (h->levels > RPP_MAX_LEVELS) return fail(RPP_EINVAL, "too many levels");
+  if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
+  if (dtype != RPP_DT_F32 && dtype != RPP_DT_F16 && dtype != RPP_DT_BF16) return fail(RPP_EINVAL, "bad dtype");
+  if (n_pieces != 1 && n_pieces != h->levels)
+    return fail(RPP_EINVAL, "n_pieces must be 1 (fused tensors) or the number of levels (%d)", h->levels);
+  if (n_pieces > RPP_MAX_LEVELS) return fail(RPP_EINVAL, "too many levels");
   Levels lv;
   memset(&lv, 0, sizeof(lv));
-  lv.L = h->levels;
-  for (int l = 0; l < h->levels; ++l) {
-    if (!d_deltas_levels[l] || !d_logits_levels[l]) return fail(RPP_EINVAL, "null level pointer");
-    if (((uintptr_t)d_deltas_levels[l] % 16) || ((uintptr_t)d_logits_levels[l] % 16))
-      return fail(RPP_EINVAL, "level tensors must be 16-byte aligned");
-    lv.off[l] = h->ap.bounds[l];
-    lv.x[l] = d_logits_levels[l];
-    lv.d[l] = (const float4*)d_deltas_levels[l];
+  lv.L = n_pieces;
+  lv.dtype = dtype;
+  for (int l = 0; l < n_pieces; ++l) {
+    if (!d_deltas[l] || !d_logits[l]) return fail(RPP_EINVAL, "null tensor pointer");
+    if (((uintptr_t)d_deltas[l] % 16) || ((uintptr_t)d_logits[l] % 16))
+      return fail(RPP_EINVAL, "tensors must be 16-byte aligned");
+    lv.off[l] = n_pieces == 1 ? 0 : h->ap.bounds[l];
+    lv.x[l] = (const float*)d_logits[l];
+    lv.d[l] = (const float4*)d_deltas[l];
   }
-  lv.off[h->levels] = h->ap.bounds[h->levels];
+  lv.off[n_pieces] = h->N;
   const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     return detect_pipeline(h, ar, nullptr, nullptr, B, out, (cudaStream_t)stream, &lv);
   });
+}
+
+int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const float* const* d_logits_levels, int B,
+                      float* d_boxes_out, float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws,
+                      size_t ws_bytes, void* stream) {
+  Handle* h = (Handle*)handle;
+  if (!h) return fail(RPP_EINVAL, "bad argument");
+  return rpp_detect_typed(handle, h->levels, (const void* const*)d_deltas_levels,
+                          (const void* const*)d_logits_levels, RPP_DT_F32, B, d_boxes_out, d_scores_out,
+                          d_classes_out, d_valid_out, ws, ws_bytes, stream);
 }
 
 int rpp_detect(void* handle, const float* d_deltas, const float* d_logits, int B, float* d_boxes_out,

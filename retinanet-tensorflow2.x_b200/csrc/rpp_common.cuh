@@ -4,6 +4,8 @@
 // that no FMA contraction can change a result relative to the reference's unfused TensorFlow ops
 // (SURVEY.md A.1, A.6); the translation unit is additionally compiled with -fmad=false.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -64,21 +66,13 @@ __device__ __forceinline__ float4 decode_box(float4 d, float4 a, const DecodePar
                      __fdiv_rn(__fadd_rn(cx, hw), p.shape[2]), __fdiv_rn(__fadd_rn(cy, hh), p.shape[3]));
 }
 
-// IoU of TF's NMS kernels.  canon_box returns (min0, min1, max0, max1) and the area.
+// Boxes are canonicalised once for the IoU of TF's NMS kernels (iou_gt / iou_val in rpp_kernels.cuh):
+// canon_box returns (min0, min1, max0, max1) and the area.
 __device__ __forceinline__ float4 canon_box(float4 b, float& area) {
   float4 c = make_float4(fminf(b.x, b.z), fminf(b.y, b.w), fmaxf(b.x, b.z), fmaxf(b.y, b.w));
   area = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
   return c;
 }
-__device__ __forceinline__ float iou_canon(float4 a, float area_a, float4 b, float area_b) {
-  if (area_a <= 0.0f || area_b <= 0.0f) return 0.0f;
-  const float h0 = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
-  const float h1 = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
-  const float inter = __fmul_rn(h0, h1);
-  if (inter <= 0.0f) return 0.0f;  // 0 / (positive) == 0
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // block primitives (NT threads, NT a multiple of 32, <= 1024)
 // ---------------------------------------------------------------------------------------------------------------

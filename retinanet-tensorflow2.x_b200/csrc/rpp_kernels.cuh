@@ -10,8 +10,14 @@
 // concatenates them).  Reading the levels in place saves the 1.65 GB concat copy per batch.
 // ===============================================================================================================
 #define RPP_MAX_LEVELS 8
+#define RPP_DT_F32 0
+#define RPP_DT_F16 1
+#define RPP_DT_BF16 2
 struct Levels {
   int L;
+  int dtype;                           // element type of x and d: the reference casts whatever the heads emit to
+                                       // fp32 first (postprocessing_ops.py:111-112); f16 / bf16 are converted on
+                                       // load (exactly), so half-precision heads stream half the bytes
   long off[RPP_MAX_LEVELS + 1];        // cumulative rows: level l holds rows [off[l], off[l+1])
   const float* x[RPP_MAX_LEVELS];      // [B, n_l, C]
   const float4* d[RPP_MAX_LEVELS];     // [B, n_l] float4 (may be null for score tensors)
@@ -22,13 +28,25 @@ __device__ __forceinline__ int lv_find(const Levels& lv, long r) {
   while (l + 1 < lv.L && r >= lv.off[l + 1]) ++l;
   return l;
 }
-__device__ __forceinline__ const float* lv_row(const Levels& lv, int b, long r, int C) {
+__device__ __forceinline__ float half_bits_to_f32(unsigned short h, int dtype) {
+  return dtype == RPP_DT_F16 ? __half2float(__ushort_as_half(h)) : __uint_as_float((u32)h << 16);
+}
+// element (b, r, c) as fp32, any dtype (for half types x[] really points at 16-bit data)
+__device__ __forceinline__ float lv_val(const Levels& lv, int b, long r, int C, int c) {
   const int l = lv_find(lv, r);
-  return lv.x[l] + ((size_t)b * (lv.off[l + 1] - lv.off[l]) + (r - lv.off[l])) * C;
+  const size_t idx = ((size_t)b * (lv.off[l + 1] - lv.off[l]) + (r - lv.off[l])) * C + c;
+  if (lv.dtype == RPP_DT_F32) return __ldg(lv.x[l] + idx);
+  return half_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(lv.x[l]) + idx), lv.dtype);
 }
 __device__ __forceinline__ float4 lv_delta(const Levels& lv, int b, long r) {
   const int l = lv_find(lv, r);
-  return lv.d[l][(size_t)b * (lv.off[l + 1] - lv.off[l]) + (r - lv.off[l])];
+  const size_t idx = (size_t)b * (lv.off[l + 1] - lv.off[l]) + (r - lv.off[l]);
+  if (lv.dtype == RPP_DT_F32) return lv.d[l][idx];
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(lv.d[l]) + idx);   // 4 x 16 bit
+  return make_float4(half_bits_to_f32((unsigned short)(h.x & 0xffffu), lv.dtype),
+                     half_bits_to_f32((unsigned short)(h.x >> 16), lv.dtype),
+                     half_bits_to_f32((unsigned short)(h.y & 0xffffu), lv.dtype),
+                     half_bits_to_f32((unsigned short)(h.y >> 16), lv.dtype));
 }
 
 // ===============================================================================================================
@@ -111,7 +129,7 @@ __global__ void decode_kernel(const float4* __restrict__ deltas, const float4* _
 // ===============================================================================================================
 #define RPP_GPT 8   // groups per thread; G = lanes * RPP_GPT
 
-template <bool LEVELS>
+template <bool LEVELS, bool HALF>
 __global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stride, int lanes,
                                   int rounds, u32* __restrict__ gm /*[B][G][C]*/) {
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
@@ -122,12 +140,16 @@ __global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stri
 #pragma unroll
   for (int i = 0; i < RPP_GPT; ++i) m[i] = -INFINITY;
   const float* base = lv.x[0] + (size_t)b * N * C + c;   // fused tensor (LEVELS == false)
+  const unsigned short* hbase = reinterpret_cast<const unsigned short*>(lv.x[0]) + (size_t)b * N * C + c;
+  const int dtype = lv.dtype;
   for (int r = split; r < rounds; r += nsplit) {
     float v[RPP_GPT];
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) {
       const long s = (long)r * G + rl + i * lanes;  // sampled row index; group = rl + i * lanes
-      v[i] = LEVELS ? __ldg(lv_row(lv, b, s * stride, C) + c) : __ldg(base + (size_t)(s * stride) * C);
+      if (LEVELS) v[i] = lv_val(lv, b, s * stride, C, c);
+      else if (HALF) v[i] = half_bits_to_f32(__ldg(hbase + (size_t)(s * stride) * C), dtype);
+      else v[i] = __ldg(base + (size_t)(s * stride) * C);
     }
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) m[i] = fmaxf(m[i], v[i]);
@@ -342,6 +364,120 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
     }
     __syncthreads();
     // flush: one global atomic per class that staged anything
+    for (int c = tid; c < C; c += RPP_COLLECT_NT) {
+      const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+      s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+    }
+    __syncthreads();
+    for (int e = tid; e < C * RPP_STAGE_CAP; e += RPP_COLLECT_NT) {
+      const int c = e / RPP_STAGE_CAP, r = e - c * RPP_STAGE_CAP;
+      const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+      if ((u32)r < n) {
+        const u32 slot = s_base[c] + (u32)r;
+        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[e];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// 16-bit variant (f16 / bf16 logits, fused or per-level): one LDG.128 = 8 classes of one anchor, converted exactly to
+// fp32 and compared against 8 register-resident thresholds; everything downstream sees fp32 logit bits.
+// packed helpers: two 16-bit values per 32-bit word, compared natively (HSETP2) against thresholds that were rounded
+// UP to the 16-bit type — for a 16-bit value v and a float T:  v >= T  <=>  v >= ceil16(T)
+template <int DT> __device__ __forceinline__ u32 pack_thresholds_ru(float lo, float hi);
+template <> __device__ __forceinline__ u32 pack_thresholds_ru<RPP_DT_F16>(float lo, float hi) {
+  return (u32)__half_as_ushort(__float2half_ru(lo)) | ((u32)__half_as_ushort(__float2half_ru(hi)) << 16);
+}
+template <> __device__ __forceinline__ u32 pack_thresholds_ru<RPP_DT_BF16>(float lo, float hi) {
+  return (u32)__bfloat16_as_ushort(__float2bfloat16_ru(lo)) | ((u32)__bfloat16_as_ushort(__float2bfloat16_ru(hi)) << 16);
+}
+template <int DT> __device__ __forceinline__ u32 ge2_mask(u32 v, u32 t);
+template <> __device__ __forceinline__ u32 ge2_mask<RPP_DT_F16>(u32 v, u32 t) {
+  return __hge2_mask(*reinterpret_cast<const __half2*>(&v), *reinterpret_cast<const __half2*>(&t));
+}
+template <> __device__ __forceinline__ u32 ge2_mask<RPP_DT_BF16>(u32 v, u32 t) {
+  return __hge2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v), *reinterpret_cast<const __nv_bfloat162*>(&t));
+}
+
+template <int UNROLL, int DT>
+__global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
+collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32* __restrict__ cand_count,
+                          uint2* __restrict__ cand, int CAP, int B, long N, int C8, int lanes, int rows_per_tile,
+                          int tiles_per_image, u32* __restrict__ tile_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = C8 * 8;
+  uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);
+  u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);
+  u32* s_base = s_cnt + C;
+  __shared__ long s_tile;
+  const int tid = threadIdx.x;
+  const int co = tid % C8, rl = tid / C8;
+  const bool active = rl < lanes;
+  const int dtype = lv.dtype;
+  const long n_tiles = (long)B * tiles_per_image;
+  for (;;) {
+    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    __syncthreads();
+    const long tile = s_tile;
+    if (tile >= n_tiles) break;
+    const int b = (int)(tile / tiles_per_image);
+    const int t_img = (int)(tile % tiles_per_image);
+    int l = 0;
+    while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
+    const long n_l = lv.off[l + 1] - lv.off[l], goff = lv.off[l];
+    const long r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
+    const long r1 = r0 + rows_per_tile < n_l ? r0 + rows_per_tile : n_l;
+    const size_t pbase = (size_t)b * C;
+    const unsigned short* xb = reinterpret_cast<const unsigned short*>(lv.x[l]) + (size_t)b * n_l * C;
+    if (active) {
+      u32 th[4];   // the 8 class thresholds of this thread, packed in the input's 16-bit type
+      {
+        const float4 ta = __ldg(reinterpret_cast<const float4*>(T + (size_t)b * C) + 2 * co);
+        const float4 tb = __ldg(reinterpret_cast<const float4*>(T + (size_t)b * C) + 2 * co + 1);
+        th[0] = pack_thresholds_ru<DT>(ta.x, ta.y); th[1] = pack_thresholds_ru<DT>(ta.z, ta.w);
+        th[2] = pack_thresholds_ru<DT>(tb.x, tb.y); th[3] = pack_thresholds_ru<DT>(tb.z, tb.w);
+      }
+      const uint4* src = reinterpret_cast<const uint4*>(xb) + co;
+      for (long row = r0 + rl; row < r1; row += (long)lanes * UNROLL) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const long r = row + (long)u * lanes;
+          if (r < r1) {
+            asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + (size_t)r * C8));
+          } else {
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        u32 mask = 0u;   // bit 8u+i: class 8*co+i of load u passes
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const u32 w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          u32 m = 0u;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const u32 g = ge2_mask<DT>(w[i], th[i]);          // 0xFFFF per passing half
+            m |= ((g & 1u) | ((g >> 15) & 2u)) << (2 * i);
+          }
+          if (row + (long)u * lanes >= r1) m = 0u;
+          mask |= m << (8 * u);
+        }
+        while (mask) {
+          const int bit = __ffs(mask) - 1;
+          mask &= mask - 1u;
+          const int c = co * 8 + (bit & 7);
+          const long r = row + (long)(bit >> 3) * lanes;
+          const float val = half_bits_to_f32(__ldg(xb + (size_t)r * C + c), dtype);
+          const u32 slot = atomicAdd(&s_cnt[c], 1u);
+          if (slot < RPP_STAGE_CAP) s_stage[c * RPP_STAGE_CAP + slot] = make_uint2(__float_as_uint(val), (u32)(goff + r));
+          else append_cand(cand_count, cand, CAP, pbase + c, val, (u32)(goff + r));
+        }
+      }
+    }
+    __syncthreads();
     for (int c = tid; c < C; c += RPP_COLLECT_NT) {
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
@@ -974,7 +1110,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   if (!sh->done && consumed < P.k_lim && (!list_complete || overflow || P.force_scan)) {
     u64 KB = (s_edge == INFINITY) ? ~0ull : ((u64)(ord_f32(s_edge) + 1u) << 32);
     auto keyfn = [&](int i) -> u64 {
-      const float raw = __ldg(lv_row(P.lv, b, i, P.C) + c);
+      const float raw = lv_val(P.lv, b, i, P.C, c);
       if (!(raw >= P.T_min)) return 0ull;
       const float s = col_score(P, raw);
       return s > P.score_threshold ? make_key(s, (u32)i) : 0ull;
@@ -1216,7 +1352,7 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
         // argmax of the column under (score desc, index asc)
         u64 best = 0ull;
         for (long r = tid; r < P.N; r += RPP_MERGE_NT) {
-          const float raw = __ldg(lv_row(P.lv, b, r, P.C) + c);
+          const float raw = lv_val(P.lv, b, r, P.C, c);
           const u64 k = ((u64)ord_f32(raw) << 32) | (u64)(0xffffffffu - (u32)r);
           best = k > best ? k : best;
         }
@@ -1237,7 +1373,7 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
           const float raw_lo = unord_f32(hi_o);
           u64 best2 = 0ull;
           for (long r = tid; r < P.N; r += RPP_MERGE_NT) {
-            const float raw = __ldg(lv_row(P.lv, b, r, P.C) + c);
+            const float raw = lv_val(P.lv, b, r, P.C, c);
             if (raw >= raw_lo) { const u64 k = (u64)(0xffffffffu - (u32)r); best2 = k > best2 ? k : best2; }
           }
           cnt = 0; mn = ~0ull;

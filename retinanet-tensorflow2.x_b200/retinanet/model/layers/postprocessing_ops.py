@@ -393,29 +393,37 @@ class FusedPostProcessing(Layer):
             outputs = self.call(predictions)
         return graph.replay, outputs
 
-    def _levels_supported(self, num_classes):
-        inf = self._params.inference
-        return (num_classes % 4 == 0 and not self.mode.startswith('Global')
-                and (inf.pre_nms_top_k <= 0 or inf.filter_per_class))
+    _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
-    def _call_levels(self, lazy):
-        """Per-level head outputs in place (rpp_detect_levels): no FuseDetections concat."""
-        cls = [_as_f32(t) for t in lazy.class_levels]
-        box = [_as_f32(t) for t in lazy.box_levels]
+    def _native_pieces(self, cls, box):
+        """Can rpp_detect_typed read these tensors where they lie (per-level pieces and / or 16-bit elements)?"""
+        inf = self._params.inference
+        dts = {t.dtype for t in cls + box}
+        if len(dts) != 1 or next(iter(dts)) not in self._DTYPES:
+            return False
+        half = next(iter(dts)) != torch.float32
+        C = cls[0].shape[2]
+        return (C % (8 if half else 4) == 0 and not self.mode.startswith('Global')
+                and (inf.pre_nms_top_k <= 0 or inf.filter_per_class)
+                and all(t.is_cuda and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in cls + box))
+
+    def _call_pieces(self, cls, box):
+        """Head outputs in place (rpp_detect_typed): per-level pieces without the FuseDetections concat, f16 / bf16
+        elements without the fp32 cast of postprocessing_ops.py:111-112 (both are folded into the loads)."""
         B, C = cls[0].shape[0], cls[0].shape[2]
         h = self.handle(C)
         if sum(t.shape[1] for t in cls) != h.num_anchors or any(b.shape[1] != c.shape[1] for b, c in zip(box, cls)):
-            raise ValueError('per-level head outputs do not add up to the {} anchors of the configured input shape'
+            raise ValueError('head outputs do not add up to the {} anchors of the configured input shape'
                              .format(h.num_anchors))
         out = h.outputs(B, cls[0].device)
         ws = h.workspace(B, 0, cls[0].device)
         n = len(cls)
         cls_p = (ctypes.c_void_p * n)(*[t.data_ptr() for t in cls])
         box_p = (ctypes.c_void_p * n)(*[t.data_ptr() for t in box])
-        _native.check(_native.lib().rpp_detect_levels(h.ptr, box_p, cls_p, B, out['boxes'].data_ptr(),
-                                                      out['scores'].data_ptr(), out['classes'].data_ptr(),
-                                                      out['valid_detections'].data_ptr(), ws.data_ptr(), ws.numel(),
-                                                      _stream()))
+        _native.check(_native.lib().rpp_detect_typed(h.ptr, n, box_p, cls_p, self._DTYPES[cls[0].dtype], B,
+                                                     out['boxes'].data_ptr(), out['scores'].data_ptr(),
+                                                     out['classes'].data_ptr(), out['valid_detections'].data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), _stream()))
         return {
             'scores': out['scores'],
             'boxes': out['boxes'],
@@ -424,9 +432,13 @@ class FusedPostProcessing(Layer):
         }
 
     def call(self, predictions):
-        if isinstance(predictions, _LazyFused) and self._levels_supported(predictions.class_levels[0].shape[2]) \
-                and all(t.data_ptr() % 16 == 0 for t in predictions.class_levels + predictions.box_levels):
-            return self._call_levels(predictions)
+        if isinstance(predictions, _LazyFused):
+            if self._native_pieces(predictions.class_levels, predictions.box_levels):
+                return self._call_pieces(predictions.class_levels, predictions.box_levels)
+        elif predictions['class_logits'].dtype != torch.float32:
+            cls, box = [predictions['class_logits']], [predictions['encoded_boxes']]
+            if self._native_pieces(cls, box):
+                return self._call_pieces(cls, box)
         class_logits = _as_f32(predictions['class_logits'])
         encoded_boxes = _as_f32(predictions['encoded_boxes'])
         B, N, C = class_logits.shape

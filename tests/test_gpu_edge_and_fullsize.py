@@ -325,3 +325,40 @@ def test_coco_post_format_epilogue(ref, mode):
         ev.accumulate_results({'image_id': ids, 'detections': out, 'resize_scale': scales}, rescale_detections=rescale)
         exp = ref.coco_format(to_numpy(out), ids, scales, [H, H], rescale, cmap if remap else None)
         assert len(exp) > 0 and ev.processed_detections == exp
+
+
+@pytest.mark.parametrize('dtype', ['float16', 'bfloat16'])
+@pytest.mark.parametrize('mode,k,levels', [('PerClassHardNMS', 5000, False), ('CombinedNMS', -1, True),
+                                           ('PerClassSoftNMS', 400, True), ('GlobalSoftNMS', 500, False)])
+def test_half_precision_head_outputs(ref, dtype, mode, k, levels):
+    """f16 / bf16 head outputs: the reference casts to fp32 first (postprocessing_ops.py:111-112), so the oracle runs
+    on the exactly converted values; the native path converts on load (rpp_detect_typed), Global* modes fall back to a
+    torch cast.  Exercises the fused tensor and the per-level pieces, and the exact scan through 16-bit data."""
+    from retinanet import _native
+    from retinanet.model.builder import ModelBuilder
+    tdt = getattr(torch, dtype)
+    H, C, B, A = 320, 16, 3, 9
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=k, filter_per_class=not mode.startswith('Global'),
+                    max_detections=50)
+    rng = np.random.default_rng(81)
+    cls, box = {}, {}
+    for level in range(3, 8):
+        f = int(np.ceil(H / 2 ** level))
+        cls[str(level)] = torch.from_numpy(rng.standard_normal((B, f, f, A * C)).astype(np.float32)).to(tdt).cuda()
+        box[str(level)] = torch.from_numpy(
+            np.clip(rng.standard_normal((B, f, f, A * 4)) * 0.5, -4, 4).astype(np.float32)).to(tdt).cuda()
+    logits = torch.cat([cls[str(l)].reshape(B, -1, C) for l in range(3, 8)], 1).contiguous()
+    deltas = torch.cat([box[str(l)].reshape(B, -1, 4) for l in range(3, 8)], 1).contiguous()
+    model = ModelBuilder(p).add_post_processing_stage(None)
+    if levels:
+        got = model({'class-predictions': cls, 'box-predictions': box})
+    else:
+        got = model.layers[-1]({'class_logits': logits, 'encoded_boxes': deltas})
+    exp = oracle_detect(ref, p, logits.float().cpu().numpy(), deltas.float().cpu().numpy())
+    assert image_mismatches(to_numpy(got), exp) == []
+    if not mode.startswith('Global'):
+        h = model.layers[-1].handle(C)
+        _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 1))
+        slow = model.layers[-1]({'class_logits': logits, 'encoded_boxes': deltas})
+        _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 0))
+        assert image_mismatches(to_numpy(slow), exp) == []
