@@ -286,6 +286,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
+      if (const char* v = getenv("RPP_TILE_ROWS")) rows_per_tile = std::max<long>((long)lanes * UNROLL, atol(v) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL));
       {   // small batches: shrink the tiles until every resident CTA has work
         const long want_tiles = (long)h->sm_count * MINB;
         const long unit = (long)lanes * UNROLL;

@@ -134,6 +134,15 @@ __global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stri
                                   int rounds, u32* __restrict__ gm /*[B][G][C]*/) {
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
   const int c = threadIdx.x % C, rl = threadIdx.x / C;
+  // LEVELS: the table is indexed at run time, so it is staged in shared memory (run-time indexing of kernel
+  // parameters costs a select chain per access); the sampled rows of a thread only grow -> running level cursor
+  __shared__ long s_off[RPP_MAX_LEVELS + 1];
+  __shared__ const float* s_x[RPP_MAX_LEVELS];
+  if (LEVELS) {
+    if (threadIdx.x <= lv.L) s_off[threadIdx.x] = lv.off[threadIdx.x];
+    if (threadIdx.x < lv.L) s_x[threadIdx.x] = lv.x[threadIdx.x];
+    __syncthreads();
+  }
   if (rl >= lanes) return;
   const int G = lanes * RPP_GPT;
   float m[RPP_GPT];
@@ -142,14 +151,24 @@ __global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stri
   const float* base = lv.x[0] + (size_t)b * N * C + c;   // fused tensor (LEVELS == false)
   const unsigned short* hbase = reinterpret_cast<const unsigned short*>(lv.x[0]) + (size_t)b * N * C + c;
   const int dtype = lv.dtype;
+  const int nlv = lv.L;
+  int lvl = 0;
   for (int r = split; r < rounds; r += nsplit) {
     float v[RPP_GPT];
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) {
       const long s = (long)r * G + rl + i * lanes;  // sampled row index; group = rl + i * lanes
-      if (LEVELS) v[i] = lv_val(lv, b, s * stride, C, c);
-      else if (HALF) v[i] = half_bits_to_f32(__ldg(hbase + (size_t)(s * stride) * C), dtype);
-      else v[i] = __ldg(base + (size_t)(s * stride) * C);
+      if (LEVELS) {
+        const long row = s * stride;
+        while (lvl + 1 < nlv && row >= s_off[lvl + 1]) ++lvl;
+        const size_t idx = ((size_t)b * (s_off[lvl + 1] - s_off[lvl]) + (row - s_off[lvl])) * C + c;
+        v[i] = dtype == RPP_DT_F32 ? __ldg(s_x[lvl] + idx)
+                                   : half_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(s_x[lvl]) + idx), dtype);
+      } else if (HALF) {
+        v[i] = half_bits_to_f32(__ldg(hbase + (size_t)(s * stride) * C), dtype);
+      } else {
+        v[i] = __ldg(base + (size_t)(s * stride) * C);
+      }
     }
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) m[i] = fmaxf(m[i], v[i]);
@@ -304,29 +323,34 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
   u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);  // [C]
   u32* s_base = s_cnt + C;                               // [C]
   __shared__ long s_tile;
+  __shared__ long s_nl, s_goff, s_r0;      // per-tile level geometry, resolved once by thread 0
+  __shared__ const float* s_xb;
   const int tid = threadIdx.x;
   const int cq = tid % C4, rl = tid / C4;
   const bool active = rl < lanes;
   const long n_tiles = (long)B * tiles_per_image;
   for (;;) {
-    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
+    if (tid == 0) {
+      const long t = (long)atomicAdd(tile_counter, 1u);
+      s_tile = t;
+      if (t < n_tiles) {
+        const int bb = (int)(t / tiles_per_image), t_img = (int)(t % tiles_per_image);
+        int l = 0;
+        while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
+        s_nl = lv.off[l + 1] - lv.off[l];
+        s_goff = lv.off[l];
+        s_r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
+        s_xb = lv.x[l] + (size_t)bb * (lv.off[l + 1] - lv.off[l]) * C;
+      }
+    }
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
     const int b = (int)(tile / tiles_per_image);
-    const int t_img = (int)(tile % tiles_per_image);
     // rows are LOCAL to the level inside the loop; `goff` turns them into fused row indices when staged
-    long n_l, goff, r0;
-    const float* __restrict__ xb;
-    {
-      int l = 0;
-      while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
-      n_l = lv.off[l + 1] - lv.off[l];
-      goff = lv.off[l];
-      r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
-      xb = lv.x[l] + (size_t)b * n_l * C;
-    }
+    const long n_l = s_nl, goff = s_goff, r0 = s_r0;
+    const float* __restrict__ xb = s_xb;
     const long r1 = r0 + rows_per_tile < n_l ? r0 + rows_per_tile : n_l;
     const size_t pbase = (size_t)b * C;
     if (active) {
@@ -411,26 +435,36 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
   u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);
   u32* s_base = s_cnt + C;
   __shared__ long s_tile;
+  __shared__ long s_nl, s_goff, s_r0;      // per-tile level geometry, resolved once by thread 0
+  __shared__ const unsigned short* s_xb;
   const int tid = threadIdx.x;
   const int co = tid % C8, rl = tid / C8;
   const bool active = rl < lanes;
   const int dtype = lv.dtype;
   const long n_tiles = (long)B * tiles_per_image;
   for (;;) {
-    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
+    if (tid == 0) {
+      const long t = (long)atomicAdd(tile_counter, 1u);
+      s_tile = t;
+      if (t < n_tiles) {
+        const int bb = (int)(t / tiles_per_image), t_img = (int)(t % tiles_per_image);
+        int l = 0;
+        while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
+        s_nl = lv.off[l + 1] - lv.off[l];
+        s_goff = lv.off[l];
+        s_r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
+        s_xb = reinterpret_cast<const unsigned short*>(lv.x[l]) + (size_t)bb * (lv.off[l + 1] - lv.off[l]) * C;
+      }
+    }
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
     const int b = (int)(tile / tiles_per_image);
-    const int t_img = (int)(tile % tiles_per_image);
-    int l = 0;
-    while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
-    const long n_l = lv.off[l + 1] - lv.off[l], goff = lv.off[l];
-    const long r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
+    const long n_l = s_nl, goff = s_goff, r0 = s_r0;
     const long r1 = r0 + rows_per_tile < n_l ? r0 + rows_per_tile : n_l;
     const size_t pbase = (size_t)b * C;
-    const unsigned short* xb = reinterpret_cast<const unsigned short*>(lv.x[l]) + (size_t)b * n_l * C;
+    const unsigned short* __restrict__ xb = s_xb;
     if (active) {
       u32 th[4];   // the 8 class thresholds of this thread, packed in the input's 16-bit type
       {
