@@ -258,7 +258,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       const int C8 = C / 8;
       const int lanes = RPP_COLLECT_NT / C8;
       const int UNROLL = 4;
-      long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
+      long rows_per_tile = plan.on ? (long)(24.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
       int tiles_per_image = 0;
@@ -282,16 +282,17 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       const int lanes = RPP_COLLECT_NT / C4;
       const int UNROLL = h->collect_variant == 2 ? 8 : 4;
       const int MINB = h->collect_variant == 0 ? 3 : 2;
-      // tile: ~10 expected hits per class (stage capacity 32) when the plan aims at `target` candidates per column
-      long rows_per_tile = plan.on ? (long)(10.0 * n / target) : 4L * lanes * UNROLL;
+      // tile: ~24 expected hits per class (stage capacity 64) when the plan aims at `target` candidates per column
+      long rows_per_tile = plan.on ? (long)(24.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
       if (const char* v = getenv("RPP_TILE_ROWS")) rows_per_tile = std::max<long>((long)lanes * UNROLL, atol(v) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL));
-      {   // small batches: shrink the tiles until every resident CTA has work
-        const long want_tiles = (long)h->sm_count * MINB;
+      {   // small batches: shrink the tiles until every resident CTA gets ~4 of them (dynamic scheduling then
+          // balances the tail to within a quarter of a CTA's share)
+        const long want_tiles = 4L * h->sm_count * MINB;
         const long unit = (long)lanes * UNROLL;
-        while (rows_per_tile > unit && (long)B * ((n + rows_per_tile - 1) / rows_per_tile) < want_tiles)
-          rows_per_tile = std::max(unit, (rows_per_tile / 2 + unit - 1) / unit * unit);
+        while (rows_per_tile > 4 * unit && (long)B * ((n + rows_per_tile - 1) / rows_per_tile) < want_tiles)
+          rows_per_tile = std::max(4 * unit, (rows_per_tile / 2 + unit - 1) / unit * unit);   // >= 4 loop trips
       }
       int tiles_per_image = 0;
       for (int l = 0; l < lv.L; ++l) {

@@ -227,7 +227,7 @@ __device__ __forceinline__ void append_cand(u32* cand_count, uint2* cand, int CA
   if (slot < (u32)CAP) cand[p * (size_t)CAP + slot] = make_uint2(__float_as_uint(v), idx);
 }
 
-#define RPP_STAGE_CAP 32
+#define RPP_STAGE_CAP 64
 #define RPP_COLLECT_NT 512
 
 template <int UNROLL, int MINB>
@@ -242,6 +242,7 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
   u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);  // [C]
   u32* s_base = s_cnt + C;                               // [C]
   __shared__ long s_tile;
+  __shared__ u32 s_span;
   const int tid = threadIdx.x;
   const int cq = tid % C4, rl = tid / C4;
   const bool active = rl < lanes;
@@ -250,6 +251,7 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
   for (;;) {
     if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    if (tid == 0) s_span = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
@@ -296,14 +298,16 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
     for (int c = tid; c < C; c += RPP_COLLECT_NT) {
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+      if (n) atomicMax(&s_span, n);
     }
     __syncthreads();
-    for (int e = tid; e < C * RPP_STAGE_CAP; e += RPP_COLLECT_NT) {
-      const int c = e / RPP_STAGE_CAP, r = e - c * RPP_STAGE_CAP;
+    const int span = (int)s_span;   // the fullest class stage of this tile: copy only that many slots per class
+    for (int e = tid; e < C * span; e += RPP_COLLECT_NT) {
+      const int c = e / span, r = e - c * span;
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       if ((u32)r < n) {
         const u32 slot = s_base[c] + (u32)r;
-        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[e];
+        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[c * RPP_STAGE_CAP + r];
       }
     }
     __syncthreads();
@@ -323,6 +327,7 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
   u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);  // [C]
   u32* s_base = s_cnt + C;                               // [C]
   __shared__ long s_tile;
+  __shared__ u32 s_span;
   __shared__ long s_nl, s_goff, s_r0;      // per-tile level geometry, resolved once by thread 0
   __shared__ const float* s_xb;
   const int tid = threadIdx.x;
@@ -344,6 +349,7 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
       }
     }
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    if (tid == 0) s_span = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
@@ -391,14 +397,16 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
     for (int c = tid; c < C; c += RPP_COLLECT_NT) {
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+      if (n) atomicMax(&s_span, n);
     }
     __syncthreads();
-    for (int e = tid; e < C * RPP_STAGE_CAP; e += RPP_COLLECT_NT) {
-      const int c = e / RPP_STAGE_CAP, r = e - c * RPP_STAGE_CAP;
+    const int span = (int)s_span;   // the fullest class stage of this tile: copy only that many slots per class
+    for (int e = tid; e < C * span; e += RPP_COLLECT_NT) {
+      const int c = e / span, r = e - c * span;
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       if ((u32)r < n) {
         const u32 slot = s_base[c] + (u32)r;
-        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[e];
+        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[c * RPP_STAGE_CAP + r];
       }
     }
     __syncthreads();
@@ -435,6 +443,7 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
   u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);
   u32* s_base = s_cnt + C;
   __shared__ long s_tile;
+  __shared__ u32 s_span;
   __shared__ long s_nl, s_goff, s_r0;      // per-tile level geometry, resolved once by thread 0
   __shared__ const unsigned short* s_xb;
   const int tid = threadIdx.x;
@@ -457,6 +466,7 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
       }
     }
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    if (tid == 0) s_span = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
@@ -515,14 +525,16 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
     for (int c = tid; c < C; c += RPP_COLLECT_NT) {
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+      if (n) atomicMax(&s_span, n);
     }
     __syncthreads();
-    for (int e = tid; e < C * RPP_STAGE_CAP; e += RPP_COLLECT_NT) {
-      const int c = e / RPP_STAGE_CAP, r = e - c * RPP_STAGE_CAP;
+    const int span = (int)s_span;   // the fullest class stage of this tile: copy only that many slots per class
+    for (int e = tid; e < C * span; e += RPP_COLLECT_NT) {
+      const int c = e / span, r = e - c * span;
       const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
       if ((u32)r < n) {
         const u32 slot = s_base[c] + (u32)r;
-        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[e];
+        if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[c * RPP_STAGE_CAP + r];
       }
     }
     __syncthreads();
