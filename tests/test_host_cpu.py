@@ -168,3 +168,24 @@ def test_gather_detections_gloo_world2(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out.decode()
+
+
+def _build_abi_smoke(tmp_path):
+    exe = str(tmp_path / 'abi_smoke')
+    cmd = ['gcc', os.path.join(ROOT, 'tests', 'abi_smoke.c'), '-I' + os.path.join(ROOT, 'include'),
+           '-I/usr/local/cuda/include', '-L' + PKG, '-lretinapost', '-L/usr/local/cuda/lib64', '-lcudart', '-lm',
+           '-Wl,-rpath,' + PKG, '-Wl,-rpath,/usr/local/cuda/lib64', '-o', exe]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_abi_compiles_and_links_from_plain_c(tmp_path):
+    """include/retinapost.h is a C header and the library links from C (no torch, no Python)."""
+    assert os.path.exists(_build_abi_smoke(tmp_path))
+
+
+@pytest.mark.gpu
+def test_abi_smoke_runs_from_plain_c(tmp_path):
+    out = subprocess.run([_build_abi_smoke(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'abi_smoke ok' in out.stdout
