@@ -139,6 +139,11 @@ int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, co
 int rpp_detect_host(void* handle, int device, const float* h_deltas_BN4, const float* h_logits_BNC, int B,
                     float* h_boxes_BM4, float* h_scores_BM, void* h_classes_BM, int* h_valid_B);
 
+/* rpp_detect_host over f32 / f16 / bf16 host buffers (same restrictions as rpp_detect_typed for the 16-bit types):
+ * half-precision heads halve the PCIe traffic that bounds this call. */
+int rpp_detect_host_typed(void* handle, int device, const void* h_deltas_BN4, const void* h_logits_BNC, int dtype,
+                          int B, float* h_boxes_BM4, float* h_scores_BM, void* h_classes_BM, int* h_valid_B);
+
 /* COCO post-formatting epilogue = the per-image loop of COCOEvaluator.accumulate_results
  * (eval/coco_evaluator.py:111-134) on the device: rows [0, valid) of every image, boxes divided by
  * (resize_scale / input_shape) tiled to 4 (skipped when d_resize_scale_B2 is NULL: rescale_detections=False),

@@ -1050,18 +1050,22 @@ void host_path_free(Handle* h) {
 
 extern "C" {
 
-int rpp_detect_host(void* handle, int device, const float* h_deltas, const float* h_logits, int B, float* h_boxes,
-                    float* h_scores, void* h_classes, int* h_valid) {
+int rpp_detect_host_typed(void* handle, int device, const void* h_deltas, const void* h_logits, int dtype, int B,
+                          float* h_boxes, float* h_scores, void* h_classes, int* h_valid) {
   Handle* h = (Handle*)handle;
   g_launches = 0;
   if (!h || !h_deltas || !h_logits || !h_boxes || !h_scores || !h_classes || !h_valid || B <= 0)
     return fail(RPP_EINVAL, "bad argument");
+  if (dtype != RPP_DT_F32 && dtype != RPP_DT_F16 && dtype != RPP_DT_BF16) return fail(RPP_EINVAL, "bad dtype");
+  const size_t esz = dtype == RPP_DT_F32 ? 4 : 2;
   CUDA_OK(cudaSetDevice(device));
   Handle::HostPath& hp = h->hp;
   const int C = h->cfg.num_classes, M = h->cfg.max_detections;
-  const size_t lg_img = (size_t)h->N * C * sizeof(float), dl_img = (size_t)h->N * 4 * sizeof(float);
+  const size_t lg_img = (size_t)h->N * C * esz, dl_img = (size_t)h->N * 4 * esz;
+  // staging is sized for fp32 so that a handle can serve both element types
+  const size_t lg_img32 = (size_t)h->N * C * sizeof(float), dl_img32 = (size_t)h->N * 4 * sizeof(float);
   // chunk: ~256 MB of logits per staging buffer, at least one image
-  int chunk = (int)std::max<size_t>(1, (256u << 20) / lg_img);
+  int chunk = (int)std::max<size_t>(1, (256u << 20) / lg_img32);
   if (chunk > B) chunk = B;
   const int csz = rpp_classes_itemsize(h);
   if (hp.chunk < chunk || hp.B_out < B) {
@@ -1071,8 +1075,8 @@ int rpp_detect_host(void* handle, int device, const float* h_deltas, const float
     for (int i = 0; i < 2; ++i) {
       CUDA_OK(cudaEventCreateWithFlags(&hp.ready[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
-      CUDA_OK(cudaMalloc(&hp.d_logits[i], lg_img * chunk));
-      CUDA_OK(cudaMalloc(&hp.d_deltas[i], dl_img * chunk));
+      CUDA_OK(cudaMalloc(&hp.d_logits[i], lg_img32 * chunk));
+      CUDA_OK(cudaMalloc(&hp.d_deltas[i], dl_img32 * chunk));
     }
     hp.ws_bytes = rpp_workspace_bytes(h, chunk, 0);
     CUDA_OK(cudaMalloc(&hp.ws, hp.ws_bytes));
@@ -1095,9 +1099,20 @@ int rpp_detect_host(void* handle, int device, const float* h_deltas, const float
                             cudaMemcpyHostToDevice, hp.s_copy));
     CUDA_OK(cudaEventRecord(hp.ready[buf], hp.s_copy));
     CUDA_OK(cudaStreamWaitEvent(hp.s_comp, hp.ready[buf], 0));
-    int rc = detect_impl(h, hp.d_deltas[buf], hp.d_logits[buf], bc, hp.d_boxes + (size_t)b0 * M * 4,
-                         hp.d_scores + (size_t)b0 * M, (char*)hp.d_classes + (size_t)b0 * M * csz, hp.d_valid + b0,
-                         hp.ws, hp.ws_bytes, hp.s_comp);
+    int rc;
+    if (dtype == RPP_DT_F32) {
+      rc = detect_impl(h, hp.d_deltas[buf], hp.d_logits[buf], bc, hp.d_boxes + (size_t)b0 * M * 4,
+                       hp.d_scores + (size_t)b0 * M, (char*)hp.d_classes + (size_t)b0 * M * csz, hp.d_valid + b0,
+                       hp.ws, hp.ws_bytes, hp.s_comp);
+    } else {
+      const void* dp[1] = {hp.d_deltas[buf]};
+      const void* lp[1] = {hp.d_logits[buf]};
+      const int launched = g_launches;
+      rc = rpp_detect_typed(h, 1, dp, lp, dtype, bc, hp.d_boxes + (size_t)b0 * M * 4, hp.d_scores + (size_t)b0 * M,
+                            (char*)hp.d_classes + (size_t)b0 * M * csz, hp.d_valid + b0, hp.ws, hp.ws_bytes,
+                            hp.s_comp);
+      g_launches += launched;
+    }
     if (rc) return rc;
     CUDA_OK(cudaEventRecord(hp.done[buf], hp.s_comp));
   }
@@ -1107,6 +1122,12 @@ int rpp_detect_host(void* handle, int device, const float* h_deltas, const float
   CUDA_OK(cudaMemcpyAsync(h_valid, hp.d_valid, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, hp.s_comp));
   CUDA_OK(cudaStreamSynchronize(hp.s_comp));
   return RPP_OK;
+}
+
+int rpp_detect_host(void* handle, int device, const float* h_deltas, const float* h_logits, int B, float* h_boxes,
+                    float* h_scores, void* h_classes, int* h_valid) {
+  return rpp_detect_host_typed(handle, device, h_deltas, h_logits, RPP_DT_F32, B, h_boxes, h_scores, h_classes,
+                               h_valid);
 }
 
 }  // extern "C"

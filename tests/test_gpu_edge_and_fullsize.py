@@ -362,3 +362,24 @@ def test_half_precision_head_outputs(ref, dtype, mode, k, levels):
         slow = model.layers[-1]({'class_logits': logits, 'encoded_boxes': deltas})
         _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 0))
         assert image_mismatches(to_numpy(slow), exp) == []
+
+
+@pytest.mark.parametrize('dtype', ['float16', 'bfloat16'])
+def test_host_entry_half_precision(dtype):
+    """rpp_detect_host_typed on 16-bit pinned host buffers == the device path on the same values."""
+    from retinanet import _native
+    tdt = getattr(torch, dtype)
+    p = make_params(320, num_classes=16, mode='PerClassHardNMS', pre_nms_top_k=1000, max_detections=50)
+    layer = _fused(p)
+    h = layer.handle(16)
+    B, N, M = 5, h.num_anchors, 50
+    logits, deltas = synth_inputs(B, N, 16, seed=91)
+    hl, hd = torch.from_numpy(logits).to(tdt).pin_memory(), torch.from_numpy(deltas).to(tdt).pin_memory()
+    dev = to_numpy(layer({'class_logits': hl.cuda(), 'encoded_boxes': hd.cuda()}))
+    ob, os_ = torch.empty((B, M, 4)).pin_memory(), torch.empty((B, M)).pin_memory()
+    oc, ov = torch.empty((B, M), dtype=torch.int32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory()
+    _native.check(_native.lib().rpp_detect_host_typed(h.ptr, 0, hd.data_ptr(), hl.data_ptr(),
+                                                      {'float16': 1, 'bfloat16': 2}[dtype], B, ob.data_ptr(),
+                                                      os_.data_ptr(), oc.data_ptr(), ov.data_ptr()))
+    assert np.array_equal(ob.numpy(), dev['boxes']) and np.array_equal(os_.numpy(), dev['scores'])
+    assert np.array_equal(oc.numpy(), dev['classes']) and np.array_equal(ov.numpy(), dev['valid_detections'])
