@@ -56,6 +56,7 @@ struct Handle {
   int device;
   int sm_count;
   int force_scan;
+  int warp_probe;        // env RPP_WARP_PROBE (default 1): warp-per-problem probe kernel for the hard modes
   int probe_extra;       // env RPP_PROBE_EXTRA: boxes per class kept by the probe beyond ceil(M / C)
   int two_pass;          // env RPP_TWO_PASS (default 1): probe / bound / finish scheme of the per-class modes
   int collect_ctas;      // env RPP_COLLECT_CTAS: CTAs per SM of the collect kernel (0 = automatic)
@@ -388,7 +389,10 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   if (ps.two_pass_m1 > 0) {
     const int m1 = ps.two_pass_m1;
     pp.pass = 1; pp.M_cap = m1; pp.want0 = std::max(24, 6 * m1);
-    launch();
+    if (ps.consumer == RPP_CONSUME_HARD && m1 <= RPP_PROBE_MAXCAP && h->warp_probe)
+      probe_warp_kernel<<<(unsigned)((P + RPP_PROBE_WARPS - 1) / RPP_PROBE_WARPS), RPP_PROBE_WARPS * 32, 0, st>>>(pp, P);
+    else
+      launch();
     LAUNCHED();
     perclass_bound_kernel<<<B, 256, (size_t)C * m1 * sizeof(float), st>>>(ps.sel_key, ps.sel_cnt, C, ps.M, m1, ps.M,
                                                                          stop_L);
@@ -727,6 +731,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_WARP_PROBE");
+    h->warp_probe = v ? atoi(v) : 1;
     v = getenv("RPP_PROBE_EXTRA");
     h->probe_extra = v ? atoi(v) : 3;
     if (h->probe_extra < 1) h->probe_extra = 1;

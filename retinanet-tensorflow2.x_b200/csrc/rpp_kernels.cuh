@@ -1212,6 +1212,175 @@ __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Warp-per-problem PROBE of the hard per-class modes (pass 1 of the cross-class bound).  The probe only needs the
+// first few boxes of a class, so it avoids the block machinery altogether: no block barrier, one warp = one problem.
+//   1. every lane scans its share of the candidate list keeping its 3 largest raw keys (logit bits | ~index);
+//   2. tau = the largest 3rd-best over the lanes: every key > tau is among some lane's best two, so {key > tau} is a
+//      COMPLETE prefix of the list in raw order (<= 64 keys); everything else scores <= e0 = score(logit(tau));
+//   3. the prefix is scored (sigmoid only here), re-keyed by (score, index), candidates not strictly above e0 dropped
+//      (same edge rule as everywhere), and sorted with a 64-key register bitonic network (shuffles);
+//   4. greedy NMS over up to two tiles of 32 with the suppression bit-mask / bit-chain, stopping at M_cap boxes.
+// bound[p] = score of the last kept box when the cap was hit, else an upper bound for anything the class can still
+// keep (e0, the collect edge, or -inf when the class is exhausted).  Exactness never depends on tau.
+// ---------------------------------------------------------------------------------------------------------------
+#define RPP_PROBE_WARPS 8
+#define RPP_PROBE_MAXCAP 16
+
+struct ProbeWarpShared {
+  float4 cbox[32];
+  float carea[32];
+  float4 kbox[RPP_PROBE_MAXCAP];
+  float karea[RPP_PROBE_MAXCAP];
+};
+
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const u64 t = __shfl_xor_sync(RPP_FULL_MASK, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(RPP_PROBE_WARPS * 32) probe_warp_kernel(ColProblemParams P, size_t n_problems) {
+  __shared__ ProbeWarpShared s_all[RPP_PROBE_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t p = (size_t)blockIdx.x * RPP_PROBE_WARPS + warp;
+  if (p >= n_problems) return;
+  ProbeWarpShared* sh = &s_all[warp];
+  const int b = (int)(p / P.C), c = (int)(p % P.C);
+  const u32 n_raw = P.cand_count[p];
+  if (P.force_scan || n_raw > (u32)P.CAP) {   // no usable list: the finish pass does the whole class
+    if (lane == 0) { P.sel_cnt[p] = 0; P.bound[p] = INFINITY; }
+    return;
+  }
+  const int n = (int)n_raw;
+  const float T = P.T[p];
+  const bool list_complete = !(T > P.T_min);
+  const float s_edge = list_complete ? -INFINITY : col_score(P, T);
+  const uint2* lst = P.cand + p * (size_t)P.CAP;
+
+  // 1. per-lane top-3 raw keys
+  u64 t0 = 0ull, t1 = 0ull, t2 = 0ull;
+  for (int i = lane; i < n; i += 32) {
+    const uint2 e = lst[i];
+    const u64 rk = ((u64)ord_f32(__uint_as_float(e.x)) << 32) | (u64)(0xffffffffu - e.y);
+    if (rk > t2) {
+      if (rk > t1) {
+        t2 = t1;
+        if (rk > t0) { t1 = t0; t0 = rk; } else { t1 = rk; }
+      } else {
+        t2 = rk;
+      }
+    }
+  }
+  // 2. complete prefix {rk > tau}
+  const u64 tau = warp_max_u64(t2);
+  float e0 = s_edge;                                 // nothing outside the prefix scores above e0
+  if (tau != 0ull) e0 = col_score(P, unord_f32((u32)(tau >> 32)));
+  const bool whole_list = tau == 0ull;
+  // 3. score + re-key the prefix (two slots per lane), drop what is not strictly above e0 / the score threshold
+  u64 k[2];
+  {
+    const u64 r[2] = {t0, t1};
+#pragma unroll
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      k[sidx] = 0ull;
+      if (r[sidx] > tau) {
+        const float sc = col_score(P, unord_f32((u32)(r[sidx] >> 32)));
+        if (sc > P.score_threshold && sc > e0) k[sidx] = make_key(sc, key_tie(r[sidx]));
+      }
+    }
+  }
+  // 64-key descending bitonic sort across the warp: element e = slot * 32 + lane
+#pragma unroll
+  for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j == 32) {
+        if (k[0] < k[1]) { const u64 t = k[0]; k[0] = k[1]; k[1] = t; }   // size == 64: all descending
+      } else {
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+          const int e = sidx * 32 + lane;
+          const u64 other = __shfl_xor_sync(RPP_FULL_MASK, k[sidx], j);
+          const bool desc = (e & size) == 0;
+          const bool low = (lane & j) == 0;
+          const bool keep_max = desc == low;
+          k[sidx] = keep_max ? (other > k[sidx] ? other : k[sidx]) : (other < k[sidx] ? other : k[sidx]);
+        }
+      }
+    }
+  }
+  // pre_nms_top_k caps the candidates a class may consume
+  if ((long)lane >= P.k_lim) k[0] = 0ull;
+  if ((long)(32 + lane) >= P.k_lim) k[1] = 0ull;
+  const int n_valid = __popc(__ballot_sync(RPP_FULL_MASK, k[0] != 0ull)) + __popc(__ballot_sync(RPP_FULL_MASK, k[1] != 0ull));
+
+  // 4. greedy NMS, tile by tile
+  const float thr = P.iou_threshold;
+  int nk = 0;
+  u64 last_key = 0ull;   // key of the last box kept so far (uniform)
+  for (int tile = 0; tile < 2 && nk < P.M_cap; ++tile) {
+    const u64 key = k[tile];
+    bool alive = key != 0ull;
+    const u32 cand_any = __ballot_sync(RPP_FULL_MASK, alive);
+    if (cand_any == 0u) break;
+    float4 orig = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bx = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+    float area = 0.0f;
+    if (alive) {
+      orig = col_box(P, b, c, key_tie(key));
+      if (P.clip_before) orig = clip01(orig);
+      const float4 cb = canon_box(orig, area);
+      if (area > 0.0f) bx = cb; else area = 0.0f;
+    }
+    sh->cbox[lane] = bx;
+    sh->carea[lane] = area;
+    __syncwarp();
+    for (int q = 0; q < nk && alive; ++q)
+      if (iou_gt(bx, area, sh->kbox[q], sh->karea[q], thr)) alive = false;
+    const u32 cand_bits = __ballot_sync(RPP_FULL_MASK, alive);
+    u32 row = 0u;
+    for (int j = 0; j < 31; ++j) {
+      if (!((cand_bits >> j) & 1u)) continue;   // uniform
+      if (alive && j < lane && iou_gt(bx, area, sh->cbox[j], sh->carea[j], thr)) row |= 1u << j;
+    }
+    u32 kept_bits = 0u;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const u32 r = __shfl_sync(RPP_FULL_MASK, row, l);
+      if (((cand_bits >> l) & 1u) && (r & kept_bits) == 0u) kept_bits |= 1u << l;
+    }
+    int nnew = __popc(kept_bits);
+    const int room = P.M_cap - nk;
+    while (nnew > room) {
+      kept_bits &= ~(1u << (31 - __clz(kept_bits)));
+      --nnew;
+    }
+    if ((kept_bits >> lane) & 1u) {
+      const int pos = nk + __popc(kept_bits & ((1u << lane) - 1u));
+      sh->kbox[pos] = bx;
+      sh->karea[pos] = area;
+      P.sel_key[p * P.M + pos] = key;
+      P.sel_box[p * P.M + pos] = orig;
+    }
+    if (nnew > 0) last_key = __shfl_sync(RPP_FULL_MASK, key, 31 - __clz(kept_bits));
+    nk += nnew;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    P.sel_cnt[p] = nk;
+    float bd;
+    if (nk >= P.M_cap && nk > 0) bd = key_score(last_key);
+    else if ((long)n_valid >= P.k_lim) bd = -INFINITY;                         // consumed all the class may consume
+    else if (whole_list && list_complete) bd = -INFINITY;                      // class exhausted
+    else bd = whole_list ? s_edge : e0;                                        // the rest scores <= this
+    P.bound[p] = bd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Top-k emission fast path (FilterTopKDetections, rpp_topk and the global pre-NMS filter): when a problem's whole
 // candidate list fits in shared memory, one 1024-thread block scores it, sorts it once (bitonic, <= 16 K keys) and
 // writes the k best keys.  Problems it cannot serve exactly (list overflowed, too long, or fewer than k candidates
