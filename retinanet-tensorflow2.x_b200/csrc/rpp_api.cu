@@ -239,9 +239,14 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       sample_max_kernel<false, false><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
                                                                           plan.rows_per_group, gm);
     LAUNCHED();
-    const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
-    sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
-                                                                                        ps.T_min, T);
+    if (plan.G <= 128) {
+      sample_rank_sort_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), RPP_RANK_CPB * 32, 0, st>>>(
+          gm, C, plan.G, plan.rank, ps.T_min, T);
+    } else {
+      const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
+      sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
+                                                                                          ps.T_min, T);
+    }
     LAUNCHED();
   } else {
     fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(T, P, ps.T_min);
@@ -394,10 +399,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     else
       launch();
     LAUNCHED();
-    perclass_bound_kernel<<<B, 256, (size_t)C * m1 * sizeof(float), st>>>(ps.sel_key, ps.sel_cnt, C, ps.M, m1, ps.M,
-                                                                         stop_L);
+    const int bthreads = (int)std::min<size_t>(1024, align_up((size_t)C * m1, 32));
+    perclass_bound_kernel<<<B, bthreads, (size_t)C * m1 * sizeof(float), st>>>(ps.sel_key, ps.sel_cnt, C, ps.M, m1,
+                                                                              ps.M, stop_L);
     LAUNCHED();
-    pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 248;
+    pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 96;   // re-run classes usually need a few dozen boxes
   }
   if (emit) {   // whole-list sort in shared memory where it applies; the generic kernel takes the rest
     emit_sort_kernel<<<(unsigned)P, RPP_EMIT_NT, sizeof(EmitShared), st>>>(pp);

@@ -202,6 +202,62 @@ __global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int
   }
 }
 
+// Same result with a 128-key register bitonic sort per (image, class): one warp per class (G <= 128).
+__global__ void __launch_bounds__(RPP_RANK_CPB * 32)
+sample_rank_sort_kernel(const u32* __restrict__ gm, int C, int G, int rank, float T_min, float* __restrict__ T) {
+  __shared__ u32 s_gm[128 * RPP_RANK_CPB];
+  const int b = blockIdx.x, c0 = blockIdx.y * RPP_RANK_CPB;
+  const int nc = C - c0 < RPP_RANK_CPB ? C - c0 : RPP_RANK_CPB;
+  for (int i = threadIdx.x; i < G * nc; i += blockDim.x) {
+    const int g = i / nc, cc = i - g * nc;
+    s_gm[g * RPP_RANK_CPB + cc] = gm[((size_t)b * G + g) * C + c0 + cc];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, cc = threadIdx.x >> 5;
+  if (cc >= nc) return;
+  u32 v[4];
+#pragma unroll
+  for (int sidx = 0; sidx < 4; ++sidx) {
+    const int g = sidx * 32 + lane;
+    v[sidx] = g < G ? s_gm[g * RPP_RANK_CPB + cc] : 0xffffffffu;   // pads sort to the end
+  }
+#pragma unroll
+  for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+    for (int j = size >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int ds = j >> 5;   // slot distance 1 or 2
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx) {
+          if ((sidx & ds) == 0) {
+            const int e = sidx * 32 + lane;
+            const bool asc = (e & size) == 0;
+            const u32 a0 = v[sidx], a1 = v[sidx | ds];
+            if (asc ? (a0 > a1) : (a0 < a1)) { v[sidx] = a1; v[sidx | ds] = a0; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx) {
+          const int e = sidx * 32 + lane;
+          const u32 other = __shfl_xor_sync(RPP_FULL_MASK, v[sidx], j);
+          const bool asc = (e & size) == 0;
+          const bool low = (lane & j) == 0;
+          const bool keep_min = asc == low;
+          v[sidx] = keep_min ? (other < v[sidx] ? other : v[sidx]) : (other > v[sidx] ? other : v[sidx]);
+        }
+      }
+    }
+  }
+  // ascending: element `rank` is the answer
+  const int rs = rank >> 5, rl = rank & 31;
+  u32 ans = 0u;
+#pragma unroll
+  for (int sidx = 0; sidx < 4; ++sidx)
+    if (sidx == rs) ans = v[sidx];
+  if (lane == rl) T[(size_t)b * C + c0 + cc] = fmaxf(unord_f32(ans), T_min);
+}
+
 __global__ void fill_kernel(float* p, size_t n, float v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
