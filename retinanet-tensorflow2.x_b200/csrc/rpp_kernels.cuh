@@ -1539,10 +1539,48 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
     if (slot < scnt[c]) return make_key(key_score(sk[i]), (u32)i);
     return P.combined ? 0ull : make_key(0.0f, (u32)i);  // NMSV5 pads scores with 0.0 (A.2)
   };
-  // stage the C*M keys in shared memory once, then select over them.  The per-class counts go to shared memory
-  // first so that only filled slots cost a global load (after the cross-class bound most classes hold a few boxes).
   u64* skeys = reinterpret_cast<u64*>(sh + 1);
-  if (P.keys_in_smem) {
+  int got = 0;
+  // Fast path (the usual case after the cross-class bound: a few boxes per class, at least M in total and no more than
+  // the chunk buffer holds): compact the kept boxes' keys and sort them once.
+  bool fast = false;
+  {
+    // per-class counts -> exclusive offsets (thread 0; C is at most a few thousand)
+    __shared__ int s_total;
+    int* s_pref = reinterpret_cast<int*>(sh->top);   // top[] (1024 u64 = 2048 ints) is not live yet
+    const bool fits = C <= 2047;
+    if (fits) {
+      for (int c = tid; c < C; c += RPP_MERGE_NT) s_pref[c + 1] = scnt[c] < M ? scnt[c] : M;
+      __syncthreads();
+      if (tid == 0) {
+        int run = 0;
+        for (int c = 0; c < C; ++c) { const int n = s_pref[c + 1]; s_pref[c] = run; run += n; }
+        s_pref[C] = run;
+        s_total = run;
+      }
+      __syncthreads();
+      const int total = s_total;
+      // (PerClass*: the zero-score pads of NMSV5 can only matter when a kept score may be <= 0, i.e. with a
+      // negative score threshold; those cases take the general path)
+      fast = total >= M && total <= RPP_CHUNK_CAP && (P.combined || P.score_nonneg);
+      if (fast) {
+        for (int c = tid; c < C; c += RPP_MERGE_NT) {
+          const int o = s_pref[c], n = s_pref[c + 1] - o;
+          for (int slot = 0; slot < n; ++slot)
+            sh->chunk[o + slot] = make_key(key_score(sk[(size_t)c * M + slot]), (u32)(c * M + slot));
+        }
+        const int P2 = next_pow2(total < 2 ? 2 : total);
+        for (int i = total + tid; i < P2; i += RPP_MERGE_NT) sh->chunk[i] = 0ull;
+        __syncthreads();
+        bitonic_sort_desc<RPP_MERGE_NT>(sh->chunk, P2);
+        for (int i = tid; i < M; i += RPP_MERGE_NT) sh->top[i] = sh->chunk[i];   // s_pref is dead from here on
+        got = M;
+        __syncthreads();
+      }
+    }
+  }
+  // General path: stage the C*M keys (pads included) in shared memory once, then select over them.
+  if (!fast && P.keys_in_smem) {
     int* s_cnt = reinterpret_cast<int*>(sh->top);   // top[] is not live yet: C <= 2048 ints fit
     const bool cnt_smem = C <= 2048;
     if (cnt_smem) {
@@ -1557,8 +1595,7 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
     __syncthreads();
   }
   u64 KB = ~0ull;
-  int got = 0;
-  while (got < M) {
+  while (!fast && got < M) {
     const int m = P.keys_in_smem
         ? select_chunk<RPP_MERGE_NT>([&](int i) { return skeys[i]; }, C * M, KB, M - got, sh->chunk, RPP_CHUNK_CAP,
                                      &sh->sel)
