@@ -61,7 +61,13 @@ typedef struct rpp_config {
   int filter_per_class;           /* inference.filter_per_class */
   int max_detections;             /* inference.max_detections */
   int soft_ignores_iou_threshold; /* 1 = TF >= 2.3 NonMaxSuppressionV5 (default); 0 = older kernel form */
-  int reserved[7];                /* must be zero */
+  int tpu_semantics;              /* 1 = GlobalHardNMS / PerClassHardNMS run the reference's TPUStrategy branches
+                                     (_tpu_global_hard_nms :381-432, _tpu_per_class_hard_nms :288-379: a real global
+                                     hard NMS, tf.image.non_max_suppression_padded arithmetic, int32 classes, -1
+                                     padding in every field); the reference selects them by detecting a TPUStrategy
+                                     (:199-208), which has no counterpart here.  0 (default) = the non-TPU branches.
+                                     Ignored by the other modes, as in the reference. */
+  int reserved[6];                /* must be zero */
 } rpp_config;
 
 /* Lifetime.  rpp_create validates the config (reference: GenerateDetections.__init__ :185-217 and
@@ -131,6 +137,24 @@ int rpp_detect_levels(void* handle, const float* const* d_deltas_levels, const f
 int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, const void* const* d_logits, int dtype,
                      int B, float* d_boxes_BM4, float* d_scores_BM, void* d_classes_BM, int* d_valid_B,
                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* EfficientNMS_TRT-compatible entry: the node the reference appends to the exported graph in mode onnx_tensorrt
+ * (onnx_utils.py:13-85) — inputs in the node's order (raw-boxes [B,N,4], class-logits [B,N,C], anchor-boxes [1,N,4] =
+ * AnchorBoxGenerator.boxes, [cx,cy,w,h] pixels; NULL = the handle's own table), outputs in the node's order
+ * (valid_detections [B,1] i32, detection_boxes [B,M,4], detection_scores [B,M], detection_classes [B,M] i32) — with
+ * the attributes the reference sets: max_output_boxes = max_detections, score_threshold, iou_threshold,
+ * score_activation = True (sigmoid), box_coding = 1 (centre-size boxes decoded against the anchors, no variance
+ * scaling, no normalisation; outputs in the same coding, pixels), background_class = -1 (none), class-aware
+ * suppression.  The handle's NMS mode and pre_nms_top_k are not used.
+ * Semantics as published for TensorRT's efficientNMSPlugin: candidates = sigmoid(logit) >= score_threshold; per image
+ * the 4096 best (anchor, class) pairs; greedy in score order, a box is dropped when a kept box of the same class has
+ * IoU > iou_threshold; the first max_output_boxes kept; outputs zero-filled beyond the count.  Ties are ordered by
+ * flat index (the plugin's own tie order is unspecified).  PARITY UNPINNED: the plugin is not part of the reference
+ * tree nor installed here; the oracle restates the same algorithm (rpp_ref_efficient_nms). */
+int rpp_efficient_nms(void* handle, const float* d_raw_boxes_BN4, const float* d_class_logits_BNC,
+                      const float* d_anchor_boxes_N4, int B, int* d_valid_detections_B1, float* d_detection_boxes_BM4,
+                      float* d_detection_scores_BM, int* d_detection_classes_BM,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Same, from HOST buffers (the serving call of export.py:233-253 / evaluate_saved_model.py: tensors arrive from
  * the host and detections are consumed on the host).  Copies H2D in image chunks overlapped with the kernels,

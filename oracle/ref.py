@@ -203,6 +203,93 @@ def detect(class_logits, encoded_boxes, anchor_boxes, H, W, mode, iou_threshold=
     return {'boxes': bo, 'scores': so, 'classes': co, 'valid_detections': vo}
 
 
+def iou_padded(a, b):
+    """_bbox_overlap of tf.image.non_max_suppression_padded for one pair of boxes."""
+    a = _f32(a)
+    b = _f32(b)
+    lib().rpp_ref_iou_padded.restype = ctypes.c_float
+    return float(lib().rpp_ref_iou_padded(_p(a), _p(b)))
+
+
+def nms_padded(boxes, scores, max_output_size, iou_threshold, score_threshold=None, exact_fixed_point=True):
+    """tf.image.non_max_suppression_padded(..., pad_to_max_output_size=True, canonicalized_coordinates=True) for one
+    image -> (indices[M], num_valid).  score_threshold=None: no score filter (the per-class TPU branch)."""
+    b = _f32(boxes)
+    s = _f32(scores)
+    M = int(max_output_size)
+    idx = np.zeros(M, np.int32)
+    use = score_threshold is not None
+    valid = lib().rpp_ref_nms_padded(_p(b), _p(s), len(s), M, ctypes.c_float(iou_threshold), int(use),
+                                     ctypes.c_float(score_threshold if use else 0.0), int(bool(exact_fixed_point)),
+                                     _p(idx, _i32p))
+    return idx, int(valid)
+
+
+def generate_detections_tpu(mode, scores, boxes, iou_threshold=0.5, score_threshold=0.05, max_detections=100,
+                            exact_fixed_point=True, threads=1):
+    """GenerateDetections under TPUStrategy (postprocessing_ops.py:288-432): mode GlobalHardNMS / PerClassHardNMS."""
+    m = _mode_id(mode)
+    s = _f32(scores)
+    b = _f32(boxes)
+    B, n, C = s.shape
+    q = 1 if b.ndim == 3 else b.shape[2]
+    M = int(max_detections)
+    bo = np.empty((B, M, 4), np.float32)
+    so = np.empty((B, M), np.float32)
+    co = np.empty((B, M), np.int32)
+    vo = np.empty((B,), np.int32)
+    r = lib().rpp_ref_generate_detections_tpu(m, _p(s), _p(b), ctypes.c_long(B), ctypes.c_long(n), q, C,
+                                              ctypes.c_float(iou_threshold), ctypes.c_float(score_threshold), M,
+                                              int(bool(exact_fixed_point)), _p(bo), _p(so), _p(co, _i32p),
+                                              _p(vo, _i32p), threads)
+    if r != 0:
+        raise ValueError('the TPU branches exist for GlobalHardNMS (3-D boxes) and PerClassHardNMS only')
+    return {'boxes': bo, 'scores': so, 'classes': co, 'valid_detections': vo}
+
+
+def detect_tpu(class_logits, encoded_boxes, anchor_boxes, H, W, mode, iou_threshold=0.5, score_threshold=0.05,
+               pre_nms_top_k=5000, filter_per_class=True, max_detections=100, box_variance=(0.1, 0.1, 0.2, 0.2),
+               scale_box_targets=False, threads=1):
+    """TransformBoxesAndScores -> FilterTopKDetections -> GenerateDetections (TPU branches)."""
+    m = _mode_id(mode)
+    lg = _f32(class_logits)
+    d = _f32(encoded_boxes)
+    a = _f32(anchor_boxes)
+    B, N, C = lg.shape
+    M = int(max_detections)
+    bv = np.asarray(box_variance, np.float32)
+    bo = np.empty((B, M, 4), np.float32)
+    so = np.empty((B, M), np.float32)
+    co = np.empty((B, M), np.int32)
+    vo = np.empty((B,), np.int32)
+    r = lib().rpp_ref_detect_tpu(_p(lg), _p(d), _p(a), ctypes.c_long(B), ctypes.c_long(N), C, H, W, _p(bv),
+                                 int(bool(scale_box_targets)), m, ctypes.c_float(iou_threshold),
+                                 ctypes.c_float(score_threshold), int(pre_nms_top_k), int(bool(filter_per_class)), M,
+                                 _p(bo), _p(so), _p(co, _i32p), _p(vo, _i32p), threads)
+    if r != 0:
+        raise ValueError('invalid mode / filter combination for the TPU branches')
+    return {'boxes': bo, 'scores': so, 'classes': co, 'valid_detections': vo}
+
+
+def efficient_nms(raw_boxes, class_logits, anchor_boxes, max_output_boxes=100, score_threshold=0.05, iou_threshold=0.5,
+                  threads=1):
+    """EfficientNMS_TRT as the reference configures it (onnx_utils.py:38-46) -> (valid_detections [B,1],
+    detection_boxes [B,M,4] centre-size, detection_scores [B,M], detection_classes [B,M] i32).  Parity unpinned."""
+    d = _f32(raw_boxes)
+    lg = _f32(class_logits)
+    a = _f32(anchor_boxes).reshape(-1, 4)
+    B, N, C = lg.shape
+    M = int(max_output_boxes)
+    vo = np.empty((B, 1), np.int32)
+    bo = np.empty((B, M, 4), np.float32)
+    so = np.empty((B, M), np.float32)
+    co = np.empty((B, M), np.int32)
+    lib().rpp_ref_efficient_nms(_p(d), _p(lg), _p(a), ctypes.c_long(B), ctypes.c_long(N), C, M,
+                                ctypes.c_float(score_threshold), ctypes.c_float(iou_threshold), _p(vo, _i32p), _p(bo),
+                                _p(so), _p(co, _i32p), threads)
+    return vo, bo, so, co
+
+
 def coco_format(detections, image_ids, resize_scales, input_shape, rescale_detections=True, class_id_map=None):
     """COCOEvaluator.accumulate_results (eval/coco_evaluator.py:95-134) restated in numpy, line by line."""
     out = []

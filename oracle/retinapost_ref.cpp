@@ -190,6 +190,134 @@ int nms_v5(const float* boxes /*[n,4]*/, long box_stride, const float* scores, l
   return valid;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// tf.image.non_max_suppression_padded (tensorflow/python/ops/image_ops_impl.py: non_max_suppression_padded ->
+// non_max_suppression_padded_v2 with its helpers _bbox_overlap, _self_suppression, _cross_suppression,
+// _suppression_loop_body) for ONE image, as the TPU branches call it (postprocessing_ops.py:323-330,
+// :392-400): canonicalized_coordinates=True (no min/max flip), sorted_input=False, pad_to_max_output_size=True,
+// tile_size=512.  TensorFlow is not in /root/reference: restated from the published algorithm, tile structure
+// included, so that the CUDA path (a plain greedy scan) is checked against the reference's formulation:
+//   1. optional score filter: scores *= (score > thr), boxes *= (score > thr);
+//   2. argsort descending (top_k: ties -> lower index);
+//   3. pad to a multiple of 512 boxes with zeros; while output_size < M and tiles remain:
+//        cross-suppress the tile against every earlier tile (kept boxes only, the others are already zeroed), then
+//        iterate the in-tile self-suppression to its fixed point, zero the suppressed boxes, count the boxes with
+//        any coordinate > 0;
+//   4. the first M non-zero boxes are the selection; indices beyond num_valid = min(output_size, M) are 0.
+// IoU (_bbox_overlap): inter / (area_a + area_b - inter + 1e-8), fp32; a box suppresses when iou >= threshold
+// (the NonMaxSuppressionV5 kernel uses a strict >).
+// exact_fixed_point = 1: the self-suppression loop runs until no row changes.  0: TF's own stop test
+// `iou_sum - iou_sum_new > iou_threshold` on fp32 sums (it can stop one round early when the removed IoU mass is
+// within rounding of the threshold; the sums' association is the framework's, here row-major sequential).
+// Returns num_valid; idx_out [M].  The batched loop condition of TF (`reduce_min(output_size) < M`) only makes
+// finished images idle along: per-image results are independent.
+// ------------------------------------------------------------------------------------------------------------
+inline float iou_padded_ref(const float* a, const float* b) {
+  const float i_xmin = std::max(a[1], b[1]), i_xmax = std::min(a[3], b[3]);
+  const float i_ymin = std::max(a[0], b[0]), i_ymax = std::min(a[2], b[2]);
+  const float i_area = std::max(i_xmax - i_xmin, 0.0f) * std::max(i_ymax - i_ymin, 0.0f);
+  const float a_area = (a[2] - a[0]) * (a[3] - a[1]);
+  const float b_area = (b[2] - b[0]) * (b[3] - b[1]);
+  const float u_area = a_area + b_area - i_area + 1e-8f;
+  return i_area / u_area;
+}
+
+int nms_padded(const float* boxes_in /*[n,4]*/, long box_stride, const float* scores_in, long score_stride, int n, int M,
+               float iou_threshold, bool use_score_threshold, float score_threshold, int exact_fixed_point,
+               int* idx_out /*[M]*/) {
+  const int TS = 512;
+  std::vector<float> sc(n);
+  std::vector<float> bx((size_t)n * 4);
+  for (int i = 0; i < n; ++i) {
+    float s = scores_in[(long)i * score_stride];
+    const float* b = boxes_in + (long)i * box_stride;
+    float m = 1.0f;
+    if (use_score_threshold) m = s > score_threshold ? 1.0f : 0.0f;   // filter_by_score
+    sc[i] = use_score_threshold ? s * m : s;
+    for (int k = 0; k < 4; ++k) bx[(size_t)i * 4 + k] = use_score_threshold ? b[k] * m : b[k];
+  }
+  std::vector<int> order(n);   // _sort_scores_and_boxes: argsort DESCENDING = top_k(k = n)
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int d) { return sc[a] > sc[d]; });
+  const int nbp = (std::max(n, M) + TS - 1) / TS * TS;   // num_boxes_after_padding
+  std::vector<float> sb((size_t)nbp * 4, 0.0f);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 4; ++k) sb[(size_t)i * 4 + k] = bx[(size_t)order[i] * 4 + k];
+  const int num_iterations = nbp / TS;
+  int output_size = 0;
+  std::vector<float> iou((size_t)TS * TS);
+  for (int idx = 0; idx < num_iterations && output_size < M; ++idx) {   // _suppression_loop_body
+    float* slice = sb.data() + (size_t)idx * TS * 4;
+    for (int inner = 0; inner < idx; ++inner) {                         // _cross_suppression
+      const float* prev = sb.data() + (size_t)inner * TS * 4;
+      for (int j = 0; j < TS; ++j) {
+        bool all_below = true;
+        for (int i = 0; i < TS && all_below; ++i)
+          if (!(iou_padded_ref(prev + (size_t)i * 4, slice + (size_t)j * 4) < iou_threshold)) all_below = false;
+        if (!all_below) slice[j * 4] = slice[j * 4 + 1] = slice[j * 4 + 2] = slice[j * 4 + 3] = 0.0f;
+      }
+      // (TF multiplies the slice by the 0/1 mask after each earlier tile; zeroing at once is the same because a
+      // zeroed box has IoU 0 with everything and iou_threshold > 0)
+    }
+    for (int i = 0; i < TS; ++i)
+      for (int j = 0; j < TS; ++j) {
+        float v = 0.0f;
+        if (j > i) {
+          v = iou_padded_ref(slice + (size_t)i * 4, slice + (size_t)j * 4);
+          if (!(v >= iou_threshold)) v = 0.0f;
+        }
+        iou[(size_t)i * TS + j] = v;
+      }
+    auto total = [&]() { float t = 0.0f; for (float v : iou) t += v; return t; };
+    float iou_sum = total();
+    for (;;) {                                                          // _self_suppression
+      std::vector<char> can_suppress_others(TS), keep_row(TS);
+      for (int j = 0; j < TS; ++j) {
+        float mx = 0.0f;
+        for (int i = 0; i < TS; ++i) mx = std::max(mx, iou[(size_t)i * TS + j]);
+        can_suppress_others[j] = mx < iou_threshold;
+      }
+      for (int j = 0; j < TS; ++j) {
+        float mx = 0.0f;
+        for (int i = 0; i < TS; ++i)
+          if (can_suppress_others[i]) mx = std::max(mx, iou[(size_t)i * TS + j]);
+        keep_row[j] = mx < iou_threshold;
+      }
+      bool changed = false;
+      for (int j = 0; j < TS; ++j)
+        if (!keep_row[j])
+          for (int k = 0; k < TS; ++k)
+            if (iou[(size_t)j * TS + k] != 0.0f) { iou[(size_t)j * TS + k] = 0.0f; changed = true; }
+      const float iou_sum_new = total();
+      const bool again = exact_fixed_point ? changed : (iou_sum - iou_sum_new > iou_threshold);
+      iou_sum = iou_sum_new;
+      if (!again) break;
+    }
+    for (int j = 0; j < TS; ++j) {
+      float col = 0.0f;
+      for (int i = 0; i < TS; ++i) col += iou[(size_t)i * TS + j];
+      if (col > 0.0f) slice[j * 4] = slice[j * 4 + 1] = slice[j * 4 + 2] = slice[j * 4 + 3] = 0.0f;   // suppressed_box
+    }
+    for (int j = 0; j < TS; ++j)
+      if (slice[j * 4] > 0.0f || slice[j * 4 + 1] > 0.0f || slice[j * 4 + 2] > 0.0f || slice[j * 4 + 3] > 0.0f)
+        ++output_size;
+  }
+  const int num_valid = std::min(output_size, M);
+  // idx = nbp - top_k(any(selected > 0) * range(nbp, 0, -1), M): positions of the first M non-zero boxes
+  int found = 0;
+  for (int i = 0; i < nbp && found < M; ++i) {
+    const float* b = sb.data() + (size_t)i * 4;
+    if (b[0] > 0.0f || b[1] > 0.0f || b[2] > 0.0f || b[3] > 0.0f) {
+      const int pos = std::min(i, n - 1);
+      idx_out[found] = found < num_valid ? order[pos] : 0;
+      ++found;
+    }
+  }
+  for (int i = found; i < M; ++i) idx_out[i] = 0;
+  for (int i = num_valid; i < M; ++i) idx_out[i] = 0;
+  return num_valid;
+}
+
 struct Det {
   float score;
   int cls;
@@ -499,15 +627,124 @@ int rpp_ref_generate_detections(int mode, const float* scores, const float* boxe
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// a10/a11  the TPUStrategy branches of GenerateDetections (postprocessing_ops.py:288-432), offered by the product as
+// the opt-in `tpu_semantics` of the two hard modes.
+//   mode 2 (GlobalHardNMS)   -> _tpu_global_hard_nms   :381-432: a real global hard NMS (true IoU threshold);
+//   mode 4 (PerClassHardNMS) -> _tpu_per_class_hard_nms :288-379.
+// Outputs: boxes [B,M,4], scores [B,M], classes [B,M] int32 (both), valid [B] i32; invalid positions are -1 in
+// every field.
+// ------------------------------------------------------------------------------------------------------------
+int rpp_ref_nms_padded(const float* boxes, const float* scores, int n, int M, float iou_threshold,
+                       int use_score_threshold, float score_threshold, int exact_fixed_point, int* idx_out) {
+  return nms_padded(boxes, 4, scores, 1, n, M, iou_threshold, use_score_threshold != 0, score_threshold,
+                    exact_fixed_point, idx_out);
+}
+
+float rpp_ref_iou_padded(const float* a, const float* b) { return iou_padded_ref(a, b); }
+
+int rpp_ref_generate_detections_tpu(int mode, const float* scores, const float* boxes_in, long B, long n, int q, int C,
+                                    float iou_threshold, float score_threshold, int M, int exact_fixed_point,
+                                    float* boxes_out, float* scores_out, int* classes_out, int* valid_out,
+                                    int threads) {
+  if (mode != 2 && mode != 4) return -1;
+  if (mode == 2 && q != 1) return -1;
+  std::vector<float> boxes((size_t)B * n * q * 4);   // tf.clip_by_value :291, :385
+  for (size_t i = 0; i < boxes.size(); ++i) boxes[i] = clip01(boxes_in[i]);
+
+  if (mode == 2) {
+    parallel_for(B, threads, [&](long b) {
+      std::vector<float> s(n);
+      std::vector<int> cls(n);
+      for (long i = 0; i < n; ++i) {   // reduce_max :382 / argmax :383 (first maximum)
+        const float* row = scores + (b * n + i) * C;
+        int best = 0;
+        for (int c = 1; c < C; ++c)
+          if (row[c] > row[best]) best = c;
+        s[i] = row[best];
+        cls[i] = best;
+      }
+      std::vector<int> idx(M);
+      const int valid = nms_padded(boxes.data() + b * n * 4, 4, s.data(), 1, (int)n, M, iou_threshold, true,
+                                   score_threshold, exact_fixed_point, idx.data());   // :392-400
+      valid_out[b] = valid;
+      for (int i = 0; i < M; ++i) {    // :402-420: gather [boxes, classes, scores], -1 beyond valid
+        float* bo = boxes_out + (b * M + i) * 4;
+        if (i < valid) {
+          const float* bx = boxes.data() + (b * n + idx[i]) * 4;
+          bo[0] = bx[0]; bo[1] = bx[1]; bo[2] = bx[2]; bo[3] = bx[3];
+          scores_out[b * M + i] = s[idx[i]];
+          classes_out[b * M + i] = (int)(float)cls[idx[i]];   // cast f32 -> int32 (:425-426)
+        } else {
+          bo[0] = bo[1] = bo[2] = bo[3] = -1.0f;
+          scores_out[b * M + i] = -1.0f;
+          classes_out[b * M + i] = -1;
+        }
+      }
+    });
+    return 0;
+  }
+
+  std::vector<float> f_scores((size_t)B * C * M), f_boxes((size_t)B * C * M * 4);
+  parallel_for(B * C, threads, [&](long t) {
+    const long b = t / C;
+    const int c = (int)(t % C);
+    const int qi = q > 1 ? c : 0;    // boxes_idx :303-320
+    std::vector<int> idx(M);
+    const float* bx0 = boxes.data() + (b * n * q + qi) * 4;
+    const float* sc0 = scores + b * n * C + c;
+    nms_padded(bx0, (long)q * 4, sc0, C, (int)n, M, iou_threshold, false, 0.0f, exact_fixed_point,
+               idx.data());           // :323-330: no score threshold inside
+    for (int i = 0; i < M; ++i) {     // :332-335 gathers (padded index 0 -> that class's row 0, score included)
+      const float* bx = bx0 + (long)idx[i] * q * 4;
+      float* bo = f_boxes.data() + (t * M + i) * 4;
+      bo[0] = bx[0]; bo[1] = bx[1]; bo[2] = bx[2]; bo[3] = bx[3];
+      f_scores[t * M + i] = sc0[(long)idx[i] * C];
+    }
+  });
+  parallel_for(B, threads, [&](long b) {
+    const int tot = C * M;
+    std::vector<int> top(M);
+    topk_row(f_scores.data() + b * tot, tot, M, true, top.data());   // :350-351 tf.nn.top_k (sorted)
+    int valid = 0;
+    for (int i = 0; i < M; ++i) {
+      const float sc = f_scores[b * tot + top[i]];
+      const bool ok = sc > score_threshold;                           // :358-359
+      float* bo = boxes_out + (b * M + i) * 4;
+      if (ok) {
+        const float* bx = f_boxes.data() + (b * tot + top[i]) * 4;
+        bo[0] = bx[0]; bo[1] = bx[1]; bo[2] = bx[2]; bo[3] = bx[3];
+        scores_out[b * M + i] = sc;
+        classes_out[b * M + i] = top[i] / M;
+        ++valid;
+      } else {                                                        // :365-368
+        bo[0] = bo[1] = bo[2] = bo[3] = -1.0f;
+        scores_out[b * M + i] = -1.0f;
+        classes_out[b * M + i] = -1;
+      }
+    }
+    valid_out[b] = valid;                                             // :361-363
+  });
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // a12  ModelBuilder.add_post_processing_stage (model/builder.py:153-190) after FuseDetections:
 //      TransformBoxesAndScores -> [FilterTopKDetections if pre_nms_top_k > 0] -> GenerateDetections.
 // class_logits [B,N,C], encoded_boxes [B,N,4], anchors [N,4].
 // ------------------------------------------------------------------------------------------------------------
-int rpp_ref_detect(const float* class_logits, const float* encoded_boxes, const float* anchors, long B, long N, int C,
-                   int H, int W, const float* box_variance, int scale_box_targets, int mode, float iou_threshold,
-                   float score_threshold, float sigma, int pre_nms_top_k, int filter_per_class, int M,
-                   int topk_sorted, int soft_ignores_iou_threshold, float* boxes_out, float* scores_out,
-                   void* classes_out, int* valid_out, int threads) {
+static int detect_common(const float* class_logits, const float* encoded_boxes, const float* anchors, long B, long N,
+                         int C, int H, int W, const float* box_variance, int scale_box_targets, int mode,
+                         float iou_threshold, float score_threshold, float sigma, int pre_nms_top_k,
+                         int filter_per_class, int M, int topk_sorted, int soft_ignores_iou_threshold, int tpu,
+                         float* boxes_out, float* scores_out, void* classes_out, int* valid_out, int threads) {
+  auto gen = [&](const float* sc, const float* bx, long n, int q) -> int {
+    if (tpu)
+      return rpp_ref_generate_detections_tpu(mode, sc, bx, B, n, q, C, iou_threshold, score_threshold, M, 1,
+                                             boxes_out, scores_out, (int*)classes_out, valid_out, threads);
+    return rpp_ref_generate_detections(mode, sc, bx, B, n, q, C, iou_threshold, score_threshold, M, sigma, topk_sorted,
+                                       soft_ignores_iou_threshold, boxes_out, scores_out, classes_out, valid_out,
+                                       threads);
+  };
   std::vector<float> scores((size_t)B * N * C), boxes((size_t)B * N * 4);
   rpp_ref_sigmoid(class_logits, scores.data(), B * N * C, threads);
   rpp_ref_decode_boxes(encoded_boxes, anchors, B, N, H, W, box_variance, scale_box_targets, boxes.data(), threads);
@@ -517,21 +754,105 @@ int rpp_ref_detect(const float* class_logits, const float* encoded_boxes, const 
       std::vector<float> fs((size_t)B * kk * C), fb((size_t)B * kk * C * 4);
       rpp_ref_filter_per_class(scores.data(), boxes.data(), B, N, C, pre_nms_top_k, topk_sorted, fs.data(),
                                fb.data(), nullptr, threads);
-      return rpp_ref_generate_detections(mode, fs.data(), fb.data(), B, kk, C, C, iou_threshold, score_threshold, M,
-                                         sigma, topk_sorted, soft_ignores_iou_threshold, boxes_out, scores_out,
-                                         classes_out, valid_out, threads);
+      return gen(fs.data(), fb.data(), kk, C);
     }
     const long kk = std::min<long>(pre_nms_top_k, N * C);
     std::vector<float> fs((size_t)B * kk * C), fb((size_t)B * kk * 4);
     rpp_ref_filter_global(scores.data(), boxes.data(), B, N, C, pre_nms_top_k, topk_sorted, fs.data(), fb.data(),
                           nullptr, threads);
-    return rpp_ref_generate_detections(mode, fs.data(), fb.data(), B, kk, 1, C, iou_threshold, score_threshold, M,
-                                       sigma, topk_sorted, soft_ignores_iou_threshold, boxes_out, scores_out,
-                                       classes_out, valid_out, threads);
+    return gen(fs.data(), fb.data(), kk, 1);
   }
-  return rpp_ref_generate_detections(mode, scores.data(), boxes.data(), B, N, 1, C, iou_threshold, score_threshold,
-                                     M, sigma, topk_sorted, soft_ignores_iou_threshold, boxes_out, scores_out,
-                                     classes_out, valid_out, threads);
+  return gen(scores.data(), boxes.data(), N, 1);
+}
+
+int rpp_ref_detect(const float* class_logits, const float* encoded_boxes, const float* anchors, long B, long N, int C,
+                   int H, int W, const float* box_variance, int scale_box_targets, int mode, float iou_threshold,
+                   float score_threshold, float sigma, int pre_nms_top_k, int filter_per_class, int M,
+                   int topk_sorted, int soft_ignores_iou_threshold, float* boxes_out, float* scores_out,
+                   void* classes_out, int* valid_out, int threads) {
+  return detect_common(class_logits, encoded_boxes, anchors, B, N, C, H, W, box_variance, scale_box_targets, mode,
+                       iou_threshold, score_threshold, sigma, pre_nms_top_k, filter_per_class, M, topk_sorted,
+                       soft_ignores_iou_threshold, 0, boxes_out, scores_out, classes_out, valid_out, threads);
+}
+
+// The same composition with the TPU branches of GenerateDetections (mode 2 or 4).
+int rpp_ref_detect_tpu(const float* class_logits, const float* encoded_boxes, const float* anchors, long B, long N,
+                       int C, int H, int W, const float* box_variance, int scale_box_targets, int mode,
+                       float iou_threshold, float score_threshold, int pre_nms_top_k, int filter_per_class, int M,
+                       float* boxes_out, float* scores_out, int* classes_out, int* valid_out, int threads) {
+  if (mode != 2 && mode != 4) return -1;
+  if (mode == 2 && pre_nms_top_k > 0 && filter_per_class) return -1;
+  return detect_common(class_logits, encoded_boxes, anchors, B, N, C, H, W, box_variance, scale_box_targets, mode,
+                       iou_threshold, score_threshold, 0.0f, pre_nms_top_k, filter_per_class, M, 1, 1, 1, boxes_out,
+                       scores_out, classes_out, valid_out, threads);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// §8f-4  EfficientNMS_TRT, the node the reference appends in export mode onnx_tensorrt (onnx_utils.py:13-85) with
+// attributes score_activation=True, box_coding=1, background_class=-1, max_output_boxes=M.  The plugin is part of
+// TensorRT (plugin/efficientNMSPlugin), which is neither in /root/reference nor installable here: PARITY UNPINNED.
+// Restated from its published algorithm: filter sigmoid(logit) >= score_threshold, keep the 4096 best (anchor,
+// class) pairs per image, decode centre-size boxes against the anchors (no variance, no normalisation), greedy
+// class-aware NMS (IoU > threshold drops; IoU = inter / (a1 + a2 - inter), 0 when an area or the intersection is
+// not positive), first M kept, outputs in centre-size coding, zero-filled beyond the count.  Ties are ordered by
+// flat index (anchor * C + class); the plugin's own tie order is unspecified.
+// ------------------------------------------------------------------------------------------------------------
+int rpp_ref_efficient_nms(const float* raw_boxes /*[B,N,4]*/, const float* class_logits /*[B,N,C]*/,
+                          const float* anchors /*[N,4] cx,cy,w,h*/, long B, long N, int C, int M,
+                          float score_threshold, float iou_threshold, int* valid_out /*[B]*/,
+                          float* boxes_out /*[B,M,4]*/, float* scores_out /*[B,M]*/, int* classes_out /*[B,M]*/,
+                          int threads) {
+  const long selected = 4096;
+  parallel_for(B, threads, [&](long b) {
+    std::vector<std::pair<float, long>> cand;
+    for (long f = 0; f < N * C; ++f) {
+      const float s = sigmoid_ref(class_logits[b * N * C + f]);
+      if (s >= score_threshold) cand.emplace_back(s, f);
+    }
+    auto better = [](const std::pair<float, long>& a, const std::pair<float, long>& d) {
+      return a.first > d.first || (a.first == d.first && a.second < d.second);
+    };
+    const long take = std::min<long>(selected, (long)cand.size());
+    std::partial_sort(cand.begin(), cand.begin() + take, cand.end(), better);
+    struct Kept { float box[4]; float area; int cls; };
+    std::vector<Kept> kept;
+    for (int i = 0; i < M; ++i) {
+      float* bo = boxes_out + (b * M + i) * 4;
+      bo[0] = bo[1] = bo[2] = bo[3] = 0.0f;
+      scores_out[b * M + i] = 0.0f;
+      classes_out[b * M + i] = 0;
+    }
+    for (long i = 0; i < take && (int)kept.size() < M; ++i) {
+      const long row = cand[i].second / C;
+      const int cls = (int)(cand[i].second % C);
+      const float* d = raw_boxes + (b * N + row) * 4;
+      const float* a = anchors + row * 4;
+      const float cx = d[0] * a[2] + a[0], cy = d[1] * a[3] + a[1];
+      const float hw = (a[2] * exp_ref(d[2])) * 0.5f, hh = (a[3] * exp_ref(d[3])) * 0.5f;
+      Kept k{{cx - hw, cy - hh, cx + hw, cy + hh}, 0.0f, cls};
+      const float w = k.box[2] - k.box[0], h = k.box[3] - k.box[1];
+      k.area = (w > 0.0f && h > 0.0f) ? w * h : 0.0f;
+      bool ok = true;
+      for (const Kept& o : kept) {
+        if (o.cls != cls || !(k.area > 0.0f) || !(o.area > 0.0f)) continue;
+        const float iw = std::min(k.box[2], o.box[2]) - std::max(k.box[0], o.box[0]);
+        const float ih = std::min(k.box[3], o.box[3]) - std::max(k.box[1], o.box[1]);
+        if (!(iw > 0.0f && ih > 0.0f)) continue;
+        const float inter = iw * ih;
+        const float uni = k.area + o.area - inter;
+        if (uni > 0.0f && inter / uni > iou_threshold) { ok = false; break; }
+      }
+      if (!ok) continue;
+      const int pos = (int)kept.size();
+      float* bo = boxes_out + (b * M + pos) * 4;
+      bo[0] = k.box[0] + 0.5f * w; bo[1] = k.box[1] + 0.5f * h; bo[2] = w; bo[3] = h;
+      scores_out[b * M + pos] = cand[i].first;
+      classes_out[b * M + pos] = cls;
+      kept.push_back(k);
+    }
+    valid_out[b] = (int)kept.size();
+  });
+  return 0;
 }
 
 int rpp_ref_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

@@ -152,6 +152,12 @@ struct Arena {
   }
 };
 
+// rpp_config.tpu_semantics: the TPUStrategy branches of GenerateDetections replace the two hard modes
+// (postprocessing_ops.py:549-550, :558-559); the other modes are not affected by it.
+bool tpu_branch(const rpp_config& c) {
+  return c.tpu_semantics && (c.mode == RPP_GLOBAL_HARD_NMS || c.mode == RPP_PER_CLASS_HARD_NMS);
+}
+
 bool is_per_class_mode(int mode) {
   return mode == RPP_COMBINED_NMS || mode == RPP_PER_CLASS_HARD_NMS || mode == RPP_PER_CLASS_SOFT_NMS;
 }
@@ -167,8 +173,11 @@ struct ProblemSet {
   int clip_before; float iou_threshold; float score_threshold; float T_min;
   float soft_sigma_tf; int tie_is_rank;
   int two_pass_m1;         // > 0: probe with this many kept per class, bound per image, finish (per-class modes)
+  int padded;              // RPP_CONSUME_PADDED: 1 global (score filter inside), 2 per class (no score filter inside)
+  int row0_mode;
   // out (workspace)
   u64* sel_key; float4* sel_box; int* sel_cnt; u64* emit_key;
+  float* pad_score; float4* pad_box;
 };
 
 int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaStream_t st2 = nullptr,
@@ -207,6 +216,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       r_meta = ar.take<uint2>(P * (size_t)r_cap);
       r_box = ar.take<float4>(P * (size_t)r_cap);
     }
+  }
+  ps.pad_score = nullptr; ps.pad_box = nullptr;
+  if (ps.padded == 2) {
+    ps.pad_score = ar.take<float>(P);
+    ps.pad_box = ar.take<float4>(P);
   }
   float* bound = nullptr;
   float* stop_L = nullptr;
@@ -380,10 +394,19 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   pp.r_key = r_key; pp.r_meta = r_meta; pp.r_box = r_box; pp.r_cap = r_cap;
   pp.emit_key = ps.emit_key;
   pp.emit_done = emit_done;
+  pp.padded = ps.padded; pp.row0_mode = ps.row0_mode;
+  pp.stop_score = ps.score_threshold;
+  pp.pad_score = ps.pad_score; pp.pad_box = ps.pad_box;
+  if (ps.padded == 2) {   // every row is a candidate of the NMS; the collect pass still lists the rows above the threshold
+    pp.score_threshold = -INFINITY;
+    pp.T_min = -INFINITY;
+  }
   const size_t smem_nms = align_up(nms_shared_bytes(pp.M_lim), 16);
   auto launch = [&](void) {
     if (ps.consumer == RPP_CONSUME_HARD)
       col_problem_kernel<RPP_CONSUME_HARD><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+    else if (ps.consumer == RPP_CONSUME_PADDED)
+      col_problem_kernel<RPP_CONSUME_PADDED><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
     else if (ps.consumer == RPP_CONSUME_SOFT)
       col_problem_kernel<RPP_CONSUME_SOFT><<<(unsigned)P, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
     else
@@ -444,7 +467,15 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   ps.score_threshold = c.score_threshold;
   ps.T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
   ps.tie_is_rank = tie_is_rank;
-  if (c.mode == RPP_COMBINED_NMS) {
+  const bool tpu = tpu_branch(c);
+  if (tpu) {   // _tpu_per_class_hard_nms (:288-379)
+    ps.consumer = RPP_CONSUME_PADDED;
+    ps.padded = 2;
+    ps.row0_mode = row0_mode;
+    ps.clip_before = 1;
+    ps.iou_threshold = c.iou_threshold;
+    ps.M_lim = M;
+  } else if (c.mode == RPP_COMBINED_NMS) {
     ps.consumer = RPP_CONSUME_HARD;
     ps.clip_before = 0;
     ps.iou_threshold = c.iou_threshold;
@@ -461,11 +492,23 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   // cross-class bound: the merge keeps only the M best of C * M_lim boxes, so a class rarely needs more than a few
   {
     const int m1 = std::min(ps.M_lim, (M + C - 1) / C + h->probe_extra);
-    ps.two_pass_m1 = (h->two_pass && C > 1 && 2 * m1 < ps.M_lim && (long)C * m1 <= 8192) ? m1 : 0;
+    ps.two_pass_m1 = (h->two_pass && C > 1 && 2 * m1 < ps.M_lim && (long)C * m1 <= 8192 && !tpu) ? m1 : 0;
   }
   int rc = run_problem_set(h, ar, ps, st, st2, ev);
   if (rc || ar.dry) return rc;
   if (ev) st = st2;
+  if (tpu) {
+    MergePaddedParams mq{};
+    mq.C = C; mq.M = M; mq.score_threshold = c.score_threshold;
+    mq.sel_key = ps.sel_key; mq.sel_box = ps.sel_box; mq.sel_cnt = ps.sel_cnt;
+    mq.pad_score = ps.pad_score; mq.pad_box = ps.pad_box;
+    mq.out_boxes = out.boxes; mq.out_scores = out.scores; mq.out_classes = (int*)out.classes;
+    mq.out_valid = out.valid;
+    merge_padded_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mq);
+    LAUNCHED();
+    stage_mark(h, 4, st);
+    return RPP_OK;
+  }
 
   MergeParams mp{};
   mp.C = C; mp.M = M; mp.combined = c.mode == RPP_COMBINED_NMS;
@@ -553,9 +596,16 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   ps.clip_before = 1;
   ps.iou_threshold = iou_thr;
   ps.soft_sigma_tf = sigma_tf;
+  const bool tpu = tpu_branch(c);
+  if (tpu) {   // _tpu_global_hard_nms (:381-432): the real IoU threshold, padded-NMS arithmetic
+    ps.consumer = RPP_CONSUME_PADDED;
+    ps.padded = 1;
+    ps.iou_threshold = c.iou_threshold;
+  }
   int rc = run_problem_set(h, ar, ps, st);
   if (rc || ar.dry) return rc;
   GlobalOutParams gp{};
+  gp.tpu = tpu ? 1 : 0;
   gp.M = M; gp.sel_key = ps.sel_key; gp.sel_box = ps.sel_box; gp.sel_cnt = ps.sel_cnt;
   gp.x = x; gp.is_logit = is_logit; gp.n = n; gp.C = C;
   gp.deltas = deltas; gp.anchors = h->d_anchors; gp.boxes = boxes; gp.dp = h->dp;
@@ -705,6 +755,12 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     return fail(RPP_EINVAL, "max_detections must be in 1..1024");
   if ((cfg->mode == RPP_GLOBAL_SOFT_NMS || cfg->mode == RPP_PER_CLASS_SOFT_NMS) && !(cfg->soft_nms_sigma == cfg->soft_nms_sigma))
     return fail(RPP_EINVAL, "soft_nms_sigma is required for the soft NMS modes");
+  if (cfg->tpu_semantics != 0 && cfg->tpu_semantics != 1) return fail(RPP_EINVAL, "tpu_semantics must be 0 or 1");
+  for (int i = 0; i < 6; ++i)
+    if (cfg->reserved[i] != 0) return fail(RPP_EINVAL, "rpp_config.reserved must be zero");
+  if (tpu_branch(*cfg) && !(cfg->iou_threshold > 0.0f))
+    return fail(RPP_EINVAL, "tpu_semantics needs iou_threshold > 0 (non_max_suppression_padded suppresses at "
+                            "iou >= threshold: a non-positive threshold suppresses everything)");
 
   int dev = 0, count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
@@ -797,6 +853,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_SOFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_PADDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(merge_padded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(emit_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -840,6 +898,7 @@ int rpp_anchor_boundaries(void* handle, long* h_out) {
 int rpp_classes_itemsize(void* handle) {
   Handle* h = (Handle*)handle;
   if (!h) return -1;
+  if (tpu_branch(h->cfg)) return 4;   // both TPU branches cast the classes to int32 (:375, :425-426)
   return (h->cfg.mode == RPP_GLOBAL_SOFT_NMS || h->cfg.mode == RPP_GLOBAL_HARD_NMS) ? 8 : 4;
 }
 int rpp_debug_force_exact_scan(void* handle, int on) {
@@ -893,6 +952,13 @@ size_t rpp_workspace_bytes(void* handle, int B, long n) {
   {
     Arena a{nullptr, 0, true};
     if (n <= 0 && detect_pipeline(h, a, nullptr, nullptr, B, none, nullptr) == RPP_OK) need = std::max(need, a.off);
+  }
+  if (n <= 0 && (double)h->N * h->cfg.num_classes < 2147483647.0) {   // rpp_efficient_nms
+    Arena a{nullptr, 0, true};
+    u64* keys = nullptr;
+    if (topk_keys(h, a, nullptr, 1, B, h->N * h->cfg.num_classes, 1,
+                  std::min<long>(RPP_EFFNMS_SELECTED, h->N * h->cfg.num_classes), &keys, nullptr) == RPP_OK)
+      need = std::max(need, a.off);
   }
   if (n > 0) {
     const bool per_class = is_per_class_mode(h->cfg.mode);
@@ -995,6 +1061,39 @@ int rpp_coco_format(void* handle, const float* d_boxes, const float* d_scores, c
   coco_format_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(cp);
   LAUNCHED();
   return RPP_OK;
+}
+
+int rpp_efficient_nms(void* handle, const float* d_raw_boxes, const float* d_class_logits, const float* d_anchor_boxes,
+                      int B, int* d_valid_detections, float* d_detection_boxes, float* d_detection_scores,
+                      int* d_detection_classes, void* ws, size_t ws_bytes, void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !d_raw_boxes || !d_class_logits || !d_valid_detections || !d_detection_boxes || !d_detection_scores ||
+      !d_detection_classes || B <= 0)
+    return fail(RPP_EINVAL, "bad argument");
+  const int C = h->cfg.num_classes, M = h->cfg.max_detections;
+  const long N = h->N;
+  if ((double)N * C >= 2147483647.0) return fail(RPP_EINVAL, "anchors x classes out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  return with_arena(ws, ws_bytes, [&](Arena& ar) {
+    const long k = std::min<long>(RPP_EFFNMS_SELECTED, N * C);
+    u64* keys = nullptr;
+    int rc = topk_keys(h, ar, d_class_logits, 1, B, N * C, 1, k, &keys, st);
+    if (rc || ar.dry) return rc;
+    EffNmsParams ep{};
+    ep.emit_key = keys; ep.k = k;
+    ep.deltas = (const float4*)d_raw_boxes;
+    ep.anchors = d_anchor_boxes ? (const float4*)d_anchor_boxes : h->d_anchors;
+    ep.N = N; ep.C = C;
+    ep.score_threshold = h->cfg.score_threshold; ep.iou_threshold = h->cfg.iou_threshold;
+    ep.M = M;
+    ep.out_valid = d_valid_detections; ep.out_boxes = (float4*)d_detection_boxes;
+    ep.out_scores = d_detection_scores; ep.out_classes = d_detection_classes;
+    effnms_kernel<<<B, RPP_NMS_NT, (size_t)M * 24, st>>>(ep);
+    LAUNCHED();
+    stage_mark(h, 4, st);
+    return (int)RPP_OK;
+  });
 }
 
 int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, const void* const* d_logits, int dtype,

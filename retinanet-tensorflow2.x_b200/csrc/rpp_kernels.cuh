@@ -742,6 +742,14 @@ struct ColProblemParams {
   // top-k emission (FilterTopKDetections): sorted keys of the k_lim best rows
   u64* emit_key;           // [P][k_lim]
   int* emit_done;          // [P] 1 = emit_sort_kernel already wrote this problem's keys
+  // tf.image.non_max_suppression_padded semantics (the TPU branches, postprocessing_ops.py:288-432; consumer
+  // RPP_CONSUME_PADDED): 1 = _tpu_global_hard_nms (score filter inside), 2 = _tpu_per_class_hard_nms (every row is
+  // a candidate; score_threshold / T_min of this struct are -inf and stop_score holds the config threshold)
+  int padded;
+  float stop_score;
+  int row0_mode;           // as MergeParams.row0_mode: which row is "index 0" of the class's NMS input
+  float* pad_score;        // [P] padded == 2: score of index 0 (what the padded selection slots gather, :332-335)
+  float4* pad_box;         // [P] its box (clipped)
 };
 
 struct NmsShared {
@@ -753,6 +761,7 @@ struct NmsShared {
   float4 corig[RPP_NMS_NT];  // boxes as emitted
   int nkept;
   int done;
+  int need_all;              // padded == 2: the class's padded slots can reach the output -> count past the threshold
   // followed in dynamic shared memory by: float4 kbox[M_lim] (kept, canonical), float karea[M_lim]
 };
 __device__ __forceinline__ float4* nms_kbox(NmsShared* sh) { return reinterpret_cast<float4*>(sh + 1); }
@@ -792,6 +801,24 @@ __device__ __forceinline__ bool iou_gt(float4 a, float area_a, float4 b, float a
   return iou > thr;
 }
 
+// _bbox_overlap of tf.image.non_max_suppression_padded (image_ops_impl.py): no canonicalisation,
+// inter / (area_a + area_b - inter + 1e-8) in fp32, and a box is suppressed when iou >= threshold.
+__device__ __forceinline__ bool iou_padded_ge(float4 a, float area_a, float4 b, float area_b, float thr) {
+  const float h0 = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.0f);
+  const float h1 = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.0f);
+  const float inter = __fmul_rn(h1, h0);
+  const float uni = __fadd_rn(__fsub_rn(__fadd_rn(area_a, area_b), inter), 1e-8f);
+  return __fdiv_rn(inter, uni) >= thr;
+}
+template <bool PADDED>
+__device__ __forceinline__ bool nms_suppresses(float4 a, float area_a, float4 b, float area_b, float thr) {
+  return PADDED ? iou_padded_ge(a, area_a, b, area_b, thr) : iou_gt(a, area_a, b, area_b, thr);
+}
+
+// PADDED = true: the greedy scan that non_max_suppression_padded's tiled fixed-point iteration computes — same
+// order (score desc, index asc), iou_padded_ge as the test, and a box whose coordinates are all <= 0 is never
+// selected (TF counts `any(box > 0)`; such a box has IoU 0 with everything, so it does not suppress either).
+template <bool PADDED>
 __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b, int c, size_t p, int m,
                                  long& consumed) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -809,6 +836,27 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
     cut = ok < m_eff;
     m_eff = ok;
   }
+  if (PADDED && P.padded == 2) {
+    if (consumed == 0 && P.row0_mode == 1) {
+      // the per-class top-k ran first: index 0 of this class's NMS input is the head of the sorted stream
+      if (tid == 0) {
+        const u64 k0 = sh->chunk[0];
+        float4 b0 = col_box(P, b, c, key_tie(k0));
+        if (P.clip_before) b0 = clip01(b0);
+        P.pad_score[p] = key_score(k0);
+        P.pad_box[p] = b0;
+        sh->need_all = key_score(k0) > P.stop_score;
+      }
+      __syncthreads();
+    }
+    if (!sh->need_all) {   // nothing at or below the score threshold can reach the output: stop there
+      int ok = 0;
+      for (int i0 = 0; i0 < m_eff; i0 += RPP_NMS_NT)
+        ok += __syncthreads_count(i0 + tid < m_eff && key_score(sh->chunk[i0 + tid]) > P.stop_score);
+      cut = cut || ok < m_eff;
+      m_eff = ok;
+    }
+  }
   for (int g0 = 0; g0 < m_eff; g0 += RPP_NMS_NT) {
     const int gcount = m_eff - g0 < RPP_NMS_NT ? m_eff - g0 : RPP_NMS_NT;
     bool alive = tid < gcount;
@@ -818,8 +866,14 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       float4 orig = col_box(P, b, c, key_tie(sh->chunk[g0 + tid]));
       if (P.clip_before) orig = clip01(orig);
       sh->corig[tid] = orig;
-      const float4 cb = canon_box(orig, area);
-      if (area > 0.0f) bx = cb; else area = 0.0f;
+      if (PADDED) {
+        bx = orig;
+        area = __fmul_rn(__fsub_rn(orig.z, orig.x), __fsub_rn(orig.w, orig.y));
+        alive = orig.x > 0.0f || orig.y > 0.0f || orig.z > 0.0f || orig.w > 0.0f;
+      } else {
+        const float4 cb = canon_box(orig, area);
+        if (area > 0.0f) bx = cb; else area = 0.0f;
+      }
       sh->cbox[tid] = bx;
       sh->carea[tid] = area;
     }
@@ -834,7 +888,7 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       for (int j = 0; j < tcount - 1; ++j) {
         const float4 ob = sh->cbox[tbase + j];
         const float oa = sh->carea[tbase + j];
-        if (j < lane && lane < tcount && iou_gt(bx, area, ob, oa, thr)) row |= 1u << j;
+        if (j < lane && lane < tcount && nms_suppresses<PADDED>(bx, area, ob, oa, thr)) row |= 1u << j;
       }
     }
     int tested = 0;
@@ -843,7 +897,7 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       const int nk = sh->nkept;
       if (alive && warp >= tile) {
         for (int k = tested; k < nk; ++k)
-          if (iou_gt(bx, area, kbox[k], karea[k], thr)) { alive = false; break; }
+          if (nms_suppresses<PADDED>(bx, area, kbox[k], karea[k], thr)) { alive = false; break; }
       }
       tested = nk;
       if (warp == tile) {
@@ -1099,6 +1153,7 @@ __device__ void emit_consume(const ColProblemParams& P, NmsShared* sh, size_t p,
 #define RPP_CONSUME_HARD 0
 #define RPP_CONSUME_SOFT 1
 #define RPP_CONSUME_EMIT 2
+#define RPP_CONSUME_PADDED 3   // hard NMS with tf.image.non_max_suppression_padded semantics (TPU branches)
 
 template <int MODE>
 __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParams P) {
@@ -1116,13 +1171,27 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   if (tid == 0) {
     sh->nkept = 0;
     sh->done = 0;
+    sh->need_all = 0;
     if (MODE == RPP_CONSUME_SOFT) ss->rcount = 0;
+    if (MODE == RPP_CONSUME_PADDED && P.padded == 2) {
+      float s0 = -INFINITY;
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (P.row0_mode == 0) {   // index 0 of the NMS input = row 0 of the source
+        s0 = col_score(P, lv_val(P.lv, b, 0, P.C, c));
+        b0 = col_box(P, b, c, 0u);
+        if (P.clip_before) b0 = clip01(b0);
+        sh->need_all = s0 > P.stop_score;
+      }
+      P.pad_score[p] = s0;
+      P.pad_box[p] = b0;
+    }
   }
   __syncthreads();
 
   long consumed = 0;
   auto consume = [&](int m) {
-    if (MODE == RPP_CONSUME_HARD) hard_nms_consume(P, sh, b, c, p, m, consumed);
+    if (MODE == RPP_CONSUME_HARD) hard_nms_consume<false>(P, sh, b, c, p, m, consumed);
+    else if (MODE == RPP_CONSUME_PADDED) hard_nms_consume<true>(P, sh, b, c, p, m, consumed);
     else if (MODE == RPP_CONSUME_SOFT) soft_nms_consume(P, sh, ss, b, c, p, m, consumed, false);
     else emit_consume(P, sh, p, m, consumed);
   };
@@ -1703,6 +1772,60 @@ __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
   }
 }
 
+// Per-image merge of _tpu_per_class_hard_nms (postprocessing_ops.py:337-379): the C*M per-class slots — the kept
+// boxes, then for a class that kept fewer than M the padded slots, which gather that class's index 0 (box AND
+// score, :332-335) — go through tf.nn.top_k(M) (score desc, flat index asc) and every position whose score is not
+// above the score threshold becomes -1 in all fields.  Only slots scoring above the threshold can surface, so the
+// keys of the others are left out.
+struct MergePaddedParams {
+  int C, M;
+  float score_threshold;
+  const u64* sel_key; const float4* sel_box; const int* sel_cnt;
+  const float* pad_score; const float4* pad_box;
+  float4* out_boxes; float* out_scores; int* out_classes; int* out_valid;
+};
+
+__global__ void __launch_bounds__(RPP_MERGE_NT) merge_padded_kernel(MergePaddedParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MergeShared* sh = reinterpret_cast<MergeShared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  const int C = P.C, M = P.M;
+  const u64* sk = P.sel_key + (size_t)b * C * M;
+  const int* scnt = P.sel_cnt + (size_t)b * C;
+  const float* ps = P.pad_score + (size_t)b * C;
+  auto keyfn = [&](int i) -> u64 {
+    const int c = i / M, slot = i - c * M;
+    const float s = slot < scnt[c] ? key_score(sk[i]) : ps[c];
+    return s > P.score_threshold ? make_key(s, (u32)i) : 0ull;
+  };
+  int got = 0;
+  u64 KB = ~0ull;
+  while (got < M) {
+    const int m = select_chunk<RPP_MERGE_NT>(keyfn, C * M, KB, M - got, sh->chunk, RPP_CHUNK_CAP, &sh->sel);
+    if (m == 0) break;
+    const int take = m < M - got ? m : M - got;
+    for (int i = tid; i < take; i += RPP_MERGE_NT) sh->top[got + i] = sh->chunk[i];
+    got += take;
+    __syncthreads();
+  }
+  if (tid == 0) P.out_valid[b] = got;   // :361-363: count of positions above the threshold
+  for (int i = tid; i < M; i += RPP_MERGE_NT) {
+    const size_t o = (size_t)b * M + i;
+    if (i < got) {
+      const u32 flat = key_tie(sh->top[i]);
+      const int c = flat / M, slot = flat - c * M;
+      P.out_boxes[o] = slot < scnt[c] ? P.sel_box[(size_t)b * C * M + flat] : P.pad_box[(size_t)b * C + c];
+      P.out_scores[o] = key_score(sh->top[i]);
+      P.out_classes[o] = c;
+    } else {
+      P.out_boxes[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
+      P.out_scores[o] = -1.0f;
+      P.out_classes[o] = -1;
+    }
+  }
+}
+
 // ===============================================================================================================
 // K5  Global* modes (GenerateDetections._global_nms, postprocessing_ops.py:244-286): NonMaxSuppressionV5 runs on
 // the per-row maximum over classes.  rowmax_kernel reduces [B,n,C] -> [B,n] (max raw value per row; the score is
@@ -1748,6 +1871,7 @@ struct GlobalOutParams {
   int is_logit; long n; int C;
   const float4* deltas; const float4* anchors; const float4* boxes; DecodeParams dp;
   float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
+  int tpu;                // _tpu_global_hard_nms (:402-431): int32 classes, -1 in every field beyond valid
 };
 
 __global__ void global_out_kernel(GlobalOutParams P) {
@@ -1771,7 +1895,11 @@ __global__ void global_out_kernel(GlobalOutParams P) {
       }
       P.out_boxes[o] = P.sel_box[o];
       P.out_scores[o] = key_score(k);
-      P.out_classes[o] = cls;
+      if (P.tpu) reinterpret_cast<int*>(P.out_classes)[o] = cls; else P.out_classes[o] = cls;
+    } else if (P.tpu) {
+      P.out_boxes[o] = make_float4(-1.f, -1.f, -1.f, -1.f);
+      P.out_scores[o] = -1.0f;
+      reinterpret_cast<int*>(P.out_classes)[o] = -1;
     } else {
       // padded selected index 0 -> boxes[0] (clipped), score -1, class -1 (:258-268)
       float4 bx = P.boxes ? P.boxes[(size_t)b * P.n] : decode_box(P.deltas[(size_t)b * P.n], P.anchors[0], P.dp);
@@ -1780,6 +1908,129 @@ __global__ void global_out_kernel(GlobalOutParams P) {
       P.out_classes[o] = -1;
     }
   }
+}
+
+// ===============================================================================================================
+// K7  EfficientNMS_TRT-compatible entry (the node the reference appends for export mode onnx_tensorrt,
+// onnx_utils.py:13-85, with the attributes it sets: score_activation = sigmoid, box_coding = 1 (centre-size, decoded
+// against the anchor input), background_class = -1, class-aware suppression).  The emission kernels deliver, per
+// image, the RPP_EFFNMS_SELECTED best (anchor, class) pairs sorted by (score desc, flat index asc); this kernel walks
+// them greedily — a candidate is dropped when a kept box of the SAME class overlaps it by more than iou_threshold —
+// until max_output_boxes are kept, and writes the plugin's four outputs (zero-filled beyond the count).
+// Same tile bit-mask / bit-chain structure as hard_nms_consume.
+// ===============================================================================================================
+#define RPP_EFFNMS_SELECTED 4096
+
+struct EffNmsParams {
+  const u64* emit_key; long k;        // [B][k] sorted keys (score bits | ~flat index), flat = anchor * C + class
+  const float4* deltas;               // [B][N] raw boxes (dx, dy, dw, dh)
+  const float4* anchors;              // [N] (cx, cy, w, h)
+  long N; int C;
+  float score_threshold, iou_threshold;
+  int M;
+  int* out_valid; float4* out_boxes; float* out_scores; int* out_classes;
+};
+
+__global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* kbox = reinterpret_cast<float4*>(smem_raw);              // [M] kept boxes (corner coding)
+  float* karea = reinterpret_cast<float*>(kbox + P.M);             // [M]
+  int* kcls = reinterpret_cast<int*>(karea + P.M);                 // [M]
+  __shared__ float4 cbox[RPP_NMS_NT];
+  __shared__ float carea[RPP_NMS_NT];
+  __shared__ int ccls[RPP_NMS_NT];
+  __shared__ int s_nkept, s_done;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const float thr = P.iou_threshold;
+  for (int i = tid; i < P.M; i += RPP_NMS_NT) {   // the plugin clears its outputs first
+    const size_t o = (size_t)b * P.M + i;
+    P.out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    P.out_scores[o] = 0.0f;
+    P.out_classes[o] = 0;
+  }
+  if (tid == 0) { s_nkept = 0; s_done = 0; }
+  __syncthreads();
+  for (long g0 = 0; g0 < P.k; g0 += RPP_NMS_NT) {
+    const u64 key = g0 + tid < P.k ? P.emit_key[(size_t)b * P.k + g0 + tid] : 0ull;
+    const float score = key_score(key);
+    bool alive = key != 0ull && score >= P.score_threshold;        // sorted: the candidates are a prefix
+    const int gcount = __syncthreads_count(alive);
+    if (gcount == 0) break;
+    float4 bx = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY), corner = bx;
+    float area = 0.0f;
+    int cls = -1;
+    if (alive) {
+      const u32 flat = key_tie(key);
+      const u32 row = flat / (u32)P.C;
+      cls = (int)(flat - row * (u32)P.C);
+      // centre-size decode against the anchor, no variance scaling, no normalisation
+      const float4 d = P.deltas[(size_t)b * P.N + row];
+      const float4 a = P.anchors[row];
+      const float cx = __fadd_rn(__fmul_rn(d.x, a.z), a.x);
+      const float cy = __fadd_rn(__fmul_rn(d.y, a.w), a.y);
+      const float hw = __fmul_rn(__fmul_rn(a.z, exp_f32(d.z)), 0.5f);
+      const float hh = __fmul_rn(__fmul_rn(a.w, exp_f32(d.w)), 0.5f);
+      corner = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+      const float w = __fsub_rn(corner.z, corner.x), hgt = __fsub_rn(corner.w, corner.y);
+      if (w > 0.0f && hgt > 0.0f) { area = __fmul_rn(w, hgt); bx = corner; }
+    }
+    cbox[tid] = bx; carea[tid] = area; ccls[tid] = cls;
+    __syncthreads();
+    u32 rowm = 0u;
+    {
+      const int tbase = warp * 32;
+      const int tcount = gcount - tbase < 32 ? gcount - tbase : 32;
+      for (int j = 0; j < tcount - 1; ++j)
+        if (j < lane && lane < tcount && ccls[tbase + j] == cls && iou_gt(bx, area, cbox[tbase + j], carea[tbase + j], thr))
+          rowm |= 1u << j;
+    }
+    int tested = 0;
+    const int ntiles = (gcount + 31) >> 5;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int nk = s_nkept;
+      if (alive && warp >= tile) {
+        for (int q = tested; q < nk; ++q)
+          if (kcls[q] == cls && iou_gt(bx, area, kbox[q], karea[q], thr)) { alive = false; break; }
+      }
+      tested = nk;
+      if (warp == tile) {
+        const u32 cand_bits = __ballot_sync(RPP_FULL_MASK, alive);
+        u32 kept_bits = 0u;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) {
+          const u32 r = __shfl_sync(RPP_FULL_MASK, rowm, l);
+          if (((cand_bits >> l) & 1u) && (r & kept_bits) == 0u) kept_bits |= 1u << l;
+        }
+        int nnew = __popc(kept_bits);
+        const int room = P.M - nk;
+        while (nnew > room) {
+          kept_bits &= ~(1u << (31 - __clz(kept_bits)));
+          --nnew;
+        }
+        if ((kept_bits >> lane) & 1u) {
+          const int pos = nk + __popc(kept_bits & ((1u << lane) - 1u));
+          kbox[pos] = bx; karea[pos] = area; kcls[pos] = cls;
+          const size_t o = (size_t)b * P.M + pos;
+          // outputs use the input's box coding (centre-size), rebuilt from the corner box
+          const float w = __fsub_rn(corner.z, corner.x), hgt = __fsub_rn(corner.w, corner.y);
+          P.out_boxes[o] = make_float4(__fadd_rn(corner.x, __fmul_rn(0.5f, w)), __fadd_rn(corner.y, __fmul_rn(0.5f, hgt)),
+                                       w, hgt);
+          P.out_scores[o] = score;
+          P.out_classes[o] = cls;
+        }
+        if (lane == 0) {
+          s_nkept = nk + nnew;
+          if (nk + nnew >= P.M) s_done = 1;
+        }
+      }
+      __syncthreads();
+      if (s_done) break;
+    }
+    if (s_done || gcount < RPP_NMS_NT) break;
+  }
+  __syncthreads();
+  if (tid == 0) P.out_valid[b] = s_nkept;
 }
 
 // ===============================================================================================================

@@ -16,7 +16,7 @@ RPP_OK, RPP_EINVAL, RPP_EMODE, RPP_ECOMBO, RPP_EWORKSPACE, RPP_ECUDA = 0, -1, -2
 EXPORTS = [
     'rpp_create', 'rpp_destroy', 'rpp_last_error', 'rpp_num_anchors', 'rpp_num_levels', 'rpp_anchor_boundaries',
     'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_nms', 'rpp_detect', 'rpp_detect_levels', 'rpp_detect_typed',
-    'rpp_detect_host', 'rpp_detect_host_typed', 'rpp_coco_format',
+    'rpp_detect_host', 'rpp_detect_host_typed', 'rpp_coco_format', 'rpp_efficient_nms',
     'rpp_last_launch_count', 'rpp_classes_itemsize', 'rpp_debug_force_exact_scan', 'rpp_debug_stage_timing',
     'rpp_debug_stage_ms',
 ]
@@ -40,7 +40,8 @@ class RppConfig(ctypes.Structure):
         ('filter_per_class', ctypes.c_int),
         ('max_detections', ctypes.c_int),
         ('soft_ignores_iou_threshold', ctypes.c_int),
-        ('reserved', ctypes.c_int * 7),
+        ('tpu_semantics', ctypes.c_int),
+        ('reserved', ctypes.c_int * 6),
     ]
 
 
@@ -80,6 +81,7 @@ def lib():
         if hasattr(L, 'rpp_detect_host_typed'):
             L.rpp_detect_host_typed.argtypes = [vp, ci, vp, vp, ci, ci, vp, vp, vp, vp]
         L.rpp_coco_format.argtypes = [vp] * 5 + [ci] + [vp] * 8
+        L.rpp_efficient_nms.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.rpp_classes_itemsize.argtypes = [vp]
         L.rpp_debug_force_exact_scan.argtypes = [vp, ci]
         L.rpp_debug_stage_timing.argtypes = [vp, ci]

@@ -90,7 +90,10 @@ class ModelBuilder:
                                              max_detections=params.inference.max_detections,
                                              soft_nms_sigma=params.inference.soft_nms_sigma,
                                              num_classes=params.architecture.head.num_classes,
-                                             mode=params.inference.mode))
+                                             mode=params.inference.mode,
+                                             # optional key, absent from the reference's JSONs (the reference detects
+                                             # a TPUStrategy instead, postprocessing_ops.py:199-208)
+                                             tpu_semantics=bool(params.inference.get('tpu_semantics', False))))
         else:
             logging.warning('Skipping NMS filtering !!!')
 

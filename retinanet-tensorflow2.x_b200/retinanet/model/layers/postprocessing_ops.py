@@ -4,7 +4,8 @@ constructor signatures, dict keys, output dtypes and padding, running on hand-wr
     FuseDetections           postprocessing_ops.py:7-56
     TransformBoxesAndScores  postprocessing_ops.py:59-117
     FilterTopKDetections     postprocessing_ops.py:120-173
-    GenerateDetections       postprocessing_ops.py:176-561   (non-TPU branches)
+    GenerateDetections       postprocessing_ops.py:176-561   (non-TPU branches; the TPU branches :288-432 are the
+                                                             opt-in `tpu_semantics=True`)
 
 Tensors are torch CUDA tensors.  Each layer alone calls its stage entry point of libretinapost.so (rpp_decode,
 rpp_topk, rpp_nms); `FusedPostProcessing` — what ModelBuilder.add_post_processing_stage builds when the whole chain
@@ -50,7 +51,7 @@ class _Handle:
     def __init__(self, H=8, W=8, min_level=3, max_level=3, num_classes=1, anchor_params=None,
                  box_variance=(0.1, 0.1, 0.2, 0.2), scale_box_targets=False, mode='CombinedNMS',
                  iou_threshold=0.5, score_threshold=0.05, soft_nms_sigma=0.0, pre_nms_top_k=-1,
-                 filter_per_class=True, max_detections=100, soft_ignores_iou_threshold=True):
+                 filter_per_class=True, max_detections=100, soft_ignores_iou_threshold=True, tpu_semantics=False):
         if not torch.cuda.is_available():
             raise RuntimeError('retinapost needs a CUDA device: there is no CPU fallback')
         ap = anchor_params or self._DUMMY_ANCHORS
@@ -79,6 +80,10 @@ class _Handle:
         cfg.filter_per_class = int(bool(filter_per_class))
         cfg.max_detections = int(max_detections)
         cfg.soft_ignores_iou_threshold = int(bool(soft_ignores_iou_threshold))
+        cfg.tpu_semantics = int(bool(tpu_semantics))
+        # both TPU branches cast the classes to int32 (:375, :425-426)
+        self.class_dtype = (torch.int32 if tpu_semantics and mode in ('GlobalHardNMS', 'PerClassHardNMS')
+                            else _CLASS_DTYPES.get(mode, torch.float32))
         self.mode = mode
         self.num_classes = int(num_classes)
         self.max_detections = int(max_detections)
@@ -101,7 +106,7 @@ class _Handle:
         return {
             'boxes': torch.empty((B, M, 4), dtype=torch.float32, device=device),
             'scores': torch.empty((B, M), dtype=torch.float32, device=device),
-            'classes': torch.empty((B, M), dtype=_CLASS_DTYPES[self.mode], device=device),
+            'classes': torch.empty((B, M), dtype=self.class_dtype, device=device),
             'valid_detections': torch.empty((B,), dtype=torch.int32, device=device),
         }
 
@@ -283,16 +288,20 @@ class GenerateDetections(Layer):
                  num_classes=None,
                  mode='CombinedNMS',
                  soft_ignores_iou_threshold=True,
+                 tpu_semantics=False,
                  **kwargs):
         # soft_ignores_iou_threshold (not in the reference): True = NonMaxSuppressionV5 of TF >= 2.3, where the IoU
         # threshold is ignored when soft_nms_sigma > 0; False = the older kernel form.
+        # tpu_semantics (not in the reference, which detects a TPUStrategy instead, :199-208): True = GlobalHardNMS /
+        # PerClassHardNMS run _tpu_global_hard_nms (:381-432) / _tpu_per_class_hard_nms (:288-379): a real global hard
+        # NMS, tf.image.non_max_suppression_padded arithmetic, int32 classes, -1 in every padded field.
 
         if mode not in GenerateDetections._SUPPORTED_NMS_MODES:
             raise AssertionError(
                 'Requested unsupported mode: {}, available modes are: {}'
                 .format(mode, GenerateDetections._SUPPORTED_NMS_MODES))
 
-        self._running_on_tpu = False
+        self._running_on_tpu = bool(tpu_semantics)
 
         super(GenerateDetections, self).__init__(**kwargs)
 
@@ -315,7 +324,8 @@ class GenerateDetections(Layer):
             h = _Handle(num_classes=num_classes, mode=self.mode, iou_threshold=self.iou_threshold,
                         score_threshold=self.score_threshold, soft_nms_sigma=self.soft_nms_sigma or 0.0,
                         max_detections=self.max_detections,
-                        soft_ignores_iou_threshold=self.soft_ignores_iou_threshold)
+                        soft_ignores_iou_threshold=self.soft_ignores_iou_threshold,
+                        tpu_semantics=self._running_on_tpu)
             self._handles[num_classes] = h
         return h
 
@@ -355,6 +365,8 @@ class FusedPostProcessing(Layer):
                 .format(inf.mode, GenerateDetections._SUPPORTED_NMS_MODES))
         self._params = params
         self.mode = inf.mode
+        # optional key `inference.tpu_semantics` (absent from the reference's JSONs -> False)
+        self.tpu_semantics = bool(inf.get('tpu_semantics', False)) if hasattr(inf, 'get') else False
         self._handles = {}
 
     def handle(self, num_classes):
@@ -373,7 +385,8 @@ class FusedPostProcessing(Layer):
                         scale_box_targets=p.encoder_params.scale_box_targets,
                         mode=inf.mode, iou_threshold=inf.iou_threshold, score_threshold=inf.score_threshold,
                         soft_nms_sigma=inf.soft_nms_sigma or 0.0, pre_nms_top_k=inf.pre_nms_top_k,
-                        filter_per_class=inf.filter_per_class, max_detections=inf.max_detections)
+                        filter_per_class=inf.filter_per_class, max_detections=inf.max_detections,
+                        tpu_semantics=self.tpu_semantics)
             self._handles[num_classes] = h
         return h
 

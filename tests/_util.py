@@ -36,6 +36,12 @@ def oracle_detect(ref, params, logits, deltas, threads=8, **kw):
     ff = params.architecture.feature_fusion
     ap = params.anchor_params
     anchors, _ = ref.anchors(H, W, ff.min_level, ff.max_level, ap.areas, ap.aspect_ratios, ap.scales)
+    if inf.get('tpu_semantics', False) and inf.mode in ('GlobalHardNMS', 'PerClassHardNMS'):
+        return ref.detect_tpu(logits, deltas, anchors, H, W, inf.mode, iou_threshold=inf.iou_threshold,
+                              score_threshold=inf.score_threshold, pre_nms_top_k=inf.pre_nms_top_k,
+                              filter_per_class=inf.filter_per_class, max_detections=inf.max_detections,
+                              box_variance=params.encoder_params.box_variance,
+                              scale_box_targets=params.encoder_params.scale_box_targets, threads=threads)
     return ref.detect(logits, deltas, anchors, H, W, inf.mode, iou_threshold=inf.iou_threshold,
                       score_threshold=inf.score_threshold, soft_nms_sigma=inf.soft_nms_sigma,
                       pre_nms_top_k=inf.pre_nms_top_k, filter_per_class=inf.filter_per_class,

@@ -2,7 +2,8 @@
  * Build:  gcc tests/abi_smoke.c -Iinclude -I/usr/local/cuda/include -L<dir of libretinapost.so> -lretinapost \
  *             -L/usr/local/cuda/lib64 -lcudart -lm -o abi_smoke
  * Checks: create/anchors/workspace/detect on device buffers, rpp_detect_host on host buffers gives the same
- * detections, error codes for a bad mode and for a Global* mode with the per-class filter. */
+ * detections, the TPU-branch flag and the EfficientNMS entry run, error codes for a bad mode, a small workspace and
+ * a Global* mode with the per-class filter. */
 #include <cuda_runtime_api.h>
 #include <math.h>
 #include <stdio.h>
@@ -67,6 +68,36 @@ int main(void) {
     if (va[b] != 100) { fprintf(stderr, "image %d: %d detections\n", b, va[b]); return 1; }
     for (int i = 1; i < M; ++i) if (sc[b * M + i] > sc[b * M + i - 1]) { fprintf(stderr, "scores not sorted\n"); return 1; }
     for (int i = 0; i < M; ++i) if (cl[b * M + i] < 0 || cl[b * M + i] >= C) { fprintf(stderr, "bad class\n"); return 1; }
+  }
+  /* EfficientNMS_TRT-shaped entry (anchors = the handle's table): counts in range, scores sorted, classes valid */
+  {
+    int *dn; int nv[3];
+    CU(cudaMalloc((void**)&dn, (size_t)B * 4));
+    CHECK(rpp_efficient_nms(h, dd, dl, NULL, B, dn, db, ds, dc, ws, wsb, NULL));
+    CU(cudaMemcpy(nv, dn, sizeof(nv), cudaMemcpyDeviceToHost)); CU(cudaMemcpy(sc2, ds, sizeof(sc2), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cl2, dc, sizeof(cl2), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) {
+      if (nv[b] != 100) { fprintf(stderr, "efficient_nms image %d: %d detections\n", b, nv[b]); return 1; }
+      for (int i = 1; i < M; ++i) if (sc2[b * M + i] > sc2[b * M + i - 1]) { fprintf(stderr, "efficient_nms scores not sorted\n"); return 1; }
+      for (int i = 0; i < M; ++i) if (cl2[b * M + i] < 0 || cl2[b * M + i] >= C) { fprintf(stderr, "efficient_nms bad class\n"); return 1; }
+    }
+    cudaFree(dn);
+  }
+  /* tpu_semantics: the TPUStrategy branch of PerClassHardNMS; a non-positive IoU threshold is rejected with it */
+  {
+    void* ht = NULL;
+    rpp_config tc = cfg;
+    tc.tpu_semantics = 1;
+    CHECK(rpp_create(&tc, &ht));
+    const size_t wt = rpp_workspace_bytes(ht, B, 0);
+    void* wst; CU(cudaMalloc(&wst, wt));
+    CHECK(rpp_detect(ht, dd, dl, B, db, ds, dc, dv, wst, wt, NULL));
+    CU(cudaMemcpy(va2, dv, sizeof(va2), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; ++b) if (va2[b] != 100) { fprintf(stderr, "tpu branch image %d: %d detections\n", b, va2[b]); return 1; }
+    cudaFree(wst);
+    CHECK(rpp_destroy(ht));
+    tc.iou_threshold = 0.0f;
+    if (rpp_create(&tc, &ht) != RPP_EINVAL) { fprintf(stderr, "tpu_semantics with iou_threshold 0 accepted\n"); return 1; }
   }
   /* workspace too small -> RPP_EWORKSPACE; Global* + per-class filter -> RPP_ECOMBO */
   if (rpp_detect(h, dd, dl, B, db, ds, dc, dv, ws, 1024, NULL) != RPP_EWORKSPACE) { fprintf(stderr, "small workspace accepted\n"); return 1; }

@@ -9,6 +9,7 @@ Each fixture holds seeded inputs and the reference layers' outputs:
   anchors_*.npz      AnchorBoxGenerator(...).boxes / anchor_boundaries
   stage_*.npz        TransformBoxesAndScores / FilterTopKDetections outputs
   detect_*.npz       the full chain FuseDetections-less: Transform -> [Filter] -> GenerateDetections, every mode
+  tpu_*.npz          the same chain with GenerateDetections constructed under a TPUStrategy (the _tpu_* branches)
 """
 import hashlib
 import os
@@ -58,6 +59,8 @@ def synth(B, N, C, seed, dist):
         logits = (logits * 1.5 - 4.595).astype(np.float32)
     if dist == 'quantized':
         logits = (np.round(logits * 4) / 4).astype(np.float32)
+    if dist == 'clustered':   # boxes stay close to their anchors: heavy suppression, classes run out of boxes
+        deltas = (deltas * 0.1).astype(np.float32)
     return logits, deltas
 
 
@@ -103,6 +106,37 @@ def main():
                             out_boxes=np.asarray(det['boxes']), out_scores=np.asarray(det['scores']),
                             out_classes=np.asarray(det['classes']),
                             out_valid=np.asarray(det['valid_detections']), **stage)
+    # ---- the TPUStrategy branches (_tpu_global_hard_nms / _tpu_per_class_hard_nms, :288-432) -------------------------
+    import tf_shim
+    tpu_cases = []
+    for mode in ['GlobalHardNMS', 'PerClassHardNMS']:
+        for (k, fpc) in [(60, True), (25, True), (90, False), (-1, True)]:
+            if mode.startswith('Global') and k > 0 and fpc:
+                continue
+            for dist in ['dense', 'sparse', 'quantized', 'clustered']:
+                tpu_cases.append((mode, k, fpc, dist))
+    for ci, (mode, k, fpc, dist) in enumerate(tpu_cases):
+        p = params_for(H, W, C)
+        N = ag.AnchorBoxGenerator(H, W, 3, 7, p.anchor_params).boxes.shape[0]
+        logits, deltas = synth(B, N, C, 2000 + ci, dist)
+        x = po.TransformBoxesAndScores(p)({'class_logits': logits, 'encoded_boxes': deltas})
+        if k > 0:
+            x = po.FilterTopKDetections(top_k=k, filter_per_class=fpc)(x)
+        tf_shim.set_tpu_strategy(True)
+        try:
+            layer = po.GenerateDetections(iou_threshold=0.5, score_threshold=0.05, max_detections=M,
+                                          soft_nms_sigma=0.5, num_classes=C, mode=mode)
+        finally:
+            tf_shim.set_tpu_strategy(False)
+        assert layer._running_on_tpu
+        det = layer(x)
+        name = 'tpu_{}_k{}_{}_{}.npz'.format(mode, k, 'pc' if fpc else 'gl', dist)
+        np.savez_compressed(os.path.join(out_dir, name), H=H, W=W, C=C, M=M, mode=mode, k=k, filter_per_class=fpc,
+                            scale_box_targets=False, logits=logits, deltas=deltas,
+                            out_boxes=np.asarray(det['boxes']), out_scores=np.asarray(det['scores']),
+                            out_classes=np.asarray(det['classes']),
+                            out_valid=np.asarray(det['valid_detections']))
+    print('wrote {} tpu fixtures'.format(len(tpu_cases)))
     # ---- the rank error of Global* modes on per-class filtered boxes ------------------------------------
     p = params_for(H, W, C)
     N = ag.AnchorBoxGenerator(H, W, 3, 7, p.anchor_params).boxes.shape[0]

@@ -293,6 +293,58 @@ def _combined_nms(boxes, scores, max_output_size_per_class, max_total_size, iou_
     return _Combined((T(ob), T(os_), T(oc), T(ov)))
 
 
+def ones_like(x):
+    return T(np.ones_like(np.asarray(x)))
+
+
+def _bbox_overlap(a, b):
+    """image_ops_impl._bbox_overlap for one pair, fp32 step by step."""
+    f = np.float32
+    i_xmin, i_xmax = max(a[1], b[1]), min(a[3], b[3])
+    i_ymin, i_ymax = max(a[0], b[0]), min(a[2], b[2])
+    i_area = f(max(f(i_xmax - i_xmin), f(0))) * f(max(f(i_ymax - i_ymin), f(0)))
+    a_area = f(f(a[2] - a[0]) * f(a[3] - a[1]))
+    b_area = f(f(b[2] - b[0]) * f(b[3] - b[1]))
+    u_area = f(f(f(a_area + b_area) - i_area) + f(1e-8))
+    return f(i_area / u_area)
+
+
+def _nms_padded(boxes, scores, max_output_size, iou_threshold=0.5, score_threshold=float('-inf'),
+                pad_to_max_output_size=False, name=None, sorted_input=False, canonicalized_coordinates=False,
+                tile_size=512):
+    """tf.image.non_max_suppression_padded (-> non_max_suppression_padded_v2) for batched [B,n,4] / [B,n] inputs, as
+    the reference's TPU branches call it.  Stated as the greedy scan that the op's tiled fixed-point iteration
+    converges to: (score desc, index asc) order, a box is dropped when its _bbox_overlap with an earlier kept box is
+    >= iou_threshold, boxes at or below score_threshold are zeroed first, only boxes with a coordinate > 0 count as
+    selected, indices beyond num_valid are 0.  (The C++ oracle restates the tile iteration itself; the two are
+    compared in tests/test_oracle_tpu.py.)"""
+    assert pad_to_max_output_size and canonicalized_coordinates and not sorted_input
+    boxes = np.asarray(boxes, np.float32)
+    scores = np.asarray(scores, np.float32)
+    B, n = scores.shape
+    M = int(max_output_size)
+    idx = np.zeros((B, M), np.int32)
+    valid = np.zeros((B,), np.int32)
+    for b in builtins_range(B):
+        sc, bx = scores[b].copy(), boxes[b].copy()
+        if score_threshold != float('-inf'):
+            mask = (sc > np.float32(score_threshold)).astype(np.float32)
+            sc = sc * mask
+            bx = bx * mask[:, None]
+        order = np.argsort(-sc, kind='stable')
+        kept = []
+        for i in order:
+            if len(kept) >= M:
+                break
+            if not (bx[i] > 0).any():
+                continue
+            if all(_bbox_overlap(bx[j], bx[i]) < np.float32(iou_threshold) for j in kept):
+                kept.append(i)
+        valid[b] = len(kept)
+        idx[b, :len(kept)] = kept
+    return T(idx), T(valid)
+
+
 class _Layer:
     def __init__(self, **kwargs):
         pass
@@ -305,19 +357,29 @@ class _TPUStrategy:
     pass
 
 
+_strategy = [object()]
+
+
+def set_tpu_strategy(on):
+    """Makes tf.distribute.get_strategy() return a TPUStrategy (the reference's TPU detection, :199-208)."""
+    _strategy[0] = _TPUStrategy() if on else object()
+
+
 def install():
     """Registers this module tree as `tensorflow` and returns it."""
     tf = types.ModuleType('tensorflow')
     for name in ['float32', 'int32', 'int64', 'constant', 'convert_to_tensor', 'cast', 'range', 'meshgrid', 'stack',
                  'concat', 'expand_dims', 'tile', 'reshape', 'transpose', 'fill', 'where', 'less', 'greater',
-                 'reduce_max', 'reduce_sum', 'argmax', 'clip_by_value', 'gather', 'gather_nd', 'vectorized_map']:
+                 'reduce_max', 'reduce_sum', 'argmax', 'clip_by_value', 'gather', 'gather_nd', 'vectorized_map',
+                 'ones_like']:
         setattr(tf, name, globals()[name])
     tf.math = types.SimpleNamespace(sqrt=_sqrt, ceil=_ceil, exp=_exp, top_k=top_k)
     tf.nn = types.SimpleNamespace(sigmoid=_sigmoid, top_k=top_k)
-    tf.image = types.SimpleNamespace(combined_non_max_suppression=_combined_nms)
+    tf.image = types.SimpleNamespace(combined_non_max_suppression=_combined_nms,
+                                     non_max_suppression_padded=_nms_padded)
     tf.raw_ops = _RawOps
     tf.keras = types.SimpleNamespace(layers=types.SimpleNamespace(Layer=_Layer))
     tf.nest = types.SimpleNamespace(map_structure=lambda fn, d: {k: fn(v) for k, v in d.items()})
-    tf.distribute = types.SimpleNamespace(get_strategy=lambda: object(), TPUStrategy=_TPUStrategy)
+    tf.distribute = types.SimpleNamespace(get_strategy=lambda: _strategy[0], TPUStrategy=_TPUStrategy)
     sys.modules['tensorflow'] = tf
     return tf
