@@ -104,13 +104,13 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Pre-threshold plan for columns of n rows and C classes: aim at ~`target` candidates per problem with list
 // capacity 4096; small columns are collected whole (no sampling).
-SamplePlan make_plan(long n, int C, int target) {
+SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
   SamplePlan s{};
   s.on = false;
   s.CAP = (int)n;
   if (n < 16384 || n <= 8L * target || C > 1024) return s;
   int lanes = 1024 / C;
-  if (lanes > 12) lanes = 12;
+  if (lanes > lane_cap) lanes = lane_cap;
   const int G = lanes * RPP_GPT;
   // group size chosen so that the wanted logit sits near the 70th percentile of the group maxima:
   // rows per group g = -ln(0.7) * n / target, i.e. one sampled row every S = target / (0.357 * G) rows (~3 %)
@@ -186,11 +186,16 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   const long n = ps.n;
   const size_t P = (size_t)B * C;
   const bool emit = ps.consumer == RPP_CONSUME_EMIT;
-  // emission must reach k_lim from the list (falling short means an exact scan of the whole column): aim well
-  // above k_lim; the estimate's 1-sigma error is ~20 %
-  const int target = emit ? (int)std::min<long>(ps.k_lim + ps.k_lim / 2 + 512, 1 << 28) : h->target;
-  SamplePlan plan = make_plan(n, C, target);
-  if (plan.on && emit) plan.CAP = 2 * target;
+  // emission must reach k_lim from the list (falling short means an exact scan of the whole column, which costs
+  // tens of milliseconds on a 6 M element column): the estimate's 1-sigma error is ~17 % with 96 group maxima, so
+  // narrow problem sets (few classes: the global filter, C = 1) sample 4x as many groups (1-sigma ~8 %) and aim at
+  // 2 k candidates — both tails (fewer than k, more than the list capacity) are then > 5 sigma away
+  const int emit_lanes = std::min(1024 / std::max(1, C), 48);
+  const bool emit_fine = emit && emit_lanes * RPP_GPT >= 256;
+  const int target = emit ? (int)std::min<long>(emit_fine ? 2 * ps.k_lim + 256 : ps.k_lim + ps.k_lim / 2 + 512, 1 << 28)
+                          : h->target;
+  SamplePlan plan = make_plan(n, C, target, emit_fine ? emit_lanes : 12);
+  if (plan.on && emit) plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target;
   const size_t gm_elems = plan.on ? (size_t)B * plan.G * C : 0;
 
   float* T = ar.take<float>(P);
@@ -242,7 +247,9 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   stage_mark(h, 0, st);
   if (plan.on && !h->force_scan) {
     const int threads = (int)align_up((size_t)plan.lanes * C, 32);
-    const int split = plan.rows_per_group < 16 ? plan.rows_per_group : 16;
+    // narrow problem sets (C = 1: 48 active threads per block) need more blocks in flight to cover the load latency
+    const int max_split = threads <= 64 ? 64 : 16;
+    const int split = plan.rows_per_group < max_split ? plan.rows_per_group : max_split;
     if (lv.L > 1)
       sample_max_kernel<true, false><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
                                                                          plan.rows_per_group, gm);
