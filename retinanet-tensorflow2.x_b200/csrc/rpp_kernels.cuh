@@ -760,6 +760,7 @@ struct NmsShared {
   float carea[RPP_NMS_NT];
   float4 corig[RPP_NMS_NT];  // boxes as emitted
   int nkept;
+  int nk_slot[2];            // kept count handed from tile t to tile t+1 (double-buffered: see hard_nms_consume)
   int done;
   int need_all;              // padded == 2: the class's padded slots can reach the output -> count past the threshold
   // followed in dynamic shared memory by: float4 kbox[M_lim] (kept, canonical), float karea[M_lim]
@@ -877,6 +878,10 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       sh->cbox[tid] = bx;
       sh->carea[tid] = area;
     }
+    // Kept count at the start of this group.  Read BEFORE the barrier: inside the tile loop the count travels
+    // through nk_slot[], written by the warp of tile t before the loop's barrier and read by everybody after it,
+    // so no thread ever reads a count in the same barrier interval in which another warp writes it.
+    int nk = sh->nkept;
     __syncthreads();
     // every warp builds the suppression mask of its own tile now (pairwise IoU does not depend on what is kept):
     // bit j of `row` = candidate j < lane of my tile overlaps me.  All warps are busy; the serial part of a round
@@ -892,9 +897,9 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
       }
     }
     int tested = 0;
+    bool full = false;
     const int ntiles = (gcount + 31) >> 5;
     for (int tile = 0; tile < ntiles; ++tile) {
-      const int nk = sh->nkept;
       if (alive && warp >= tile) {
         for (int k = tested; k < nk; ++k)
           if (nms_suppresses<PADDED>(bx, area, kbox[k], karea[k], thr)) { alive = false; break; }
@@ -922,14 +927,16 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
           P.sel_box[p * P.M + pos] = sh->corig[tid];
         }
         if (lane == 0) {
+          sh->nk_slot[(tile + 1) & 1] = nk + nnew;
           sh->nkept = nk + nnew;
           if (nk + nnew >= P.M_cap) sh->done = 1;
         }
       }
       __syncthreads();
-      if (sh->done) break;
+      nk = sh->nk_slot[(tile + 1) & 1];
+      if (nk >= P.M_cap) { full = true; break; }
     }
-    if (sh->done) break;
+    if (full) break;
   }
   consumed += m_eff;
   if (consumed >= P.k_lim || cut) {
@@ -1129,6 +1136,7 @@ __device__ void soft_nms_consume(const ColProblemParams& P, NmsShared* sh, SoftS
         }
         __syncwarp();
       }
+      __syncwarp();   // every lane has read the counts of this group before lane 0 replaces them
       if (lane == 0) { sh->nkept = nsel; ss->rcount = rcount; }
     }
     __syncthreads();
@@ -1939,7 +1947,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
   __shared__ float4 cbox[RPP_NMS_NT];
   __shared__ float carea[RPP_NMS_NT];
   __shared__ int ccls[RPP_NMS_NT];
-  __shared__ int s_nkept, s_done;
+  __shared__ int s_nkept, s_slot[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;
   const float thr = P.iou_threshold;
@@ -1949,8 +1957,9 @@ __global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
     P.out_scores[o] = 0.0f;
     P.out_classes[o] = 0;
   }
-  if (tid == 0) { s_nkept = 0; s_done = 0; }
+  if (tid == 0) s_nkept = 0;
   __syncthreads();
+  bool full = false;
   for (long g0 = 0; g0 < P.k; g0 += RPP_NMS_NT) {
     const u64 key = g0 + tid < P.k ? P.emit_key[(size_t)b * P.k + g0 + tid] : 0ull;
     const float score = key_score(key);
@@ -1976,6 +1985,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
       if (w > 0.0f && hgt > 0.0f) { area = __fmul_rn(w, hgt); bx = corner; }
     }
     cbox[tid] = bx; carea[tid] = area; ccls[tid] = cls;
+    int nk = s_nkept;   // read before the barrier; inside the tile loop the count travels through s_slot[]
     __syncthreads();
     u32 rowm = 0u;
     {
@@ -1988,7 +1998,6 @@ __global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
     int tested = 0;
     const int ntiles = (gcount + 31) >> 5;
     for (int tile = 0; tile < ntiles; ++tile) {
-      const int nk = s_nkept;
       if (alive && warp >= tile) {
         for (int q = tested; q < nk; ++q)
           if (kcls[q] == cls && iou_gt(bx, area, kbox[q], karea[q], thr)) { alive = false; break; }
@@ -2020,14 +2029,15 @@ __global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
           P.out_classes[o] = cls;
         }
         if (lane == 0) {
+          s_slot[(tile + 1) & 1] = nk + nnew;
           s_nkept = nk + nnew;
-          if (nk + nnew >= P.M) s_done = 1;
         }
       }
       __syncthreads();
-      if (s_done) break;
+      nk = s_slot[(tile + 1) & 1];
+      if (nk >= P.M) { full = true; break; }
     }
-    if (s_done || gcount < RPP_NMS_NT) break;
+    if (full || gcount < RPP_NMS_NT) break;
   }
   __syncthreads();
   if (tid == 0) P.out_valid[b] = s_nkept;
