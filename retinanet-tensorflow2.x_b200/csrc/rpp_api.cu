@@ -229,9 +229,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   float* bound = nullptr;
   float* stop_L = nullptr;
+  u32* work_items = nullptr;
   if (ps.two_pass_m1 > 0) {
     bound = ar.take<float>(P);
     stop_L = ar.take<float>((size_t)B);
+    work_items = ar.take<u32>(P);
   }
   if (ar.dry) return RPP_OK;
 
@@ -410,14 +412,16 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   const size_t smem_nms = align_up(nms_shared_bytes(pp.M_lim), 16);
   auto launch = [&](void) {
+    // worklist launches (finish pass): a few persistent blocks per SM instead of one block per problem
+    const unsigned grid = pp.work_items ? (unsigned)std::min<size_t>(P, (size_t)h->sm_count * 4) : (unsigned)P;
     if (ps.consumer == RPP_CONSUME_HARD)
-      col_problem_kernel<RPP_CONSUME_HARD><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+      col_problem_kernel<RPP_CONSUME_HARD><<<grid, RPP_NMS_NT, smem_nms, st>>>(pp);
     else if (ps.consumer == RPP_CONSUME_PADDED)
-      col_problem_kernel<RPP_CONSUME_PADDED><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+      col_problem_kernel<RPP_CONSUME_PADDED><<<grid, RPP_NMS_NT, smem_nms, st>>>(pp);
     else if (ps.consumer == RPP_CONSUME_SOFT)
-      col_problem_kernel<RPP_CONSUME_SOFT><<<(unsigned)P, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
+      col_problem_kernel<RPP_CONSUME_SOFT><<<grid, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
     else
-      col_problem_kernel<RPP_CONSUME_EMIT><<<(unsigned)P, RPP_NMS_NT, smem_nms, st>>>(pp);
+      col_problem_kernel<RPP_CONSUME_EMIT><<<grid, RPP_NMS_NT, smem_nms, st>>>(pp);
   };
   pp.pass = 0; pp.M_cap = pp.M_lim; pp.want0 = 248;   // ~250 keys: a 256-wide bitonic sort
   pp.bound = bound; pp.stop_L = stop_L;
@@ -430,10 +434,13 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       launch();
     LAUNCHED();
     const int bthreads = (int)std::min<size_t>(1024, align_up((size_t)C * m1, 32));
+    u32* work_ctl = tile_counter + 16;   // zeroed with the counters by the memset above
     perclass_bound_kernel<<<B, bthreads, (size_t)C * m1 * sizeof(float), st>>>(ps.sel_key, ps.sel_cnt, C, ps.M, m1,
-                                                                              ps.M, stop_L);
+                                                                              ps.M, stop_L, bound, work_items,
+                                                                              work_ctl);
     LAUNCHED();
     pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 96;   // re-run classes usually need a few dozen boxes
+    pp.work_items = work_items; pp.work_ctl = work_ctl;
   }
   if (emit) {   // whole-list sort in shared memory where it applies; the generic kernel takes the rest
     emit_sort_kernel<<<(unsigned)P, RPP_EMIT_NT, sizeof(EmitShared), st>>>(pp);

@@ -719,6 +719,10 @@ struct ColProblemParams {
   int want0;               // size of the first chunk
   float* bound;            // [P]
   const float* stop_L;     // [B] or nullptr
+  // finish pass: the bound kernel lists the problems that still need work (usually 1-3 % of them) and a few
+  // persistent blocks pop them, instead of launching P blocks of which almost all exit at once
+  const u32* work_items;   // [P] or nullptr (one block per problem)
+  u32* work_ctl;           // [0] = number of items, [1] = pop cursor
   long k_lim;              // max candidates consumed (pre_nms_top_k after clamping; N when unfiltered)
   int M;                   // stride of the sel_* arrays
   // candidate lists
@@ -1164,12 +1168,9 @@ __device__ void emit_consume(const ColProblemParams& P, NmsShared* sh, size_t p,
 #define RPP_CONSUME_PADDED 3   // hard NMS with tf.image.non_max_suppression_padded semantics (TPU branches)
 
 template <int MODE>
-__global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  NmsShared* sh = reinterpret_cast<NmsShared*>(smem_raw);
-  SoftShared* ss = reinterpret_cast<SoftShared*>(smem_raw + ((nms_shared_bytes(P.M_lim) + 15) & ~(size_t)15));
+__device__ __forceinline__ void col_problem_body(const ColProblemParams& P, const size_t p, NmsShared* sh,
+                                                 SoftShared* ss) {
   const int tid = threadIdx.x;
-  const size_t p = blockIdx.x;
   const int b = (int)(p / P.C), c = (int)(p % P.C);
   if (MODE == RPP_CONSUME_EMIT && P.emit_done && P.emit_done[p]) return;   // done by emit_sort_kernel
   if (MODE != RPP_CONSUME_EMIT && P.pass == 2) {
@@ -1313,34 +1314,66 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
   }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsShared* sh = reinterpret_cast<NmsShared*>(smem_raw);
+  SoftShared* ss = reinterpret_cast<SoftShared*>(smem_raw + ((nms_shared_bytes(P.M_lim) + 15) & ~(size_t)15));
+  __shared__ u32 s_item;
+  for (u32 it = 0;; ++it) {   // one problem per block, or a persistent block popping the finish pass's worklist
+    size_t p = blockIdx.x;
+    if (P.work_items) {
+      __syncthreads();        // the previous problem is finished by every thread (and s_item was read)
+      if (threadIdx.x == 0) s_item = atomicAdd(&P.work_ctl[1], 1u);
+      __syncthreads();
+      if (s_item >= P.work_ctl[0]) break;
+      p = P.work_items[s_item];
+    } else if (it > 0) {
+      break;
+    }
+    col_problem_body<MODE>(P, p, sh, ss);
+  }
+}
+
 // Per image: stop_L = the Mtop-th best score among the boxes the probes kept (-inf if there are fewer): every one of
 // them is a real final candidate, so the image's Mtop-th best FINAL score is >= stop_L.
 __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int* __restrict__ sel_cnt, int C, int M,
-                                      int m1, int Mtop, float* __restrict__ stop_L) {
+                                      int m1, int Mtop, float* __restrict__ stop_L, const float* __restrict__ bound,
+                                      u32* __restrict__ work_items, u32* __restrict__ work_ctl) {
   extern __shared__ float s_sc[];  // [C * m1]
   __shared__ int s_n;
+  __shared__ float s_L;
   const int b = blockIdx.x;
   const int n_all = C * m1;
   for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
     const int c = i / m1, slot = i - c * m1;
     s_sc[i] = slot < sel_cnt[(size_t)b * C + c] ? key_score(sel_key[((size_t)b * C + c) * M + slot]) : -INFINITY;
   }
-  if (threadIdx.x == 0) { s_n = 0; stop_L[b] = -INFINITY; }
+  if (threadIdx.x == 0) { s_n = 0; s_L = -INFINITY; }
   __syncthreads();
   int local = 0;
   for (int i = threadIdx.x; i < n_all; i += blockDim.x) local += s_sc[i] > -INFINITY;
   if (local) atomicAdd(&s_n, local);
   __syncthreads();
-  if (s_n < Mtop) return;
-  for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
-    const float v = s_sc[i];
-    if (!(v > -INFINITY)) continue;
-    int rank = 0;
-    for (int j = 0; j < n_all; ++j) {
-      const float o = s_sc[j];
-      rank += (o > v) || (o == v && j < i);
+  if (s_n >= Mtop) {
+    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
+      const float v = s_sc[i];
+      if (!(v > -INFINITY)) continue;
+      int rank = 0;
+      for (int j = 0; j < n_all; ++j) {
+        const float o = s_sc[j];
+        rank += (o > v) || (o == v && j < i);
+      }
+      if (rank == Mtop - 1) s_L = v;   // exactly one element has this rank
     }
-    if (rank == Mtop - 1) stop_L[b] = v;
+  }
+  __syncthreads();
+  const float L = s_L;
+  if (threadIdx.x == 0) stop_L[b] = L;
+  // worklist of the finish pass: the classes whose probe stopped at its cap with a bound that can still matter
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float bd = bound[(size_t)b * C + c];
+    if (!(bd == -INFINITY || bd < L)) work_items[atomicAdd(&work_ctl[0], 1u)] = (u32)((size_t)b * C + c);
   }
 }
 
@@ -1360,8 +1393,6 @@ __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int
 #define RPP_PROBE_MAXCAP 16
 
 struct ProbeWarpShared {
-  float4 cbox[32];
-  float carea[32];
   float4 kbox[RPP_PROBE_MAXCAP];
   float karea[RPP_PROBE_MAXCAP];
 };
@@ -1395,15 +1426,22 @@ __global__ void __launch_bounds__(RPP_PROBE_WARPS * 32) probe_warp_kernel(ColPro
 
   // 1. per-lane top-3 raw keys
   u64 t0 = 0ull, t1 = 0ull, t2 = 0ull;
-  for (int i = lane; i < n; i += 32) {
-    const uint2 e = lst[i];
-    const u64 rk = ((u64)ord_f32(__uint_as_float(e.x)) << 32) | (u64)(0xffffffffu - e.y);
-    if (rk > t2) {
-      if (rk > t1) {
-        t2 = t1;
-        if (rk > t0) { t1 = t0; t0 = rk; } else { t1 = rk; }
-      } else {
-        t2 = rk;
+  for (int i0 = lane; i0 < n; i0 += 4 * 32) {   // 4 independent loads in flight per lane
+    uint2 e4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e4[u] = i0 + u * 32 < n ? lst[i0 + u * 32] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const u64 rk = i0 + u * 32 < n
+                         ? ((u64)ord_f32(__uint_as_float(e4[u].x)) << 32) | (u64)(0xffffffffu - e4[u].y)
+                         : 0ull;
+      if (rk > t2) {
+        if (rk > t1) {
+          t2 = t1;
+          if (rk > t0) { t1 = t0; t0 = rk; } else { t1 = rk; }
+        } else {
+          t2 = rk;
+        }
       }
     }
   }
@@ -1468,38 +1506,29 @@ __global__ void __launch_bounds__(RPP_PROBE_WARPS * 32) probe_warp_kernel(ColPro
       const float4 cb = canon_box(orig, area);
       if (area > 0.0f) bx = cb; else area = 0.0f;
     }
-    sh->cbox[lane] = bx;
-    sh->carea[lane] = area;
-    __syncwarp();
     for (int q = 0; q < nk && alive; ++q)
       if (iou_gt(bx, area, sh->kbox[q], sh->karea[q], thr)) alive = false;
-    const u32 cand_bits = __ballot_sync(RPP_FULL_MASK, alive);
-    u32 row = 0u;
-    for (int j = 0; j < 31; ++j) {
-      if (!((cand_bits >> j) & 1u)) continue;   // uniform
-      if (alive && j < lane && iou_gt(bx, area, sh->cbox[j], sh->carea[j], thr)) row |= 1u << j;
+    // The probe keeps only M_cap (a handful of) boxes: walk the survivors in order — the best remaining candidate is
+    // kept, its box is broadcast, every later candidate tests itself against it — instead of building the full
+    // 32 x 32 suppression mask first (one IoU per lane per kept box instead of 31 per lane).
+    u32 alive_bits = __ballot_sync(RPP_FULL_MASK, alive);
+    while (alive_bits != 0u && nk < P.M_cap) {
+      const int i = __ffs(alive_bits) - 1;
+      const float4 kb = make_float4(__shfl_sync(RPP_FULL_MASK, bx.x, i), __shfl_sync(RPP_FULL_MASK, bx.y, i),
+                                    __shfl_sync(RPP_FULL_MASK, bx.z, i), __shfl_sync(RPP_FULL_MASK, bx.w, i));
+      const float ka = __shfl_sync(RPP_FULL_MASK, area, i);
+      if (lane == i) {
+        sh->kbox[nk] = bx;
+        sh->karea[nk] = area;
+        P.sel_key[p * P.M + nk] = key;
+        P.sel_box[p * P.M + nk] = orig;
+      }
+      last_key = __shfl_sync(RPP_FULL_MASK, key, i);
+      ++nk;
+      alive_bits &= ~(1u << i);
+      const bool sup = ((alive_bits >> lane) & 1u) && iou_gt(bx, area, kb, ka, thr);
+      alive_bits &= ~__ballot_sync(RPP_FULL_MASK, sup);
     }
-    u32 kept_bits = 0u;
-#pragma unroll
-    for (int l = 0; l < 32; ++l) {
-      const u32 r = __shfl_sync(RPP_FULL_MASK, row, l);
-      if (((cand_bits >> l) & 1u) && (r & kept_bits) == 0u) kept_bits |= 1u << l;
-    }
-    int nnew = __popc(kept_bits);
-    const int room = P.M_cap - nk;
-    while (nnew > room) {
-      kept_bits &= ~(1u << (31 - __clz(kept_bits)));
-      --nnew;
-    }
-    if ((kept_bits >> lane) & 1u) {
-      const int pos = nk + __popc(kept_bits & ((1u << lane) - 1u));
-      sh->kbox[pos] = bx;
-      sh->karea[pos] = area;
-      P.sel_key[p * P.M + pos] = key;
-      P.sel_box[p * P.M + pos] = orig;
-    }
-    if (nnew > 0) last_key = __shfl_sync(RPP_FULL_MASK, key, 31 - __clz(kept_bits));
-    nk += nnew;
     __syncwarp();
   }
   if (lane == 0) {
