@@ -66,6 +66,7 @@ struct Handle {
   cudaStream_t side;
   cudaEvent_t ev_chunk[8];
   cudaEvent_t ev_join;
+  int half_variant;      // tuning knob (env RPP_HALF_VARIANT): 16-bit collect, 0 = unroll 4 / 3 CTAs per SM, 1 = 8 / 2
   int collect_variant;   // tuning knob (env RPP_COLLECT_VARIANT): 0 = unroll 4 / 3 CTAs per SM, 1 = 4/2, 2 = 8/2
   DecodeParams dp;
   // optional per-stage timing (bench.py roofline): 5 events per call = boundaries of sample|collect|nms|merge
@@ -114,7 +115,12 @@ SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
   const int G = lanes * RPP_GPT;
   // group size chosen so that the wanted logit sits near the 70th percentile of the group maxima:
   // rows per group g = -ln(0.7) * n / target, i.e. one sampled row every S = target / (0.357 * G) rows (~3 %)
-  int S = (int)std::floor(target / (0.357 * G));
+  static const double neg_ln_q = [] {   // tuning knob: the quantile of the group maxima the plan aims at
+    const char* v = getenv("RPP_SAMPLE_Q");
+    const double q = v ? atof(v) : 0.7;
+    return -std::log(q > 0.05 && q < 0.97 ? q : 0.7);
+  }();
+  int S = (int)std::floor(target / (neg_ln_q * G));
   if (S < 1) S = 1;
   long g = n / ((long)S * G);
   if (g < 8) {   // the target is a large fraction of the column: sample denser, accept a lower quantile
@@ -286,7 +292,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
         return fail(RPP_EINVAL, "16-bit logits need num_classes % 8 == 0 and 16-byte aligned tensors");
       const int C8 = C / 8;
       const int lanes = RPP_COLLECT_NT / C8;
-      const int UNROLL = 4;
+      const int UNROLL = h->half_variant == 1 ? 8 : 4;
       long rows_per_tile = plan.on ? (long)(24.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
@@ -297,14 +303,17 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       }
       lv.tile_off[lv.L] = tiles_per_image;
       const long n_tiles = (long)B * tiles_per_image;
-      const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
       const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
-      if (lv.dtype == RPP_DT_F16)
-        collect_cols8_half_kernel<4, RPP_DT_F16><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(
-            lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter);
-      else
-        collect_cols8_half_kernel<4, RPP_DT_BF16><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(
-            lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter);
+#define RPP_LAUNCH_HALF(U, DT, MB)                                                                               \
+      collect_cols8_half_kernel<U, DT, MB><<<(unsigned)std::min<long>((long)h->sm_count * MB, n_tiles),           \
+                                            RPP_COLLECT_NT, smem, st>>>(                                          \
+          lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter)
+      if (h->half_variant == 1) {
+        if (lv.dtype == RPP_DT_F16) RPP_LAUNCH_HALF(8, RPP_DT_F16, 2); else RPP_LAUNCH_HALF(8, RPP_DT_BF16, 2);
+      } else {
+        if (lv.dtype == RPP_DT_F16) RPP_LAUNCH_HALF(4, RPP_DT_F16, 3); else RPP_LAUNCH_HALF(4, RPP_DT_BF16, 3);
+      }
+#undef RPP_LAUNCH_HALF
       LAUNCHED();
     } else if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT) {
       const int C4 = C / 4;
@@ -807,6 +816,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_HALF_VARIANT");
+    h->half_variant = v ? atoi(v) : 1;   // measured: 0.162 ms vs 0.168 ms for the 0.79 GB bf16 stream of configs[1]
     v = getenv("RPP_WARP_PROBE");
     h->warp_probe = v ? atoi(v) : 1;
     v = getenv("RPP_PROBE_EXTRA");
@@ -873,8 +884,10 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(collect_cols8_half_kernel<4, RPP_DT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(collect_cols8_half_kernel<4, RPP_DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols8_half_kernel<4, RPP_DT_F16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols8_half_kernel<4, RPP_DT_BF16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols8_half_kernel<8, RPP_DT_F16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_cols8_half_kernel<8, RPP_DT_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_levels_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -488,8 +488,8 @@ template <> __device__ __forceinline__ u32 ge2_mask<RPP_DT_BF16>(u32 v, u32 t) {
   return __hge2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v), *reinterpret_cast<const __nv_bfloat162*>(&t));
 }
 
-template <int UNROLL, int DT>
-__global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
+template <int UNROLL, int DT, int MINB>
+__global__ void __launch_bounds__(RPP_COLLECT_NT, MINB)
 collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32* __restrict__ cand_count,
                           uint2* __restrict__ cand, int CAP, int B, long N, int C8, int lanes, int rows_per_tile,
                           int tiles_per_image, u32* __restrict__ tile_counter) {
@@ -552,22 +552,21 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
             v[u] = make_uint4(0u, 0u, 0u, 0u);
           }
         }
-        u32 mask = 0u;   // bit 8u+i: class 8*co+i of load u passes
+        u64 mask = 0ull;   // bit 8u+i: class 8*co+i of load u passes
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-          const u32 w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-          u32 m = 0u;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const u32 g = ge2_mask<DT>(w[i], th[i]);          // 0xFFFF per passing half
-            m |= ((g & 1u) | ((g >> 15) & 2u)) << (2 * i);
-          }
+          // 0xFFFF per passing half -> one bit per class: a byte of each half through PRMT, one distinct bit kept per
+          // byte, bytes summed (= OR, the bits are distinct) by a multiply
+          const u32 g0 = ge2_mask<DT>(v[u].x, th[0]), g1 = ge2_mask<DT>(v[u].y, th[1]);
+          const u32 g2 = ge2_mask<DT>(v[u].z, th[2]), g3 = ge2_mask<DT>(v[u].w, th[3]);
+          const u32 t = (__byte_perm(g0, g1, 0x6420) & 0x08040201u) | ((__byte_perm(g2, g3, 0x6420) & 0x08040201u) << 4);
+          u32 m = (t * 0x01010101u) >> 24;   // bit 2i + h = half h of word i
           if (row + (long)u * lanes >= r1) m = 0u;
-          mask |= m << (8 * u);
+          mask |= (u64)m << (8 * u);
         }
         while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1u;
+          const int bit = __ffsll((long long)mask) - 1;
+          mask &= mask - 1ull;
           const int c = co * 8 + (bit & 7);
           const long r = row + (long)(bit >> 3) * lanes;
           const float val = half_bits_to_f32(__ldg(xb + (size_t)r * C + c), dtype);
