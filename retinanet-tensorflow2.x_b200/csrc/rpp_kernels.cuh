@@ -130,7 +130,8 @@ __global__ void decode_kernel(const float4* __restrict__ deltas, const float4* _
 #define RPP_GPT 8   // groups per thread; G = lanes * RPP_GPT
 
 template <bool LEVELS, bool HALF>
-__global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stride, int lanes,
+__global__ void __launch_bounds__(1024, 2)   // two 960-thread blocks per SM: at most 32 registers
+sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stride, int lanes,
                                   int rounds, u32* __restrict__ gm /*[B][G][C]*/) {
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
   const int c = threadIdx.x % C, rl = threadIdx.x / C;
@@ -155,6 +156,29 @@ __global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stri
   int lvl = 0;
   for (int r = split; r < rounds; r += nsplit) {
     float v[RPP_GPT];
+    // LEVELS: a round covers G * stride consecutive rows; when they all lie in one level (all but the few rounds that
+    // straddle a boundary) the level is resolved once and the loads look like the fused tensor's
+    bool one_level = false;
+    const float* lbase = nullptr;
+    if (LEVELS) {
+      const long row_first = (long)r * G * stride, row_last = ((long)r * G + G - 1) * stride;
+      while (lvl + 1 < nlv && row_first >= s_off[lvl + 1]) ++lvl;
+      one_level = row_last < s_off[lvl + 1];
+      // lbase[row * C] (in elements of the input type) is element (b, row - off_l, c) of the level tensor
+      const long n_l = s_off[lvl + 1] - s_off[lvl];
+      lbase = s_x[lvl];
+      const long shift = ((long)b * n_l - s_off[lvl]) * C + c;
+      lbase = HALF ? reinterpret_cast<const float*>(reinterpret_cast<const unsigned short*>(lbase) + shift)
+                   : lbase + shift;
+    }
+    if (LEVELS && one_level) {
+#pragma unroll
+      for (int i = 0; i < RPP_GPT; ++i) {
+        const long s = (long)r * G + rl + i * lanes;
+        if (HALF) v[i] = half_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(lbase) + (size_t)(s * stride) * C), dtype);
+        else v[i] = __ldg(lbase + (size_t)(s * stride) * C);
+      }
+    } else
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) {
       const long s = (long)r * G + rl + i * lanes;  // sampled row index; group = rl + i * lanes
@@ -162,8 +186,10 @@ __global__ void sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stri
         const long row = s * stride;
         while (lvl + 1 < nlv && row >= s_off[lvl + 1]) ++lvl;
         const size_t idx = ((size_t)b * (s_off[lvl + 1] - s_off[lvl]) + (row - s_off[lvl])) * C + c;
-        v[i] = dtype == RPP_DT_F32 ? __ldg(s_x[lvl] + idx)
-                                   : half_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(s_x[lvl]) + idx), dtype);
+        // (the element type is a template parameter here too: a run-time branch around the load keeps the compiler
+        // from batching the RPP_GPT loads of a round)
+        if (HALF) v[i] = half_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(s_x[lvl]) + idx), dtype);
+        else v[i] = __ldg(s_x[lvl] + idx);
       } else if (HALF) {
         v[i] = half_bits_to_f32(__ldg(hbase + (size_t)(s * stride) * C), dtype);
       } else {
