@@ -197,7 +197,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   // narrow problem sets (few classes: the global filter, C = 1) sample 4x as many groups (1-sigma ~8 %) and aim at
   // 2 k candidates — both tails (fewer than k, more than the list capacity) are then > 5 sigma away
   const int emit_lanes = std::min(1024 / std::max(1, C), 48);
-  const bool emit_fine = emit && emit_lanes * RPP_GPT >= 256;
+  const bool emit_fine = emit && emit_lanes * RPP_GPT >= 256 && n >= (1L << 19);   // short columns: the scan is cheap
   const int target = emit ? (int)std::min<long>(emit_fine ? 2 * ps.k_lim + 256 : ps.k_lim + ps.k_lim / 2 + 512, 1 << 28)
                           : h->target;
   SamplePlan plan = make_plan(n, C, target, emit_fine ? emit_lanes : 12);
