@@ -66,6 +66,7 @@ struct Handle {
   cudaStream_t side;
   cudaEvent_t ev_chunk[8];
   cudaEvent_t ev_join;
+  int emit_short;        // test knob (env RPP_EMIT_SHORT): aim the top-k lists at k/2 so that every problem falls back
   int half_variant;      // tuning knob (env RPP_HALF_VARIANT): 16-bit collect, 0 = unroll 4 / 3 CTAs per SM, 1 = 8 / 2
   int collect_variant;   // tuning knob (env RPP_COLLECT_VARIANT): 0 = unroll 4 / 3 CTAs per SM, 1 = 4/2, 2 = 8/2
   DecodeParams dp;
@@ -200,7 +201,8 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   const bool emit_fine = emit && emit_lanes * RPP_GPT >= 256 && n >= (1L << 19);   // short columns: the scan is cheap
   const int target = emit ? (int)std::min<long>(emit_fine ? 2 * ps.k_lim + 256 : ps.k_lim + ps.k_lim / 2 + 512, 1 << 28)
                           : h->target;
-  SamplePlan plan = make_plan(n, C, target, emit_fine ? emit_lanes : 12);
+  SamplePlan plan = make_plan(n, C, h->emit_short && emit ? (int)std::max<long>(64, ps.k_lim / 2) : target,
+                              emit_fine ? emit_lanes : 12);
   if (plan.on && emit) plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target;
   const size_t gm_elems = plan.on ? (size_t)B * plan.G * C : 0;
 
@@ -819,6 +821,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_EMIT_SHORT");
+    h->emit_short = v ? atoi(v) : 0;
     v = getenv("RPP_HALF_VARIANT");
     h->half_variant = v ? atoi(v) : 1;   // measured: 0.162 ms vs 0.168 ms for the 0.79 GB bf16 stream of configs[1]
     v = getenv("RPP_WARP_PROBE");

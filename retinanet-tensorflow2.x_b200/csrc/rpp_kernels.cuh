@@ -1587,33 +1587,75 @@ __global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams
   EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
   const int tid = threadIdx.x;
   const size_t p = blockIdx.x;
+  const int b = (int)(p / P.C), c = (int)(p % P.C);
   if (tid == 0) { P.emit_done[p] = 0; sh->valid = 0; }
   const u32 n_raw = P.cand_count[p];
-  if (P.force_scan || (n_raw & 0x80000000u) || n_raw > (u32)P.CAP || n_raw > RPP_EMIT_CAP || n_raw == 0) return;
-  const int n_list = (int)n_raw;
-  const float T = P.T[p];
-  const bool list_complete = !(T > P.T_min);
-  const float s_edge = list_complete ? P.score_threshold : col_score(P, T);
-  const uint2* lst = P.cand + p * (size_t)P.CAP;
-  int local = 0;
-  for (int i = tid; i < n_list; i += RPP_EMIT_NT) {
-    const uint2 e = lst[i];
-    const float sc = col_score(P, __uint_as_float(e.x));
-    u64 k = 0ull;
-    if (sc > P.score_threshold && (list_complete || sc > s_edge)) { k = make_key(sc, e.y); ++local; }
-    sh->keys[i] = k;
+  if (n_raw & 0x80000000u) return;
+  const bool list_ok = !(P.force_scan || n_raw > (u32)P.CAP || n_raw > RPP_EMIT_CAP || n_raw == 0);
+  int n_keys = 0;   // scored keys in sh->keys[0 .. n_keys)
+  int nv = 0;       // of which valid (strictly above everything that is not in sh->keys)
+  if (list_ok) {
+    n_keys = (int)n_raw;
+    const float T = P.T[p];
+    const bool list_complete = !(T > P.T_min);
+    const float s_edge = list_complete ? P.score_threshold : col_score(P, T);
+    const uint2* lst = P.cand + p * (size_t)P.CAP;
+    int local = 0;
+    for (int i = tid; i < n_keys; i += RPP_EMIT_NT) {
+      const uint2 e = lst[i];
+      const float sc = col_score(P, __uint_as_float(e.x));
+      u64 k = 0ull;
+      if (sc > P.score_threshold && (list_complete || sc > s_edge)) { k = make_key(sc, e.y); ++local; }
+      sh->keys[i] = k;
+    }
+    __syncthreads();
+    if (local) atomicAdd(&sh->valid, local);
+    __syncthreads();
+    nv = sh->valid;
   }
-  __syncthreads();
-  if (local) atomicAdd(&sh->valid, local);
-  __syncthreads();
-  const int nv = sh->valid;
-  if ((long)nv < P.k_lim) return;   // not enough candidates strictly above the edge: the generic kernel decides
+  if ((long)nv < P.k_lim) {
+    // The list came up short of k (the sampled threshold was too high), overflowed or does not exist.  Instead of
+    // leaving the problem to repeated scored scans of the column (tens of milliseconds on the flat 6 M element axis
+    // of the global filter), collect again INSIDE the block with an exact cut: one radix select over the column's
+    // RAW keys (value bits | ~row; no sigmoid) delivers its best ~1.1 k .. 16 K rows, everything else is below the
+    // cut; the selected rows are scored and, by the edge rule, those strictly above the score of the cut are complete.
+    if (P.force_scan) return;   // debug: the generic kernel's exact scan is what is being tested
+    __syncthreads();
+    u64 KBr = ~0ull;
+    u32 population = 0u;
+    long want = P.k_lim + P.k_lim / 8 + 64;
+    if (want > RPP_EMIT_CAP) return;   // more than one block's worth: the generic kernel takes it
+    const int m = select_chunk<RPP_EMIT_NT>(
+        [&](int i) -> u64 {
+          const float raw = lv_val(P.lv, b, i, P.C, c);
+          return raw >= P.T_min ? (((u64)ord_f32(raw) << 32) | (u64)(0xffffffffu - (u32)i)) : 0ull;
+        },
+        (int)P.N, KBr, (int)want, sh->keys, RPP_EMIT_CAP, &sh->sel, /*sort=*/false, &population);
+    const bool whole = (u32)m == population;        // every eligible row of the column was selected
+    const float e0 = whole ? P.score_threshold : col_score(P, unord_f32((u32)(KBr >> 32)));
+    if (tid == 0) sh->valid = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < m; i += RPP_EMIT_NT) {
+      const u64 rk = sh->keys[i];
+      const float sc = col_score(P, unord_f32((u32)(rk >> 32)));
+      u64 k = 0ull;
+      if (sc > P.score_threshold && (whole || sc > e0)) { k = make_key(sc, key_tie(rk)); ++local; }
+      sh->keys[i] = k;
+    }
+    __syncthreads();
+    if (local) atomicAdd(&sh->valid, local);
+    __syncthreads();
+    n_keys = m;
+    nv = sh->valid;
+    if ((long)nv < P.k_lim) return;   // a huge tie group at the cut, or a coarse radix cut: the generic kernel decides
+  }
   // the k best keys, in order: usually ONE exact radix cut to [k, 8192] keys and one bitonic sort of that chunk
   u64 KB = ~0ull;
   long emitted = 0;
   while (emitted < P.k_lim) {
     const long want = P.k_lim - emitted;
-    const int m = select_chunk<RPP_EMIT_NT>([&](int i) { return sh->keys[i]; }, n_list, KB,
+    const int m = select_chunk<RPP_EMIT_NT>([&](int i) { return sh->keys[i]; }, n_keys, KB,
                                             (int)(want < RPP_EMIT_CHUNK ? want : RPP_EMIT_CHUNK), sh->chunk,
                                             RPP_EMIT_CHUNK, &sh->sel);
     if (m == 0) break;

@@ -27,10 +27,10 @@ struct SelectScratch {
 
 // Returns m in [0, CC]: chunk[0..m) = the m largest keys of {key(i) : 0 < key(i) < KB}, sorted descending; KB is
 // lowered to the smallest key returned.  m == 0 <=> the domain holds no key below KB.  m >= min(want/4, remaining).
-// All threads of the block must call; chunk must hold next_pow2(CC) keys.
+// All threads of the block must call; chunk must hold next_pow2(CC) keys (CC keys when sort == false).
 template <int NT, class KeyFn>
 __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int CC, SelectScratch<NT>* sc,
-                            bool sort = true) {
+                            bool sort = true, u32* population = nullptr) {
   const int tid = threadIdx.x;
   // pass 1: population below the bound
   u32 cnt = 0;
@@ -46,6 +46,7 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
     }
   }
   block_cnt_max_min<NT>(cnt, mx, mn, &sc->bs);
+  if (population) *population = cnt;   // number of keys below the bound (per-thread copy of a uniform value)
   if (cnt == 0) return 0;
 
   u64 lo = mn;

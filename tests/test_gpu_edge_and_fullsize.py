@@ -305,6 +305,35 @@ def test_tuning_knobs_do_not_change_results(monkeypatch, env):
         assert np.array_equal(a[key], b[key]), key
 
 
+@pytest.mark.parametrize('dist', ['dense', 'sparse', 'quantized', 'coarse'])
+def test_topk_emission_fallbacks(ref, monkeypatch, dist):
+    """RPP_EMIT_SHORT=1 aims the sampled top-k lists at k/2, so every problem takes the fallback of the emission
+    kernel (an exact in-block re-collect on raw values); 'coarse' logits (eight distinct values: tie groups far larger
+    than a block can hold) push it further, to the generic exact scan.  Results must not move."""
+    from retinanet.model.layers import FilterTopKDetections
+    monkeypatch.setenv('RPP_EMIT_SHORT', '1')
+    rng = np.random.default_rng(17)
+    # fused chain with the global filter: top-k over the flat (anchor, class) axis of 153 648 logits per image
+    p = make_params(320, num_classes=8, mode='GlobalSoftNMS', pre_nms_top_k=1500, filter_per_class=False,
+                    max_detections=50, soft_nms_sigma=0.5)
+    layer = _fused(p)
+    N = layer.handle(8).num_anchors
+    if dist == 'coarse':
+        logits = rng.choice(np.array([-30.0, -3.0, -0.5, 0.0, 0.5, 3.0, 20.0, 40.0], np.float32), size=(3, N, 8))
+        deltas = np.clip(rng.standard_normal((3, N, 4)) * 0.5, -4, 4).astype(np.float32)
+    else:
+        logits, deltas = synth_inputs(3, N, 8, seed=81, dist=dist)
+    got = to_numpy(layer({'class_logits': _gpu(logits), 'encoded_boxes': _gpu(deltas)}))
+    assert image_mismatches(got, oracle_detect(ref, p, logits, deltas)) == []
+    # the stage-wise filter (rpp_topk) on score columns of 19 206 rows, per class and global
+    scores = ref.sigmoid(logits)
+    boxes = rng.uniform(0, 1, (3, N, 4)).astype(np.float32)
+    for fpc, k in [(True, 700), (False, 1500)]:
+        z = FilterTopKDetections(k, fpc)({'scores': _gpu(scores), 'boxes': _gpu(boxes)})
+        es, eb, _ = (ref.filter_per_class if fpc else ref.filter_global)(scores, boxes, k)
+        assert np.array_equal(z['scores'].cpu().numpy(), es) and np.array_equal(z['boxes'].cpu().numpy(), eb)
+
+
 @pytest.mark.parametrize('mode', ['CombinedNMS', 'PerClassHardNMS', 'GlobalHardNMS'])
 def test_coco_post_format_epilogue(ref, mode):
     """COCOEvaluator.accumulate_results (eval/coco_evaluator.py:95-134) on the device vs its numpy restatement."""
