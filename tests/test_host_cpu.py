@@ -170,6 +170,23 @@ def test_gather_detections_gloo_world2(tmp_path):
         assert p.returncode == 0, out.decode()
 
 
+def test_config_struct_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of rpp_config (retinanet/_native.py) has the size and field offsets the C compiler gives the
+    struct of include/retinapost.h."""
+    from retinanet import _native
+    fields = [f[0] for f in _native.RppConfig._fields_]
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "retinapost.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(rpp_config));\n' +
+                   ''.join('  printf("%zu\\n", offsetof(rpp_config, {}));\n'.format(f) for f in fields) +
+                   '  return 0;\n}\n')
+    exe = str(tmp_path / 'layout')
+    subprocess.check_call(['gcc', str(src), '-I' + os.path.join(ROOT, 'include'), '-o', exe])
+    out = [int(v) for v in subprocess.check_output([exe], text=True).split()]
+    assert out[0] == ctypes.sizeof(_native.RppConfig)
+    assert out[1:] == [getattr(_native.RppConfig, f).offset for f in fields]
+
+
 def _build_abi_smoke(tmp_path):
     exe = str(tmp_path / 'abi_smoke')
     cmd = ['gcc', os.path.join(ROOT, 'tests', 'abi_smoke.c'), '-I' + os.path.join(ROOT, 'include'),
