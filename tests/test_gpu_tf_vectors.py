@@ -41,7 +41,7 @@ def test_soft_nms_vector():
     # V5 soft: config sigma 1.0 -> NonMaxSuppressionV5(soft_nms_sigma=0.5) (postprocessing_ops.py:255)
     out = _run('GlobalSoftNMS', (BOXES * S).reshape(1, 6, 4), SCORES.reshape(1, 6, 1), 6, iou=0.5, thr=0.0, sigma=1.0)
     assert out['valid_detections'].tolist() == [6]
-    assert _indices(out['boxes'][0], BOXES * S) == [3, 0, 1, 5, 4, 2]
+    assert _indices(out['boxes'][0], np.clip(BOXES * S, 0, 1)) == [3, 0, 1, 5, 4, 2]
     np.testing.assert_allclose(out['scores'][0], [0.95, 0.9, 0.384, 0.3, 0.256, 0.197], rtol=1e-2, atol=1e-2)
 
 
