@@ -1,7 +1,8 @@
 """TensorFlow's published unit-test vectors (see tests/test_tf_published_vectors.py) through the CUDA path, via the
-reference's layer API.  The layers clip boxes to [0, 1] before NonMaxSuppressionV5, so the vectors' boxes (coordinates
-up to 101) are scaled by 1/128 — a power of two: every IoU keeps its exact value — except for CombinedNMS, which takes
-them as they are and clips on output like TF's kernel."""
+reference's layer API.  The layers clip boxes to [0, 1] before NonMaxSuppressionV5 (postprocessing_ops.py:275, :501),
+so the vectors' boxes (coordinates from -0.1 to 101) are translated by +0.125 and scaled by 1/128 (IoU is invariant
+under both; the soft-NMS scores are compared at TF's own 1e-2 tolerance) — except for CombinedNMS, which takes them
+as they are and clips on output like TF's kernel."""
 import numpy as np
 import pytest
 
@@ -11,6 +12,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip('torch')
 
 S = np.float32(1.0 / 128.0)
+SHIFT = np.array([0, 0.125, 0, 0.125], np.float32)
 
 
 def _run(mode, boxes, scores, M, iou=0.5, thr=0.0, sigma=None, **kw):
@@ -26,8 +28,9 @@ def _indices(out_boxes, boxes):
 
 @pytest.mark.parametrize('boxes', [BOXES, FLIPPED], ids=['as_published', 'flipped_coordinates'])
 def test_hard_nms_select_from_three_clusters(boxes):
-    b = (boxes * S).reshape(1, 6, 4)
+    b = ((boxes + SHIFT) * S).reshape(1, 6, 4)
     clipped = np.clip(b[0], 0, 1)
+    assert np.array_equal(clipped, b[0])
     for M, exp in [(3, [3, 0, 5]), (2, [3, 0]), (30, [3, 0, 5])]:
         out = _run('PerClassHardNMS', b, SCORES.reshape(1, 6, 1), M)
         v = int(out['valid_detections'][0])
@@ -39,9 +42,10 @@ def test_hard_nms_select_from_three_clusters(boxes):
 
 def test_soft_nms_vector():
     # V5 soft: config sigma 1.0 -> NonMaxSuppressionV5(soft_nms_sigma=0.5) (postprocessing_ops.py:255)
-    out = _run('GlobalSoftNMS', (BOXES * S).reshape(1, 6, 4), SCORES.reshape(1, 6, 1), 6, iou=0.5, thr=0.0, sigma=1.0)
+    b = (BOXES + SHIFT) * S
+    out = _run('GlobalSoftNMS', b.reshape(1, 6, 4), SCORES.reshape(1, 6, 1), 6, iou=0.5, thr=0.0, sigma=1.0)
     assert out['valid_detections'].tolist() == [6]
-    assert _indices(out['boxes'][0], np.clip(BOXES * S, 0, 1)) == [3, 0, 1, 5, 4, 2]
+    assert _indices(out['boxes'][0], b) == [3, 0, 1, 5, 4, 2]
     np.testing.assert_allclose(out['scores'][0], [0.95, 0.9, 0.384, 0.3, 0.256, 0.197], rtol=1e-2, atol=1e-2)
 
 
@@ -59,7 +63,7 @@ def test_combined_nms_vector():
 
 def test_padded_nms_vector():
     # tf.image.non_max_suppression_padded through the TPU branch of GlobalHardNMS: [3, 0, 5], num_valid 3
-    b = (BOXES * S).reshape(1, 6, 4)
+    b = ((BOXES + SHIFT) * S).reshape(1, 6, 4)
     out = _run('GlobalHardNMS', b, SCORES.reshape(1, 6, 1), 5, tpu_semantics=True)
     assert out['valid_detections'].tolist() == [3]
     assert _indices(out['boxes'][0, :3], np.clip(b[0], 0, 1)) == [3, 0, 5]
