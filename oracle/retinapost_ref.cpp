@@ -8,8 +8,9 @@
 // (srihari-humbarwadi/retinanet-tensorflow2.x) holds no tests or golden vectors for this path, and its
 // arithmetic lives in TensorFlow (tf-nightly 2.8.0-dev20210925: NonMaxSuppressionV5, CombinedNonMaxSuppression,
 // TopKV2, Eigen sigmoid/exp), which is neither vendored in /root/reference nor installable here.  The TF kernels
-// are therefore RESTATED from their published algorithm and checked only against
-// hand-derived known-answer tests and torchvision's NMS.  The reference's own Python glue
+// are therefore RESTATED from their published algorithm and checked against hand-derived
+// known-answer tests, torchvision's NMS and the expectations of TensorFlow's own unit tests
+// for these kernels (restated from the upstream test files: tests/test_tf_published_vectors.py) — nothing more.  The reference's own Python glue
 // (mode dispatch, clipping, padding, dtypes, gather/top-k composition) IS pinned: tests/golden/ holds outputs of
 // the unmodified reference modules executed here over a numpy stand-in for the handful of tf.* ops they call
 // (tests/golden/make_golden.py), and this oracle is checked against them.
