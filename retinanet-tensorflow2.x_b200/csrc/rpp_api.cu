@@ -594,8 +594,11 @@ int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const
 }
 
 // Global*: NonMaxSuppressionV5 per image on the row maxima of x [B,n,C].
+// score_rowmax: x holds logits but the row maxima are scored right here (sigmoid is monotone: max score = score of the
+// max logit) and the NMS runs on that dense score column; only the class lookup of the <= M selected rows goes back
+// to the logits.  Used after the global filter, where scoring the whole [B,k,C] gather would be k*C sigmoids per image.
 int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
-                    int B, long n, const Outputs& out, cudaStream_t st) {
+                    int B, long n, const Outputs& out, cudaStream_t st, bool score_rowmax = false) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
   float* mraw = ar.take<float>((size_t)B * n);
@@ -610,7 +613,14 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
       rowmax_kernel<<<(unsigned)grid, 256, 0, st>>>(x, rows, C, mraw);
     }
     LAUNCHED();
+    if (score_rowmax) {
+      sigmoid_kernel<<<(unsigned)std::min<size_t>((rows + 255) / 256, (size_t)h->sm_count * 16), 256, 0, st>>>(mraw, mraw,
+                                                                                                            rows);
+      LAUNCHED();
+    }
   }
+  const int x_is_logit = is_logit;
+  if (score_rowmax) is_logit = 0;   // the problems below see a dense score column
   float iou_thr, sigma_tf;
   nms_v5_args(c, &iou_thr, &sigma_tf);
   ProblemSet ps{};
@@ -635,7 +645,7 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   GlobalOutParams gp{};
   gp.tpu = tpu ? 1 : 0;
   gp.M = M; gp.sel_key = ps.sel_key; gp.sel_box = ps.sel_box; gp.sel_cnt = ps.sel_cnt;
-  gp.x = x; gp.is_logit = is_logit; gp.n = n; gp.C = C;
+  gp.x = x; gp.is_logit = x_is_logit; gp.n = n; gp.C = C;
   gp.deltas = deltas; gp.anchors = h->d_anchors; gp.boxes = boxes; gp.dp = h->dp;
   gp.out_boxes = out.boxes; gp.out_scores = out.scores; gp.out_classes = (long long*)out.classes;
   gp.out_valid = out.valid;
@@ -729,15 +739,21 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   u64* keys = nullptr;
   int rc = topk_keys(h, ar, logits, 1, B, N * C, 1, k, &keys, st);
   if (rc) return rc;
+  const bool rows_as_logits = !per_class && C >= 16;   // narrow rows: scoring k * C values is cheaper than a second pass
   float* row_scores = ar.take<float>((size_t)B * k * C);
   float4* row_boxes = ar.take<float4>((size_t)B * k);
   if (!ar.dry) {
-    const size_t tot = (size_t)B * k * C;
-    size_t grid = std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
+    int tpr = 1;                          // threads per gathered row (as in the kernel; narrow rows: per element)
+    while (tpr < C && tpr < 32) tpr <<= 1;
+    if (C < 16) tpr = C;
+    size_t grid = std::min<size_t>(((size_t)B * k * tpr + 255) / 256, (size_t)h->sm_count * 16);
     fused_global_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, logits, deltas, h->d_anchors, h->dp, B, N, C, k,
-                                                            row_scores, row_boxes);
+                                                            /*apply_sigmoid=*/rows_as_logits ? 0 : 1, row_scores,
+                                                            row_boxes);
     LAUNCHED();
   }
+  if (rows_as_logits)   // Global*, wide rows: the gathered rows stay logits, only their maxima are scored
+    return global_pipeline(h, ar, row_scores, 1, nullptr, row_boxes, B, k, out, st, /*score_rowmax=*/true);
   return nms_dense(h, ar, row_scores, row_boxes, B, k, 1, out, st);
 }
 

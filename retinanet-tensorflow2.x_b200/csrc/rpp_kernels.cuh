@@ -2184,16 +2184,41 @@ __global__ void topk_gather_global_kernel(const u64* __restrict__ emit_key /*[B]
 // scores [B,k,C] = sigmoid(logit rows), boxes [B,k,4] = decoded anchors (TransformBoxesAndScores on k rows only)
 __global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][k]*/, const float* __restrict__ logits,
                                          const float4* __restrict__ deltas, const float4* __restrict__ anchors,
-                                         DecodeParams dp, int B, long N, int C, long k, float* __restrict__ scores_out,
-                                         float4* __restrict__ boxes_out) {
-  const size_t tot = (size_t)B * k * C;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(e % C);
-    const size_t bj = e / C;
+                                         DecodeParams dp, int B, long N, int C, long k, int apply_sigmoid,
+                                         float* __restrict__ scores_out, float4* __restrict__ boxes_out) {
+  if (C < 16) {   // narrow rows: one thread per element
+    const size_t tot = (size_t)B * k * C;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+      const int c = (int)(e % C);
+      const size_t bj = e / C;
+      const int b = (int)(bj / k);
+      const u32 a = key_tie(emit_key[bj]) / (u32)C;
+      const float raw = logits[((size_t)b * N + a) * C + c];
+      scores_out[e] = apply_sigmoid ? sigmoid_f32(raw) : raw;
+      if (c == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
+    }
+    return;
+  }
+  // a group of tpr = min(32, pow2 >= C) threads per selected row: the row index arithmetic (64-bit divisions) is done
+  // once per row, the C values of the row are read and written coalesced
+  const size_t rows = (size_t)B * k;
+  int tpr = 1;
+  while (tpr < C && tpr < 32) tpr <<= 1;
+  const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = (int)(gtid & (size_t)(tpr - 1));
+  const size_t warp = gtid / tpr;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) / tpr;
+  for (size_t bj = warp; bj < rows; bj += nwarps) {
     const int b = (int)(bj / k);
     const u32 a = key_tie(emit_key[bj]) / (u32)C;
-    scores_out[e] = sigmoid_f32(logits[((size_t)b * N + a) * C + c]);
-    if (c == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
+    const float* src = logits + ((size_t)b * N + a) * C;
+    float* dst = scores_out + bj * C;
+    // apply_sigmoid = 0 (Global* modes): the rows stay logits; only the row maxima are scored (global_pipeline)
+    for (int c = lane; c < C; c += tpr) {
+      const float raw = __ldg(src + c);
+      dst[c] = apply_sigmoid ? sigmoid_f32(raw) : raw;
+    }
+    if (lane == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
   }
 }
 
