@@ -10,7 +10,9 @@
  *   - plain C types only; every d_* pointer is DEVICE memory owned by the caller, h_* is HOST memory;
  *   - all device work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream);
  *     no hidden synchronisation, no allocation after rpp_create (rpp_detect_host owns staging set up lazily);
- *   - the handle is immutable after rpp_create: concurrent calls are safe with distinct workspaces;
+ *   - the handle is immutable after rpp_create: concurrent calls are safe with distinct workspaces (exception:
+ *     rpp_detect_host* keep staging buffers in the handle and are NOT re-entrant per handle); a handle belongs to the
+ *     CUDA device that was current at rpp_create, and calls made with another device current return RPP_EINVAL;
  *   - return 0 on success, a negative RPP_E* code otherwise; rpp_last_error() gives the message (thread-local);
  *     no exception crosses the ABI.  The Python shim maps RPP_EMODE -> AssertionError, others -> ValueError /
  *     RuntimeError (the reference raises AssertionError for a bad mode, postprocessing_ops.py:194-197).

@@ -757,6 +757,15 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   return nms_dense(h, ar, row_scores, row_boxes, B, k, 1, out, st);
 }
 
+// The handle's anchor table lives on the device that was current at rpp_create: calls must come from that device.
+int check_device(const Handle* h) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return fail(RPP_ECUDA, "cudaGetDevice failed");
+  if (cur != h->device)
+    return fail(RPP_EINVAL, "handle belongs to CUDA device %d but device %d is current", h->device, cur);
+  return RPP_OK;
+}
+
 template <class F>
 int with_arena(void* ws, size_t ws_bytes, F body) {
   Arena dry{nullptr, 0, true};
@@ -1031,6 +1040,7 @@ int rpp_decode(void* handle, const float* d_logits, const float* d_deltas, int B
   Handle* h = (Handle*)handle;
   g_launches = 0;
   if (!h || B <= 0) return fail(RPP_EINVAL, "bad argument");
+  if (int rc = check_device(h)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int C = h->cfg.num_classes;
   if (d_scores) {
@@ -1060,6 +1070,7 @@ int rpp_topk(void* handle, const float* d_scores, const float* d_boxes, int B, l
   if (!h || !d_scores || !d_boxes || !d_scores_out || !d_boxes_out || B <= 0 || n <= 0)
     return fail(RPP_EINVAL, "bad argument");
   if (h->cfg.pre_nms_top_k <= 0) return fail(RPP_EINVAL, "pre_nms_top_k must be positive for rpp_topk");
+  if (int rc = check_device(h)) return rc;
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     return topk_dense(h, ar, d_scores, (const float4*)d_boxes, B, n, d_scores_out, (float4*)d_boxes_out, d_index_out,
                       (cudaStream_t)stream);
@@ -1071,6 +1082,7 @@ int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, lo
   Handle* h = (Handle*)handle;
   g_launches = 0;
   if (!h || !d_scores || !d_boxes || B <= 0 || n <= 0) return fail(RPP_EINVAL, "bad argument");
+  if (int rc = check_device(h)) return rc;
   const rpp_config& c = h->cfg;
   if (q != 1 && q != c.num_classes) return fail(RPP_EINVAL, "boxes must be [B,n,4] or [B,n,num_classes,4]");
   if (!is_per_class_mode(c.mode) && q != 1)
@@ -1085,6 +1097,7 @@ static int detect_impl(Handle* h, const float* d_deltas, const float* d_logits, 
                        float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes,
                        void* stream) {
   if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
+  if (int rc = check_device(h)) return rc;
   const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     return detect_pipeline(h, ar, (const float4*)d_deltas, d_logits, B, out, (cudaStream_t)stream);
@@ -1121,6 +1134,7 @@ int rpp_efficient_nms(void* handle, const float* d_raw_boxes, const float* d_cla
   if (!h || !d_raw_boxes || !d_class_logits || !d_valid_detections || !d_detection_boxes || !d_detection_scores ||
       !d_detection_classes || B <= 0)
     return fail(RPP_EINVAL, "bad argument");
+  if (int rc = check_device(h)) return rc;
   const int C = h->cfg.num_classes, M = h->cfg.max_detections;
   const long N = h->N;
   if ((double)N * C >= 2147483647.0) return fail(RPP_EINVAL, "anchors x classes out of range");
@@ -1153,6 +1167,7 @@ int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, co
   g_launches = 0;
   if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
   if (dtype != RPP_DT_F32 && dtype != RPP_DT_F16 && dtype != RPP_DT_BF16) return fail(RPP_EINVAL, "bad dtype");
+  if (int rc = check_device(h)) return rc;
   if (n_pieces != 1 && n_pieces != h->levels)
     return fail(RPP_EINVAL, "n_pieces must be 1 (fused tensors) or the number of levels (%d)", h->levels);
   if (n_pieces > RPP_MAX_LEVELS) return fail(RPP_EINVAL, "too many levels");
@@ -1219,6 +1234,8 @@ int rpp_detect_host_typed(void* handle, int device, const void* h_deltas, const 
     return fail(RPP_EINVAL, "bad argument");
   if (dtype != RPP_DT_F32 && dtype != RPP_DT_F16 && dtype != RPP_DT_BF16) return fail(RPP_EINVAL, "bad dtype");
   const size_t esz = dtype == RPP_DT_F32 ? 4 : 2;
+  if (device != h->device)
+    return fail(RPP_EINVAL, "handle belongs to CUDA device %d, not device %d", h->device, device);
   CUDA_OK(cudaSetDevice(device));
   Handle::HostPath& hp = h->hp;
   const int C = h->cfg.num_classes, M = h->cfg.max_detections;

@@ -201,7 +201,8 @@ class TransformBoxesAndScores(Layer):
         self._handles = {}
 
     def _handle(self, num_classes):
-        h = self._handles.get(num_classes)
+        key = (num_classes, torch.cuda.current_device())   # a handle belongs to the device it was created on
+        h = self._handles.get(key)
         if h is None:
             p = self._params
             h = _Handle(H=p.input.input_shape[0], W=p.input.input_shape[1],
@@ -210,10 +211,14 @@ class TransformBoxesAndScores(Layer):
                         num_classes=num_classes, anchor_params=p.anchor_params,
                         box_variance=p.encoder_params.box_variance,
                         scale_box_targets=p.encoder_params.scale_box_targets)
-            self._handles[num_classes] = h
+            self._handles[key] = h
         return h
 
     def call(self, predictions):
+        with torch.cuda.device(predictions['class_logits'].device):
+            return self._call(predictions)
+
+    def _call(self, predictions):
         class_logits = _as_f32(predictions['class_logits'])
         encoded_boxes = _as_f32(predictions['encoded_boxes'])
         B, N, C = class_logits.shape
@@ -240,13 +245,18 @@ class FilterTopKDetections(Layer):
         self._handles = {}
 
     def _handle(self, num_classes):
-        h = self._handles.get(num_classes)
+        key = (num_classes, torch.cuda.current_device())
+        h = self._handles.get(key)
         if h is None:
             h = _Handle(num_classes=num_classes, pre_nms_top_k=self.top_k, filter_per_class=self.filter_per_class)
-            self._handles[num_classes] = h
+            self._handles[key] = h
         return h
 
     def call(self, predictions):
+        with torch.cuda.device(predictions['scores'].device):
+            return self._call(predictions)
+
+    def _call(self, predictions):
         scores = _as_f32(predictions['scores'])
         boxes = _as_f32(predictions['boxes'])
         B, n, C = scores.shape
@@ -315,7 +325,8 @@ class GenerateDetections(Layer):
         self._handles = {}
 
     def _handle(self, num_classes):
-        h = self._handles.get(num_classes)
+        key = (num_classes, torch.cuda.current_device())
+        h = self._handles.get(key)
         if h is None:
             if self.mode in ('GlobalSoftNMS', 'PerClassSoftNMS') and self.soft_nms_sigma is None:
                 # the reference evaluates `None / 2` here (:255, :450)
@@ -326,10 +337,14 @@ class GenerateDetections(Layer):
                         max_detections=self.max_detections,
                         soft_ignores_iou_threshold=self.soft_ignores_iou_threshold,
                         tpu_semantics=self._running_on_tpu)
-            self._handles[num_classes] = h
+            self._handles[key] = h
         return h
 
     def call(self, predictions):
+        with torch.cuda.device(predictions['scores'].device):
+            return self._call(predictions)
+
+    def _call(self, predictions):
         scores = _as_f32(predictions['scores'])
         boxes = _as_f32(predictions['boxes'])
         B, n, C = scores.shape
@@ -370,7 +385,8 @@ class FusedPostProcessing(Layer):
         self._handles = {}
 
     def handle(self, num_classes):
-        h = self._handles.get(num_classes)
+        key = (num_classes, torch.cuda.current_device())
+        h = self._handles.get(key)
         if h is None:
             p = self._params
             inf = p.inference
@@ -387,7 +403,7 @@ class FusedPostProcessing(Layer):
                         soft_nms_sigma=inf.soft_nms_sigma or 0.0, pre_nms_top_k=inf.pre_nms_top_k,
                         filter_per_class=inf.filter_per_class, max_detections=inf.max_detections,
                         tpu_semantics=self.tpu_semantics)
-            self._handles[num_classes] = h
+            self._handles[key] = h
         return h
 
     def capture(self, predictions, warmup=3):
@@ -445,6 +461,14 @@ class FusedPostProcessing(Layer):
         }
 
     def call(self, predictions):
+        first = predictions.class_levels[0] if isinstance(predictions, _LazyFused) else predictions['class_logits']
+        if not first.is_cuda:
+            raise RuntimeError('retinapost layers run on CUDA tensors only (no CPU fallback); got a {} tensor'
+                               .format(first.device))
+        with torch.cuda.device(first.device):
+            return self._call(predictions)
+
+    def _call(self, predictions):
         if isinstance(predictions, _LazyFused):
             if self._native_pieces(predictions.class_levels, predictions.box_levels):
                 return self._call_pieces(predictions.class_levels, predictions.box_levels)
