@@ -34,6 +34,17 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _device_guard(t):
+    """Context manager that makes the tensor's CUDA device current (handles belong to the device they were created
+    on); CPU tensors are rejected here: there is no CPU fallback."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('expected a torch.Tensor, got {}'.format(type(t)))
+    if not t.is_cuda:
+        raise RuntimeError('retinapost layers run on CUDA tensors only (no CPU fallback); got a {} tensor'
+                           .format(t.device))
+    return torch.cuda.device(t.device)
+
+
 def _as_f32(t):
     if not isinstance(t, torch.Tensor):
         raise TypeError('expected a torch.Tensor, got {}'.format(type(t)))
@@ -215,7 +226,7 @@ class TransformBoxesAndScores(Layer):
         return h
 
     def call(self, predictions):
-        with torch.cuda.device(predictions['class_logits'].device):
+        with _device_guard(predictions['class_logits']):
             return self._call(predictions)
 
     def _call(self, predictions):
@@ -253,7 +264,7 @@ class FilterTopKDetections(Layer):
         return h
 
     def call(self, predictions):
-        with torch.cuda.device(predictions['scores'].device):
+        with _device_guard(predictions['scores']):
             return self._call(predictions)
 
     def _call(self, predictions):
@@ -341,7 +352,7 @@ class GenerateDetections(Layer):
         return h
 
     def call(self, predictions):
-        with torch.cuda.device(predictions['scores'].device):
+        with _device_guard(predictions['scores']):
             return self._call(predictions)
 
     def _call(self, predictions):
@@ -462,10 +473,7 @@ class FusedPostProcessing(Layer):
 
     def call(self, predictions):
         first = predictions.class_levels[0] if isinstance(predictions, _LazyFused) else predictions['class_logits']
-        if not first.is_cuda:
-            raise RuntimeError('retinapost layers run on CUDA tensors only (no CPU fallback); got a {} tensor'
-                               .format(first.device))
-        with torch.cuda.device(first.device):
+        with _device_guard(first):
             return self._call(predictions)
 
     def _call(self, predictions):
