@@ -15,7 +15,7 @@ import torch
 
 from retinanet import _native
 from retinanet.dataloader.anchor_generator import AnchorBoxGenerator
-from retinanet.model.layers.postprocessing_ops import _Handle, _as_f32, _stream
+from retinanet.model.layers.postprocessing_ops import _Handle, _as_f32, _device_guard, _stream
 
 
 def nms_plugin_attributes(params):
@@ -51,7 +51,8 @@ class EfficientNMSPlugin:
         self._handles = {}
 
     def _handle(self, num_classes):
-        h = self._handles.get(num_classes)
+        key = (num_classes, torch.cuda.current_device())
+        h = self._handles.get(key)
         if h is None:
             p = self._params
             h = _Handle(H=p.input.input_shape[0], W=p.input.input_shape[1],
@@ -61,13 +62,17 @@ class EfficientNMSPlugin:
                         mode='PerClassHardNMS', iou_threshold=self.attributes['iou_threshold'],
                         score_threshold=self.attributes['score_threshold'],
                         max_detections=self.attributes['max_output_boxes'])
-            self._handles[num_classes] = h
+            self._handles[key] = h
         return h
 
     def __call__(self, raw_boxes, class_logits, anchor_boxes=None):
+        with _device_guard(class_logits):
+            return self._call(raw_boxes, class_logits, anchor_boxes)
+
+    def _call(self, raw_boxes, class_logits, anchor_boxes=None):
         raw_boxes = _as_f32(raw_boxes)
         class_logits = _as_f32(class_logits)
-        anchors = _as_f32(self.anchor_boxes if anchor_boxes is None else anchor_boxes)
+        anchors = _as_f32(self.anchor_boxes if anchor_boxes is None else anchor_boxes).to(class_logits.device)
         B, N, C = class_logits.shape
         h = self._handle(C)
         if N != h.num_anchors or tuple(raw_boxes.shape) != (B, N, 4) or anchors.numel() != N * 4:
