@@ -412,3 +412,32 @@ def test_host_entry_half_precision(dtype):
                                                       os_.data_ptr(), oc.data_ptr(), ov.data_ptr()))
     assert np.array_equal(ob.numpy(), dev['boxes']) and np.array_equal(os_.numpy(), dev['scores'])
     assert np.array_equal(oc.numpy(), dev['classes']) and np.array_equal(ov.numpy(), dev['valid_detections'])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two CUDA devices')
+def test_tensors_on_a_second_device(ref):
+    """Handles belong to a device: layers pick the device of their input tensors (not the current one), and the C
+    entries refuse a handle from another device instead of faulting."""
+    import ctypes
+    from retinanet import _native
+    p = make_params(128, num_classes=8, mode='PerClassHardNMS', pre_nms_top_k=500, max_detections=20)
+    layer = _fused(p)
+    with torch.cuda.device(0):
+        N = layer.handle(8).num_anchors
+    logits, deltas = synth_inputs(2, N, 8, seed=91)
+    exp = oracle_detect(ref, p, logits, deltas)
+    assert torch.cuda.current_device() == 0
+    x1 = {'class_logits': torch.from_numpy(logits).to('cuda:1'), 'encoded_boxes': torch.from_numpy(deltas).to('cuda:1')}
+    out = layer(x1)
+    assert out['boxes'].device == torch.device('cuda', 1)
+    assert image_mismatches(to_numpy(out), exp) == []
+    assert torch.cuda.current_device() == 0
+    # a device-0 handle called while device 1 is current is rejected with a message
+    h0 = layer.handle(8)
+    ws = torch.empty(int(_native.lib().rpp_workspace_bytes(h0.ptr, 2, 0)), dtype=torch.uint8, device='cuda:1')
+    o = h0.outputs(2, 'cuda:1')
+    with torch.cuda.device(1):
+        rc = _native.lib().rpp_detect(h0.ptr, x1['encoded_boxes'].data_ptr(), x1['class_logits'].data_ptr(), 2,
+                                      o['boxes'].data_ptr(), o['scores'].data_ptr(), o['classes'].data_ptr(),
+                                      o['valid_detections'].data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == _native.RPP_EINVAL and 'device' in _native.last_error()
