@@ -260,7 +260,10 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     // narrow problem sets (C = 1: 48 active threads per block) need more blocks in flight to cover the load latency
     const int max_split = threads <= 64 ? 64 : 16;
     const int split = plan.rows_per_group < max_split ? plan.rows_per_group : max_split;
-    if (lv.L > 1 && lv.dtype != RPP_DT_F32)
+    if (emit_fine && C == 1 && lv.L == 1 && lv.dtype == RPP_DT_F32 && n % 4 == 0 && aligned && plan.rows_per_group >= 8)
+      sample_max_flat4_kernel<<<dim3(B, std::min(plan.rows_per_group / 4, max_split)), threads, 0, st>>>(
+          (const float4*)lv.x[0], n / 4, plan.stride, plan.lanes, plan.rows_per_group / 4, gm);
+    else if (lv.L > 1 && lv.dtype != RPP_DT_F32)
       sample_max_kernel<true, true><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
                                                                         plan.rows_per_group, gm);
     else if (lv.L > 1)

@@ -204,6 +204,31 @@ sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stride, int lanes,
     atomicMax(&gm[((size_t)b * G + rl + i * lanes) * C + c], ord_f32(m[i]));
 }
 
+// Single-column variant (C == 1: the flat anchors x classes axis of the global filter and of the EfficientNMS entry,
+// n % 4 == 0): every sample is one 16-byte load = four consecutive elements, so the same number of sampled elements
+// touches a quarter of the sectors (a strided sample of single floats fetches 32 bytes for every 4 it uses).
+__global__ void __launch_bounds__(1024, 2)
+sample_max_flat4_kernel(const float4* __restrict__ x4 /*[B][n4]*/, long n4, int stride4, int lanes, int rounds4,
+                        u32* __restrict__ gm /*[B][G]*/) {
+  const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
+  const int rl = threadIdx.x;
+  if (rl >= lanes) return;
+  const int G = lanes * RPP_GPT;
+  float m[RPP_GPT];
+#pragma unroll
+  for (int i = 0; i < RPP_GPT; ++i) m[i] = -INFINITY;
+  const float4* base = x4 + (size_t)b * n4;
+  for (int r = split; r < rounds4; r += nsplit) {
+    float4 v[RPP_GPT];
+#pragma unroll
+    for (int i = 0; i < RPP_GPT; ++i) v[i] = __ldg(base + (size_t)((long)r * G + rl + i * lanes) * stride4);
+#pragma unroll
+    for (int i = 0; i < RPP_GPT; ++i) m[i] = fmaxf(m[i], fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+  }
+#pragma unroll
+  for (int i = 0; i < RPP_GPT; ++i) atomicMax(&gm[(size_t)b * G + rl + i * lanes], ord_f32(m[i]));
+}
+
 #define RPP_RANK_CPB 8   // classes per block
 __global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int rank, float T_min,
                                    float* __restrict__ T) {
