@@ -16,6 +16,8 @@
  *   - return 0 on success, a negative RPP_E* code otherwise; rpp_last_error() gives the message (thread-local);
  *     no exception crosses the ABI.  The Python shim maps RPP_EMODE -> AssertionError, others -> ValueError /
  *     RuntimeError (the reference raises AssertionError for a bad mode, postprocessing_ops.py:194-197).
+ *   - inputs are expected to be finite or +-inf; NaN scores are outside the contract (as in TensorFlow, whose
+ *     ordering of NaN scores is unspecified): a NaN never becomes a candidate;
  *   - there is NO CPU fallback: without a CUDA device every compute entry returns RPP_ECUDA.
  */
 #ifndef RETINAPOST_H_
