@@ -66,6 +66,7 @@ struct Handle {
   cudaStream_t side;
   cudaEvent_t ev_chunk[8];
   cudaEvent_t ev_join;
+  long tile_rows;        // tuning knob (env RPP_TILE_ROWS): anchors per collect tile, 0 = automatic
   int emit_short;        // test knob (env RPP_EMIT_SHORT): aim the top-k lists at k/2 so that every problem falls back
   int half_variant;      // tuning knob (env RPP_HALF_VARIANT): 16-bit collect, 0 = unroll 4 / 3 CTAs per SM, 1 = 8 / 2
   int collect_variant;   // tuning knob (env RPP_COLLECT_VARIANT): 0 = unroll 4 / 3 CTAs per SM, 1 = 4/2, 2 = 8/2
@@ -332,7 +333,8 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       long rows_per_tile = plan.on ? (long)(24.0 * n / target) : 4L * lanes * UNROLL;
       rows_per_tile = (rows_per_tile + (long)lanes * UNROLL - 1) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL);
       if (rows_per_tile < (long)lanes * UNROLL) rows_per_tile = (long)lanes * UNROLL;
-      if (const char* v = getenv("RPP_TILE_ROWS")) rows_per_tile = std::max<long>((long)lanes * UNROLL, atol(v) / ((long)lanes * UNROLL) * ((long)lanes * UNROLL));
+      if (h->tile_rows > 0)
+        rows_per_tile = std::max<long>((long)lanes * UNROLL, h->tile_rows / ((long)lanes * UNROLL) * ((long)lanes * UNROLL));
       {   // small batches: shrink the tiles until every resident CTA gets ~4 of them (dynamic scheduling then
           // balances the tail to within a quarter of a CTA's share)
         const long want_tiles = 4L * h->sm_count * MINB;
@@ -849,6 +851,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
+    v = getenv("RPP_TILE_ROWS");
+    h->tile_rows = v ? atol(v) : 0;
     v = getenv("RPP_EMIT_SHORT");
     h->emit_short = v ? atoi(v) : 0;
     v = getenv("RPP_HALF_VARIANT");
