@@ -441,3 +441,27 @@ def test_tensors_on_a_second_device(ref):
                                       o['boxes'].data_ptr(), o['scores'].data_ptr(), o['classes'].data_ptr(),
                                       o['valid_detections'].data_ptr(), ws.data_ptr(), ws.numel(), None)
     assert rc == _native.RPP_EINVAL and 'device' in _native.last_error()
+
+
+@pytest.mark.parametrize('mode,fpc', [('PerClassHardNMS', True), ('GlobalSoftNMS', False), ('CombinedNMS', True)])
+def test_sharded_batches_equal_the_whole_batch(mode, fpc):
+    """SURVEY.md §8e at BASELINE geometry (640 x 640, 80 classes): the path shards by image with no exchange, so the
+    detections of a batch are the concatenation of the detections of its shards (ragged shards included) — the
+    size-independent property behind the multi-GPU numbers.  Also: permuting the images permutes the outputs."""
+    from retinanet.distributed import shard_batch
+    p = make_params(640, num_classes=80, mode=mode, pre_nms_top_k=5000, filter_per_class=fpc, soft_nms_sigma=0.5)
+    layer = _fused(p)
+    N = layer.handle(80).num_anchors
+    B = 7
+    g = torch.Generator(device='cuda')
+    g.manual_seed(5)
+    x = {'class_logits': torch.randn((B, N, 80), generator=g, device='cuda'),
+         'encoded_boxes': (torch.randn((B, N, 4), generator=g, device='cuda') * 0.5).clamp_(-4, 4)}
+    whole = to_numpy(layer(x))
+    parts = [to_numpy(layer(shard_batch(x, r, 3))) for r in range(3)]
+    for key in whole:
+        assert np.array_equal(whole[key], np.concatenate([q[key] for q in parts], 0)), key
+    perm = torch.tensor([3, 0, 6, 1, 5, 2, 4], device='cuda')
+    shuffled = to_numpy(layer({k: v[perm].contiguous() for k, v in x.items()}))
+    for key in whole:
+        assert np.array_equal(whole[key][perm.cpu().numpy()], shuffled[key]), key
