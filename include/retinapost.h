@@ -193,6 +193,12 @@ int rpp_classes_itemsize(void* handle);
  * selection (1), or restore the default sampled pre-threshold (0). */
 int rpp_debug_force_exact_scan(void* handle, int on);
 
+/* Test hook (no device needed): the sampling plan the library would use for columns of n rows and C classes —
+ * NMS problems (emit = 0, k_lim ignored) or top-k emission of k_lim rows (emit = 1).  h_out[8] = {sampled?, stride,
+ * groups G, sampled rows per group, rank of the group maximum used as threshold, list capacity, targeted list
+ * length, fine (4x groups) plan?}.  tests/test_host_cpu.py checks the plan's margins by Monte Carlo. */
+int rpp_debug_sample_plan(long n, int C, long k_lim, int emit, int* h_out);
+
 /* Per-stage device timing for bench.py's roofline: when on, every rpp_detect / rpp_nms call records CUDA events on
  * the caller's stream at the stage boundaries.  rpp_debug_stage_ms synchronises on the last event and returns the
  * mean milliseconds of the 4 stages {pre-threshold sample, collect stream, NMS problems, merge} over the calls

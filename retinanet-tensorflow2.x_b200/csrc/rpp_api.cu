@@ -147,6 +147,23 @@ SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
 
 const int kTarget = 768;
 
+// The plan of one problem set: NMS problems aim at `nms_target` candidates per column; top-k emission (k_lim rows must
+// come out of the list) aims well above k_lim — see the comment in run_problem_set.  Pure host arithmetic (exported
+// for the CPU tests as rpp_debug_sample_plan).
+SamplePlan choose_plan(long n, int C, bool emit, long k_lim, int nms_target, int emit_short, bool* emit_fine_out,
+                       int* target_out) {
+  const int emit_lanes = std::min(1024 / std::max(1, C), 48);
+  const bool emit_fine = emit && emit_lanes * RPP_GPT >= 256 && n >= (1L << 19);   // short columns: the scan is cheap
+  const int target = emit ? (int)std::min<long>(emit_fine ? 2 * k_lim + 256 : k_lim + k_lim / 2 + 512, 1 << 28)
+                          : nms_target;
+  SamplePlan plan = make_plan(n, C, emit_short && emit ? (int)std::max<long>(64, k_lim / 2) : target,
+                              emit_fine ? emit_lanes : 12);
+  if (plan.on && emit) plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target;
+  if (emit_fine_out) *emit_fine_out = emit_fine;
+  if (target_out) *target_out = target;
+  return plan;
+}
+
 // Bump allocator over the caller's workspace.  Every pipeline below is written once and run twice: a dry pass
 // (no launches) sizes the workspace — rpp_workspace_bytes and the capacity check share it — then the real pass.
 struct Arena {
@@ -198,13 +215,9 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   // tens of milliseconds on a 6 M element column): the estimate's 1-sigma error is ~17 % with 96 group maxima, so
   // narrow problem sets (few classes: the global filter, C = 1) sample 4x as many groups (1-sigma ~8 %) and aim at
   // 2 k candidates — both tails (fewer than k, more than the list capacity) are then > 5 sigma away
-  const int emit_lanes = std::min(1024 / std::max(1, C), 48);
-  const bool emit_fine = emit && emit_lanes * RPP_GPT >= 256 && n >= (1L << 19);   // short columns: the scan is cheap
-  const int target = emit ? (int)std::min<long>(emit_fine ? 2 * ps.k_lim + 256 : ps.k_lim + ps.k_lim / 2 + 512, 1 << 28)
-                          : h->target;
-  SamplePlan plan = make_plan(n, C, h->emit_short && emit ? (int)std::max<long>(64, ps.k_lim / 2) : target,
-                              emit_fine ? emit_lanes : 12);
-  if (plan.on && emit) plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target;
+  bool emit_fine = false;
+  int target = 0;
+  SamplePlan plan = choose_plan(n, C, emit, ps.k_lim, h->target, h->emit_short, &emit_fine, &target);
   const size_t gm_elems = plan.on ? (size_t)B * plan.G * C : 0;
 
   float* T = ar.take<float>(P);
@@ -970,6 +983,16 @@ int rpp_classes_itemsize(void* handle) {
 int rpp_debug_force_exact_scan(void* handle, int on) {
   if (!handle) return fail(RPP_EINVAL, "null handle");
   ((Handle*)handle)->force_scan = on ? 1 : 0;
+  return RPP_OK;
+}
+
+int rpp_debug_sample_plan(long n, int C, long k_lim, int emit, int* h_out) {
+  if (!h_out || n <= 0 || C <= 0) return fail(RPP_EINVAL, "bad argument");
+  bool fine = false;
+  int target = 0;
+  const SamplePlan p = choose_plan(n, C, emit != 0, k_lim, kTarget, 0, &fine, &target);
+  h_out[0] = p.on ? 1 : 0; h_out[1] = p.stride; h_out[2] = p.G; h_out[3] = p.rows_per_group; h_out[4] = p.rank;
+  h_out[5] = p.CAP; h_out[6] = target; h_out[7] = fine ? 1 : 0;
   return RPP_OK;
 }
 

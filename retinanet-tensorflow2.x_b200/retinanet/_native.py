@@ -18,7 +18,7 @@ EXPORTS = [
     'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_nms', 'rpp_detect', 'rpp_detect_levels', 'rpp_detect_typed',
     'rpp_detect_host', 'rpp_detect_host_typed', 'rpp_coco_format', 'rpp_efficient_nms',
     'rpp_last_launch_count', 'rpp_classes_itemsize', 'rpp_debug_force_exact_scan', 'rpp_debug_stage_timing',
-    'rpp_debug_stage_ms',
+    'rpp_debug_stage_ms', 'rpp_debug_sample_plan',
 ]
 
 
@@ -84,6 +84,7 @@ def lib():
         L.rpp_efficient_nms.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.rpp_classes_itemsize.argtypes = [vp]
         L.rpp_debug_force_exact_scan.argtypes = [vp, ci]
+        L.rpp_debug_sample_plan.argtypes = [cl, ci, cl, ci, ctypes.POINTER(ci)]
         L.rpp_debug_stage_timing.argtypes = [vp, ci]
         L.rpp_debug_stage_ms.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ci)]
         _lib = L

@@ -3,6 +3,8 @@ without a GPU), host-side config / builder logic, and image sharding over a worl
 import ctypes
 import json
 import os
+
+import numpy as np
 import re
 import subprocess
 import sys
@@ -185,6 +187,49 @@ def test_config_struct_layout_matches_the_header(tmp_path):
     out = [int(v) for v in subprocess.check_output([exe], text=True).split()]
     assert out[0] == ctypes.sizeof(_native.RppConfig)
     assert out[1:] == [getattr(_native.RppConfig, f).offset for f in fields]
+
+
+def _simulate_list_lengths(plan, n, trials, rng):
+    """List length (= elements >= the sampled threshold) over `trials` synthetic N(0,1) columns, mirroring
+    sample_max_kernel / sample_rank_*: group g holds rows (r * G + g) * stride, r < rows_per_group; the threshold is
+    the rank-th smallest group maximum."""
+    on, stride, G, rows, rank, cap, target, fine = plan
+    idx = ((np.arange(rows)[:, None] * G + np.arange(G)[None, :]) * stride).ravel()
+    assert idx.max() < n
+    counts = []
+    for _ in range(trials):
+        x = rng.standard_normal(n).astype(np.float32)
+        gm = x[idx].reshape(rows, G).max(0)
+        counts.append(int((x >= np.sort(gm)[rank]).sum()))
+    return np.array(counts)
+
+
+def test_sampling_plan_margins():
+    """The sampled pre-threshold only steers speed, but a top-k list that comes up short of k (or overflows) costs a
+    fallback: the plans of the BASELINE geometries must keep both tails far away."""
+    from retinanet import _native
+    rng = np.random.default_rng(0)
+    out = (ctypes.c_int * 8)()
+
+    def plan(n, C, k, emit):
+        _native.check(_native.lib().rpp_debug_sample_plan(n, C, k, emit, out))
+        return list(out)
+
+    # NMS problems of configs[1]: columns of 76 725 logits, lists of ~768 candidates, capacity 4096
+    p = plan(76725, 80, 0, 0)
+    assert p[0] == 1 and p[5] == 4096 and p[6] == 768
+    c = _simulate_list_lengths(p, 76725, 400, rng)
+    assert 600 < c.mean() < 950 and c.max() < 4096 and c.min() > 250
+    # flat top-k of the global filter (C3) and of the EfficientNMS entry: 6.1 M elements per image, fine plan
+    for k in (5000, 4096):
+        p = plan(76725 * 80, 1, k, 1)
+        assert p[0] == 1 and p[7] == 1 and p[2] >= 256
+        c = _simulate_list_lengths(p, 76725 * 80, 24, rng)
+        sigma = c.std()
+        assert c.min() >= k and c.max() <= min(p[5], 16384)
+        assert (c.mean() - k) / sigma > 4.5 and (min(p[5], 16384) - c.mean()) / sigma > 4.5, (k, c.mean(), sigma)
+    # short columns keep the cheap plan (their fallback is a scan of < 100 K elements)
+    assert plan(19206 * 5, 1, 5000, 1)[7] == 0
 
 
 def _build_abi_smoke(tmp_path):
