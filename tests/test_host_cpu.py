@@ -232,6 +232,48 @@ def test_sampling_plan_margins():
     assert plan(19206 * 5, 1, 5000, 1)[7] == 0
 
 
+def test_kernel_resource_budgets():
+    """Build-time guard of the occupancy the design relies on, read from the cubin with cuobjdump
+    (no GPU needed): the collect kernels must fit 3 x 512 threads per SM (<= 42 registers, no spills) and stream with
+    128-bit loads; the sample kernels 2 x 1024 threads (<= 32 registers); the warp probe <= 64 registers."""
+    import shutil
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    lib = os.path.join(PKG, 'libretinapost.so')
+    txt = subprocess.check_output([cuobjdump, '-res-usage', lib], text=True, stderr=subprocess.STDOUT)
+    usage = {}
+    name = None
+    for line in txt.splitlines():
+        m = re.search(r'Function (\S+):', line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r'REG:(\d+) STACK:(\d+)', line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+            name = None
+
+    def find(prefix):
+        hits = {k: v for k, v in usage.items() if prefix in k}
+        assert hits, prefix
+        return hits
+
+    for k, (reg, stack) in find('collect_cols4_kernelILi4ELi3E').items():
+        assert reg <= 42 and stack == 0, (k, reg, stack)
+    for k, (reg, stack) in find('collect_cols4_levels_kernelILi4ELi3E').items():
+        assert reg <= 42 and stack == 0, (k, reg, stack)
+    for k, (reg, stack) in find('collect_cols8_half_kernelILi8E').items():
+        assert reg <= 64 and stack == 0, (k, reg, stack)          # 2 CTAs of 512 threads per SM
+    for k, (reg, stack) in find('sample_max').items():
+        assert reg <= 32, (k, reg)                                 # 2 blocks of up to 1024 threads per SM
+    for k, (reg, stack) in find('probe_warp_kernel').items():
+        assert reg <= 64 and stack == 0, (k, reg, stack)
+    fused = [k for k in usage if 'collect_cols4_kernelILi4ELi3E' in k][0]
+    sass = subprocess.check_output([cuobjdump, '-sass', '-fun', fused, lib], text=True, stderr=subprocess.STDOUT)
+    assert sass.count('LDG.E.128') >= 4, 'the collect kernel must keep four 128-bit streaming loads in flight'
+
+
 def _build_abi_smoke(tmp_path):
     exe = str(tmp_path / 'abi_smoke')
     cmd = ['gcc', os.path.join(ROOT, 'tests', 'abi_smoke.c'), '-I' + os.path.join(ROOT, 'include'),
