@@ -70,7 +70,8 @@ typedef struct rpp_config {
                                      hard NMS, tf.image.non_max_suppression_padded arithmetic, int32 classes, -1
                                      padding in every field); the reference selects them by detecting a TPUStrategy
                                      (:199-208), which has no counterpart here.  0 (default) = the non-TPU branches.
-                                     Ignored by the other modes, as in the reference. */
+                                     With any other mode rpp_create returns RPP_EMODE, as the reference's constructor
+                                     raises AssertionError under a TPUStrategy (:202-206). */
   int reserved[6];                /* must be zero */
 } rpp_config;
 

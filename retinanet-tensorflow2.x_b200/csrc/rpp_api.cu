@@ -178,7 +178,8 @@ struct Arena {
 };
 
 // rpp_config.tpu_semantics: the TPUStrategy branches of GenerateDetections replace the two hard modes
-// (postprocessing_ops.py:549-550, :558-559); the other modes are not affected by it.
+// (postprocessing_ops.py:549-550, :558-559); rpp_create rejects the flag with any other mode, as the reference's
+// constructor does under a TPUStrategy (:202-206).
 bool tpu_branch(const rpp_config& c) {
   return c.tpu_semantics && (c.mode == RPP_GLOBAL_HARD_NMS || c.mode == RPP_PER_CLASS_HARD_NMS);
 }
@@ -827,6 +828,9 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   if ((cfg->mode == RPP_GLOBAL_SOFT_NMS || cfg->mode == RPP_PER_CLASS_SOFT_NMS) && !(cfg->soft_nms_sigma == cfg->soft_nms_sigma))
     return fail(RPP_EINVAL, "soft_nms_sigma is required for the soft NMS modes");
   if (cfg->tpu_semantics != 0 && cfg->tpu_semantics != 1) return fail(RPP_EINVAL, "tpu_semantics must be 0 or 1");
+  if (cfg->tpu_semantics && cfg->mode != RPP_GLOBAL_HARD_NMS && cfg->mode != RPP_PER_CLASS_HARD_NMS)
+    return fail(RPP_EMODE, "Requested mode not supported on Cloud TPUs. Please use `GlobalHardNMS` or "
+                           "`PerClassHardNMS`");   // postprocessing_ops.py:202-206
   for (int i = 0; i < 6; ++i)
     if (cfg->reserved[i] != 0) return fail(RPP_EINVAL, "rpp_config.reserved must be zero");
   if (tpu_branch(*cfg) && !(cfg->iou_threshold > 0.0f))

@@ -315,7 +315,8 @@ class GenerateDetections(Layer):
         # threshold is ignored when soft_nms_sigma > 0; False = the older kernel form.
         # tpu_semantics (not in the reference, which detects a TPUStrategy instead, :199-208): True = GlobalHardNMS /
         # PerClassHardNMS run _tpu_global_hard_nms (:381-432) / _tpu_per_class_hard_nms (:288-379): a real global hard
-        # NMS, tf.image.non_max_suppression_padded arithmetic, int32 classes, -1 in every padded field.
+        # NMS, tf.image.non_max_suppression_padded arithmetic, int32 classes, -1 in every padded field.  As in the
+        # reference under a TPUStrategy, any other mode is rejected (:202-206).
 
         if mode not in GenerateDetections._SUPPORTED_NMS_MODES:
             raise AssertionError(
@@ -323,6 +324,12 @@ class GenerateDetections(Layer):
                 .format(mode, GenerateDetections._SUPPORTED_NMS_MODES))
 
         self._running_on_tpu = bool(tpu_semantics)
+
+        if self._running_on_tpu:
+            if mode != 'GlobalHardNMS' and mode != 'PerClassHardNMS':
+                raise AssertionError(
+                    'Requested mode not supported on Cloud TPUs.'
+                    ' Please use `GlobalHardNMS` or `PerClassHardNMS`')
 
         super(GenerateDetections, self).__init__(**kwargs)
 
@@ -393,6 +400,9 @@ class FusedPostProcessing(Layer):
         self.mode = inf.mode
         # optional key `inference.tpu_semantics` (absent from the reference's JSONs -> False)
         self.tpu_semantics = bool(inf.get('tpu_semantics', False)) if hasattr(inf, 'get') else False
+        if self.tpu_semantics and inf.mode not in ('GlobalHardNMS', 'PerClassHardNMS'):
+            raise AssertionError('Requested mode not supported on Cloud TPUs.'
+                                 ' Please use `GlobalHardNMS` or `PerClassHardNMS`')   # :202-206
         self._handles = {}
 
     def handle(self, num_classes):

@@ -86,16 +86,18 @@ def test_known_answers_through_the_layer(ref):
     assert out['valid_detections'].tolist() == [1]
 
 
-def test_other_modes_ignore_the_flag_and_bad_threshold_is_rejected():
+def test_tpu_flag_rejects_other_modes_and_a_non_positive_threshold():
     from retinanet.model.layers import GenerateDetections
+    from retinanet.model.layers.postprocessing_ops import _Handle
     rng = np.random.default_rng(3)
     s = _gpu(rng.uniform(0, 1, (2, 50, 3)).astype(np.float32))
     c = rng.uniform(0.1, 0.9, (2, 50, 2)).astype(np.float32)
     b = _gpu(np.concatenate([c - 0.1, c + 0.1], -1).astype(np.float32))
     for mode in ['CombinedNMS', 'GlobalSoftNMS', 'PerClassSoftNMS']:
-        a = to_numpy(GenerateDetections(0.5, 0.05, 10, 0.5, 3, mode, tpu_semantics=True)({'scores': s, 'boxes': b}))
-        e = to_numpy(GenerateDetections(0.5, 0.05, 10, 0.5, 3, mode)({'scores': s, 'boxes': b}))
-        assert all(np.array_equal(a[k], e[k]) and a[k].dtype == e[k].dtype for k in a)
+        with pytest.raises(AssertionError):        # the reference's constructor under a TPUStrategy (:202-206)
+            GenerateDetections(0.5, 0.05, 10, 0.5, 3, mode, tpu_semantics=True)
+        with pytest.raises(AssertionError):        # and the C ABI (RPP_EMODE)
+            _Handle(num_classes=3, mode=mode, soft_nms_sigma=0.5, tpu_semantics=True)
     with pytest.raises(ValueError):
         GenerateDetections(0.0, 0.05, 10, None, 3, 'GlobalHardNMS', tpu_semantics=True)({'scores': s, 'boxes': b})
 

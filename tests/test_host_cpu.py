@@ -1,5 +1,6 @@
 """CPU-side checks: the C-ABI library loads and exports every symbol include/retinapost.h declares (no compute
 without a GPU), host-side config / builder logic, and image sharding over a world_size-2 gloo group."""
+import copy
 import ctypes
 import json
 import os
@@ -38,6 +39,42 @@ def test_no_cpu_fallback_without_gpu():
     layer = GenerateDetections(mode='PerClassHardNMS', num_classes=2)
     with pytest.raises(RuntimeError):
         layer({'scores': torch.zeros(1, 4, 2), 'boxes': torch.zeros(1, 4, 4)})
+
+
+def test_tpu_flag_is_validated_like_the_reference_constructor():
+    """postprocessing_ops.py:199-208: under a TPUStrategy only GlobalHardNMS / PerClassHardNMS are accepted.  The
+    Python layers raise the reference's AssertionError at construction; rpp_create returns RPP_EMODE (validation runs
+    before any CUDA call, so this is checkable without a GPU)."""
+    from retinanet import _native
+    from retinanet.cfg.config import AttrDict
+    from retinanet.model.layers import FusedPostProcessing, GenerateDetections
+    for mode in ['CombinedNMS', 'GlobalSoftNMS', 'PerClassSoftNMS']:
+        with pytest.raises(AssertionError, match='not supported on Cloud TPUs'):
+            GenerateDetections(mode=mode, soft_nms_sigma=0.5, tpu_semantics=True)
+        params = AttrDict(copy.deepcopy(REFERENCE_CONFIG))
+        params.inference.mode = mode
+        params.inference.tpu_semantics = True
+        with pytest.raises(AssertionError, match='not supported on Cloud TPUs'):
+            FusedPostProcessing(params)
+    for mode in ['GlobalHardNMS', 'PerClassHardNMS']:
+        assert GenerateDetections(mode=mode, tpu_semantics=True)._running_on_tpu
+    areas = (ctypes.c_double * 5)(1024.0, 4096.0, 16384.0, 65536.0, 262144.0)
+    one = (ctypes.c_double * 1)(1.0)
+    cfg = _native.RppConfig()
+    cfg.H = cfg.W = 64
+    cfg.min_level, cfg.max_level, cfg.num_classes = 3, 7, 4
+    cfg.n_areas, cfg.areas = 5, areas
+    cfg.n_ratios, cfg.aspect_ratios = 1, one
+    cfg.n_scales, cfg.scales = 1, one
+    cfg.iou_threshold, cfg.score_threshold, cfg.soft_nms_sigma, cfg.max_detections = 0.5, 0.05, 0.5, 10
+    cfg.tpu_semantics = 1
+    h = ctypes.c_void_p()
+    for mode in (0, 1, 3):
+        cfg.mode = mode
+        assert _native.lib().rpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _native.RPP_EMODE
+        assert 'Cloud TPUs' in _native.last_error()
+    cfg.mode, cfg.iou_threshold = 2, 0.0
+    assert _native.lib().rpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _native.RPP_EINVAL
 
 
 def test_product_never_imports_oracle():
