@@ -714,6 +714,7 @@ int topk_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, i
     LAUNCHED();
     return RPP_OK;
   }
+  if ((double)n * C >= 2147483647.0) return fail(RPP_EINVAL, "rows x classes must stay below 2^31 for the global filter");
   const long k = std::min<long>(c.pre_nms_top_k, n * C);
   int rc = topk_keys(h, ar, scores, 0, B, n * C, 1, k, &keys, st);
   if (rc || ar.dry) return rc;
@@ -754,6 +755,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   }
   // global filter (:149-161): top-k over the flat (anchor, class) axis on raw logits, then the k selected rows are
   // transformed (sigmoid of the whole row, decoded box) and fed to GenerateDetections as in the reference.
+  if ((double)N * C >= 2147483647.0) return fail(RPP_EINVAL, "anchors x classes must stay below 2^31 for the global filter");
   const long k = std::min<long>(c.pre_nms_top_k, N * C);
   u64* keys = nullptr;
   int rc = topk_keys(h, ar, logits, 1, B, N * C, 1, k, &keys, st);
@@ -1101,7 +1103,7 @@ int rpp_topk(void* handle, const float* d_scores, const float* d_boxes, int B, l
              float* d_boxes_out, int* d_index_out, void* ws, size_t ws_bytes, void* stream) {
   Handle* h = (Handle*)handle;
   g_launches = 0;
-  if (!h || !d_scores || !d_boxes || !d_scores_out || !d_boxes_out || B <= 0 || n <= 0)
+  if (!h || !d_scores || !d_boxes || !d_scores_out || !d_boxes_out || B <= 0 || n <= 0 || n >= 0x7fffffffL)
     return fail(RPP_EINVAL, "bad argument");
   if (h->cfg.pre_nms_top_k <= 0) return fail(RPP_EINVAL, "pre_nms_top_k must be positive for rpp_topk");
   if (int rc = check_device(h)) return rc;
@@ -1115,7 +1117,7 @@ int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, lo
             float* d_scores_out, void* d_classes_out, int* d_valid_out, void* ws, size_t ws_bytes, void* stream) {
   Handle* h = (Handle*)handle;
   g_launches = 0;
-  if (!h || !d_scores || !d_boxes || B <= 0 || n <= 0) return fail(RPP_EINVAL, "bad argument");
+  if (!h || !d_scores || !d_boxes || B <= 0 || n <= 0 || n >= 0x7fffffffL) return fail(RPP_EINVAL, "bad argument");
   if (int rc = check_device(h)) return rc;
   const rpp_config& c = h->cfg;
   if (q != 1 && q != c.num_classes) return fail(RPP_EINVAL, "boxes must be [B,n,4] or [B,n,num_classes,4]");
