@@ -102,7 +102,8 @@ __global__ void logit_threshold_kernel(float score_threshold, float* out) {
 // ===============================================================================================================
 // K0c  TransformBoxesAndScores.call materialised (postprocessing_ops.py:107-117) — stage-wise entry rpp_decode.
 // ===============================================================================================================
-__global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+// (no __restrict__: global_pipeline scores the row maxima in place, y == x)
+__global__ void sigmoid_kernel(const float* x, float* y, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     y[i] = sigmoid_f32(x[i]);
 }
