@@ -311,6 +311,20 @@ def test_kernel_resource_budgets():
     assert sass.count('LDG.E.128') >= 4, 'the collect kernel must keep four 128-bit streaming loads in flight'
 
 
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle timed on the host cores) needs no GPU and prints the contract's JSON
+    line: impl, metric / unit of the own arm, cpu_baseline describing the run, a zero-copy e2e."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'images/s' and line['higher_is_better'] is True
+    assert line['value'] > 0 and line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    assert line['e2e']['value'] == line['value'] and 'workload' in line['config']
+
+
 def _build_abi_smoke(tmp_path):
     exe = str(tmp_path / 'abi_smoke')
     cmd = ['gcc', os.path.join(ROOT, 'tests', 'abi_smoke.c'), '-I' + os.path.join(ROOT, 'include'),
