@@ -206,6 +206,9 @@ int rpp_debug_sample_plan(long n, int C, long k_lim, int emit, int* h_out);
  * recorded since the last read. */
 int rpp_debug_stage_timing(void* handle, int on);
 int rpp_debug_stage_ms(void* handle, float* h_ms4, int* n_calls);
+/* The same recording by named segment: writes "label=ms;label=ms;..." (mean milliseconds per call, labels in launch
+ * order, e.g. "sample", "collect", "nms", "merge", "emit:collect", "rows") into buf and resets the recording. */
+int rpp_debug_stage_report(void* handle, char* buf, int cap, int* n_calls);
 
 #ifdef __cplusplus
 }

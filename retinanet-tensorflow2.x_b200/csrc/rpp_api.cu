@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/retinapost.h"
@@ -42,6 +43,7 @@ int fail(int code, const char* fmt, ...) {
 struct SamplePlan {
   bool on;
   int stride, G, lanes, rows_per_group, rank;
+  int rank_lo;   // complete-list rule of the rank kernels (-1: off)
   int CAP;
 };
 
@@ -73,7 +75,9 @@ struct Handle {
   DecodeParams dp;
   // optional per-stage timing (bench.py roofline): 5 events per call = boundaries of sample|collect|nms|merge
   int timing;
-  std::vector<cudaEvent_t> events;
+  std::vector<cudaEvent_t> events;       // pool, ev_used of them recorded since timing was switched on
+  std::vector<const char*> ev_label;     // label of the segment that ENDS at the event (nullptr: a chain starts)
+  size_t ev_used;
   int timed_calls;
   // rpp_detect_host staging (allocated on first use)
   struct HostPath {
@@ -89,18 +93,21 @@ struct Handle {
 };
 
 const int kStages = 4;
-const int kMaxTimedCalls = 512;
+const size_t kMaxTimedEvents = 1 << 16;
 
-inline void stage_mark(Handle* h, int boundary, cudaStream_t st) {
-  if (!h->timing || h->timed_calls >= kMaxTimedCalls) return;
-  const size_t idx = (size_t)h->timed_calls * (kStages + 1) + boundary;
-  while (h->events.size() <= idx) {
+// Per-stage timing (rpp_debug_stage_timing): every pipeline drops named marks on its stream; a mark closes the segment
+// that started at the previous mark of the same call chain (label nullptr opens a chain).  Labels are static strings
+// "bucket:kernel(s)" with bucket in {sample, collect, nms, merge, emit, rows}.
+inline void stage_mark(Handle* h, const char* label, cudaStream_t st) {
+  if (!h->timing || h->ev_used >= kMaxTimedEvents) return;
+  while (h->events.size() <= h->ev_used) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     h->events.push_back(e);
+    h->ev_label.push_back(nullptr);
   }
-  cudaEventRecord(h->events[idx], st);
-  if (boundary == kStages) ++h->timed_calls;
+  cudaEventRecord(h->events[h->ev_used], st);
+  h->ev_label[h->ev_used++] = label;
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -110,6 +117,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
   SamplePlan s{};
   s.on = false;
+  s.rank_lo = -1;
   s.CAP = (int)n;
   if (n < 16384 || n <= 8L * target || C > 1024) return s;
   int lanes = 1024 / C;
@@ -142,6 +150,15 @@ SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
   s.rows_per_group = (int)g;
   s.rank = rank;
   s.CAP = 4096;
+  // complete-list rule: a column with at most ~0.7 * CAP elements above the score threshold is collected whole
+  // (threshold = T_min).  Such a column leaves a fraction q0 = (1 - 0.7 CAP / n)^g of the groups without any element
+  // above T_min; with a true population of CAP the expected fraction is far lower (> 3 sigma at G = 96), and an
+  // overflowing list is still handled exactly (exact scan), just slowly.
+  {
+    const double q0 = std::pow(1.0 - 0.7 * s.CAP / (double)n, (double)g);
+    s.rank_lo = (n > 2L * s.CAP && q0 > 0.02) ? (int)std::floor(q0 * G) : -1;
+    if (s.rank_lo >= G - 1) s.rank_lo = G - 2;
+  }
   return s;
 }
 
@@ -158,7 +175,7 @@ SamplePlan choose_plan(long n, int C, bool emit, long k_lim, int nms_target, int
                           : nms_target;
   SamplePlan plan = make_plan(n, C, emit_short && emit ? (int)std::max<long>(64, k_lim / 2) : target,
                               emit_fine ? emit_lanes : 12);
-  if (plan.on && emit) plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target;
+  if (plan.on && emit) { plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target; plan.rank_lo = -1; }
   if (emit_fine_out) *emit_fine_out = emit_fine;
   if (target_out) *target_out = target;
   return plan;
@@ -194,6 +211,7 @@ struct ProblemSet {
   const float* x; int is_logit; int B; long n; int C;   // fused tensors ...
   const float4* deltas; const float4* boxes; int q;
   const Levels* levels;    // ... or the per-level pieces (x / deltas then unused)
+  const u64* row_keys; long k_rows; int C_src; const Levels* delta_lv;   // rows resolved through sorted keys (Global*)
   int consumer;            // RPP_CONSUME_*
   long k_lim; int M_lim; int M;
   int clip_before; float iou_threshold; float score_threshold; float T_min;
@@ -269,15 +287,17 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
 
   // ---- stage 0/1: thresholds ---------------------------------------------------------------------------------
   CUDA_OK(cudaMemsetAsync(cand_count, 0, zero_bytes, st));
-  stage_mark(h, 0, st);
+  stage_mark(h, nullptr, st);
   if (plan.on && !h->force_scan) {
     const int threads = (int)align_up((size_t)plan.lanes * C, 32);
     // narrow problem sets (C = 1: 48 active threads per block) need more blocks in flight to cover the load latency
     const int max_split = threads <= 64 ? 64 : 16;
     const int split = plan.rows_per_group < max_split ? plan.rows_per_group : max_split;
-    if (emit_fine && C == 1 && lv.L == 1 && lv.dtype == RPP_DT_F32 && n % 4 == 0 && aligned && plan.rows_per_group >= 8)
+    if (C == 1 && lv.L == 1 && lv.dtype == RPP_DT_F32 && plan.rows_per_group >= 8) {
+      const int lead = (int)(((uintptr_t)lv.x[0] % 16) / 4);
       sample_max_flat4_kernel<<<dim3(B, std::min(plan.rows_per_group / 4, max_split)), threads, 0, st>>>(
-          (const float4*)lv.x[0], n / 4, plan.stride, plan.lanes, plan.rows_per_group / 4, gm);
+          lv.x[0] - lead, lead, n, plan.stride, plan.lanes, plan.rows_per_group / 4, gm);
+    }
     else if (lv.L > 1 && lv.dtype != RPP_DT_F32)
       sample_max_kernel<true, true><<<dim3(B, split), threads, 0, st>>>(lv, n, C, plan.stride, plan.lanes,
                                                                         plan.rows_per_group, gm);
@@ -293,18 +313,18 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     LAUNCHED();
     if (plan.G <= 128) {
       sample_rank_sort_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), RPP_RANK_CPB * 32, 0, st>>>(
-          gm, C, plan.G, plan.rank, ps.T_min, T);
+          gm, C, plan.G, plan.rank, plan.rank_lo, ps.T_min, T);
     } else {
       const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
       sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
-                                                                                          ps.T_min, T);
+                                                                                          plan.rank_lo, ps.T_min, T);
     }
     LAUNCHED();
   } else {
     fill_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(T, P, ps.T_min);
     LAUNCHED();
   }
-  stage_mark(h, 1, st);
+  stage_mark(h, emit ? "emit:sample" : "sample", st);
   // ---- stage 2: collect --------------------------------------------------------------------------------------
   // Unsampled SCORE columns (dense stage inputs of a few thousand rows): a list would just be a copy of the column,
   // so the problem kernel scans the column itself (its "exact scan" phase costs no sigmoid on scores).
@@ -384,25 +404,25 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       LAUNCHED();
     } else if (lv.L > 1) {
       return fail(RPP_EINVAL, "per-level inputs need num_classes % 4 == 0 and 16-byte aligned level tensors");
-    } else if (C == 1 && n % 4 == 0 && ((uintptr_t)ps.x % 16) == 0) {
-      const long n4 = n / 4;
-      const int UNROLL = 4;
-      long f4_per_tile = (long)RPP_COLLECT_NT * UNROLL * 4;   // 32 K elements per tile
-      if (plan.on) {   // keep ~128 expected hits per tile (queue capacity 1024)
-        const long want = (long)(128.0 * n / target / 4);
-        f4_per_tile = std::max<long>((long)RPP_COLLECT_NT * UNROLL,
-                                     std::min<long>(want, (long)RPP_COLLECT_NT * UNROLL * 16));
-        f4_per_tile = f4_per_tile / ((long)RPP_COLLECT_NT * UNROLL) * ((long)RPP_COLLECT_NT * UNROLL);
-      }
-      const int tiles_per_image = (int)((n4 + f4_per_tile - 1) / f4_per_tile);
-      long grid = std::min<long>((long)h->sm_count * 3, (long)B * tiles_per_image);
-      collect_flat4_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>((const float4*)ps.x, T, cand_count, cand,
-                                                                        plan.CAP, B, n4, (int)f4_per_tile,
-                                                                        tiles_per_image, tile_counter);
-      LAUNCHED();
     } else if (C == 1) {
-      long chunks = std::max<long>(1, std::min<long>((n + 1023) / 1024, (long)h->sm_count * 16 / std::max(1, B) + 1));
-      collect_flat1_kernel<<<dim3((unsigned)chunks, (unsigned)B), 256, 0, st>>>(ps.x, T, cand_count, cand, plan.CAP, n);
+      // single column, any n and any (4-byte) alignment: the batch as one flat array of 128-bit words
+      const int lead = (int)(((uintptr_t)ps.x % 16) / 4);
+      const int UNROLL = 4;
+      const long unit = (long)RPP_COLLECT_NT * UNROLL * 4;   // elements per block-wide load round (8192)
+      long tile_elems = 4 * unit;
+      if (plan.on) {   // ~a third of the shared queue (RPP_FLAT_QCAP) expected per tile
+        const long want = (long)((RPP_FLAT_QCAP / 3.0) * (double)n / target);
+        tile_elems = std::max(unit, std::min(want / unit * unit, 16 * unit));
+      }
+      const long total = (long)lead + (long)B * n;
+      {   // small batches: at least ~4 tiles per resident CTA
+        const long want_tiles = 4L * h->sm_count * 3;
+        while (tile_elems > unit && (total + tile_elems - 1) / tile_elems < want_tiles) tile_elems -= unit;
+      }
+      const long n_tiles = (total + tile_elems - 1) / tile_elems;
+      const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
+      collect_flat_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>(ps.x - lead, lead, T, cand_count, cand, plan.CAP,
+                                                                       B, n, tile_elems, n_tiles, tile_counter);
       LAUNCHED();
     } else {
       const size_t tot = (size_t)B * n * C;
@@ -412,7 +432,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       LAUNCHED();
     }
   }
-  stage_mark(h, 2, st);
+  stage_mark(h, emit ? "emit:collect" : "collect", st);
   if (ev) {  // the problems (and what follows) run on the side stream, ordered after this collect
     CUDA_OK(cudaEventRecord(ev, st));
     CUDA_OK(cudaStreamWaitEvent(st2, ev, 0));
@@ -422,6 +442,9 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   ColProblemParams pp{};
   pp.lv = lv; pp.is_logit = ps.is_logit; pp.N = n; pp.C = C;
   pp.anchors = h->d_anchors; pp.boxes = ps.boxes; pp.q = ps.q; pp.dp = h->dp;
+  pp.row_keys = ps.row_keys; pp.k_rows = ps.k_rows; pp.C_src = ps.C_src;
+  memset(&pp.dlv, 0, sizeof(pp.dlv));
+  if (ps.delta_lv) pp.dlv = *ps.delta_lv;
   pp.clip_before = ps.clip_before;
   pp.iou_threshold = ps.iou_threshold;
   pp.score_threshold = ps.score_threshold;
@@ -481,7 +504,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   launch();
   LAUNCHED();
-  stage_mark(h, 3, st);
+  stage_mark(h, emit ? "emit:sort" : "nms", st);
   return RPP_OK;
 }
 
@@ -553,7 +576,7 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
     mq.out_valid = out.valid;
     merge_padded_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mq);
     LAUNCHED();
-    stage_mark(h, 4, st);
+    stage_mark(h, "merge", st);
     return RPP_OK;
   }
 
@@ -573,7 +596,7 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   if (!mp.keys_in_smem) merge_smem = sizeof(MergeShared);
   merge_kernel<<<B, RPP_MERGE_NT, merge_smem, st>>>(mp);
   LAUNCHED();
-  stage_mark(h, 4, st);
+  stage_mark(h, "merge", st);
   return RPP_OK;
 }
 
@@ -612,16 +635,26 @@ int per_class_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const
   return RPP_OK;
 }
 
+// Rows of the Global* NMS input that were resolved without gathering them (rpp_global.cuh): row maxima (scores) and
+// decoded boxes per filtered row, and the sorted keys that map a filtered row back to its anchor.
+struct GlobalPre {
+  const float* mraw;      // [B][k] max-class score per row
+  const u64* row_keys;    // [B][k] emitted keys (tie = anchor * C + class)
+  const Levels* src;      // the logits (class lookup of the selected rows)
+  long N;
+};
+
 // Global*: NonMaxSuppressionV5 per image on the row maxima of x [B,n,C].
 // score_rowmax: x holds logits but the row maxima are scored right here (sigmoid is monotone: max score = score of the
 // max logit) and the NMS runs on that dense score column; only the class lookup of the <= M selected rows goes back
-// to the logits.  Used after the global filter, where scoring the whole [B,k,C] gather would be k*C sigmoids per image.
+// to the logits.
 int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
-                    int B, long n, const Outputs& out, cudaStream_t st, bool score_rowmax = false) {
+                    int B, long n, const Outputs& out, cudaStream_t st, bool score_rowmax = false,
+                    const GlobalPre* pre = nullptr) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
-  float* mraw = ar.take<float>((size_t)B * n);
-  if (!ar.dry) {
+  float* mraw = pre ? const_cast<float*>(pre->mraw) : ar.take<float>((size_t)B * n);
+  if (!ar.dry && !pre) {
     const size_t rows = (size_t)B * n;
     size_t grid = (rows * 32 + 255) / 256;
     if (grid > (size_t)h->sm_count * 16) grid = (size_t)h->sm_count * 16;
@@ -637,14 +670,16 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
                                                                                                             rows);
       LAUNCHED();
     }
+    stage_mark(h, "rows:rowmax", st);
   }
-  const int x_is_logit = is_logit;
-  if (score_rowmax) is_logit = 0;   // the problems below see a dense score column
+  const int x_is_logit = pre ? 1 : is_logit;
+  if (score_rowmax || pre) is_logit = 0;   // the problems below see a dense score column
   float iou_thr, sigma_tf;
   nms_v5_args(c, &iou_thr, &sigma_tf);
   ProblemSet ps{};
   ps.x = mraw; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = 1;
   ps.deltas = deltas; ps.boxes = boxes; ps.q = 1;
+  if (pre) { ps.row_keys = pre->row_keys; ps.k_rows = n; ps.C_src = C; ps.delta_lv = pre->src; }
   ps.k_lim = n; ps.M = M; ps.M_lim = M;
   ps.score_threshold = c.score_threshold;
   ps.T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
@@ -664,13 +699,20 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   GlobalOutParams gp{};
   gp.tpu = tpu ? 1 : 0;
   gp.M = M; gp.sel_key = ps.sel_key; gp.sel_box = ps.sel_box; gp.sel_cnt = ps.sel_cnt;
-  gp.x = x; gp.is_logit = x_is_logit; gp.n = n; gp.C = C;
+  memset(&gp.lv, 0, sizeof(gp.lv));
+  if (pre) {
+    gp.lv = *pre->src;
+    gp.row_keys = pre->row_keys; gp.k_rows = n;
+  } else {
+    gp.lv.L = 1; gp.lv.off[1] = n; gp.lv.x[0] = x; gp.lv.d[0] = deltas;
+  }
+  gp.is_logit = x_is_logit; gp.n = n; gp.C = C;
   gp.deltas = deltas; gp.anchors = h->d_anchors; gp.boxes = boxes; gp.dp = h->dp;
   gp.out_boxes = out.boxes; gp.out_scores = out.scores; gp.out_classes = (long long*)out.classes;
   gp.out_valid = out.valid;
   global_out_kernel<<<B, 128, 0, st>>>(gp);
   LAUNCHED();
-  stage_mark(h, 4, st);
+  stage_mark(h, "merge:global_out", st);
   return RPP_OK;
 }
 
@@ -753,14 +795,70 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
     const long k = std::min<long>(c.pre_nms_top_k, N);
     return per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, k, 1, 1, out, st);
   }
-  // global filter (:149-161): top-k over the flat (anchor, class) axis on raw logits, then the k selected rows are
-  // transformed (sigmoid of the whole row, decoded box) and fed to GenerateDetections as in the reference.
+  // global filter (:149-161): top-k over the flat (anchor, class) axis on raw logits ...
   if ((double)N * C >= 2147483647.0) return fail(RPP_EINVAL, "anchors x classes must stay below 2^31 for the global filter");
   const long k = std::min<long>(c.pre_nms_top_k, N * C);
   u64* keys = nullptr;
   int rc = topk_keys(h, ar, logits, 1, B, N * C, 1, k, &keys, st);
   if (rc) return rc;
-  const bool rows_as_logits = !per_class && C >= 16;   // narrow rows: scoring k * C values is cheaper than a second pass
+  if (!per_class) {
+    // ... Global*: the rows the reference gathers are never materialised (rpp_global.cuh): row maxima, boxes and the
+    // NonMaxSuppressionV5 order come straight from the sorted keys
+    float iou_thr, sigma_tf;
+    nms_v5_args(c, &iou_thr, &sigma_tf);
+    const int M = c.max_detections;
+    const bool soft = sigma_tf > 0.0f && !tpu_branch(c) && k <= RPP_GS_MAXK;
+    u32* first = ar.take<u32>((size_t)B * N);
+    float* mraw = ar.take<float>((size_t)B * k);
+    float4* box_spill = soft ? ar.take<float4>((size_t)B * k) : nullptr;
+    u64* skey = soft ? ar.take<u64>((size_t)B * k) : nullptr;
+    u64* dkey = soft ? ar.take<u64>((size_t)B * k) : nullptr;
+    int* sd_cnt = soft ? ar.take<int>((size_t)B * 2) : nullptr;
+    Levels lv;
+    memset(&lv, 0, sizeof(lv));
+    lv.L = 1; lv.off[1] = N; lv.x[0] = logits; lv.d[0] = deltas;
+    if (!ar.dry) {
+      CUDA_OK(cudaMemsetAsync(first, 0xff, (size_t)B * N * sizeof(u32), st));
+      GlobalRowsParams rp{};
+      rp.emit_key = keys; rp.k = k; rp.C = C; rp.N = N;
+      rp.first = first; rp.mraw = mraw; rp.skey = skey; rp.dkey = dkey; rp.sd_cnt = sd_cnt;
+      rp.score_threshold = c.score_threshold;
+      global_rows_kernel<<<B, RPP_GROWS_NT, 0, st>>>(rp);
+      LAUNCHED();
+      stage_mark(h, "rows:resolve", st);
+    }
+    if (soft) {
+      GlobalSoftParams gs{};
+      gs.k = k;
+      gs.ring_cap = 2;
+      while (gs.ring_cap < k) gs.ring_cap <<= 1;
+      gs.M = M;
+      // boxes of the best rows live in shared memory, as many as fit next to the ring (the rest is read through L2)
+      const size_t budget = 200 * 1024;
+      const size_t fixed = global_soft_smem(k, gs.ring_cap, 0, M);
+      if (fixed > budget) return fail(RPP_EINVAL, "max_detections too large for the global soft-NMS kernel");
+      gs.box_cap = (int)std::min<size_t>((size_t)k, (budget - fixed) / 16);
+      if (ar.dry) return RPP_OK;
+      gs.box_spill = box_spill; gs.anchors = h->d_anchors; gs.dp = h->dp;
+      gs.skey = skey; gs.dkey = dkey; gs.sd_cnt = sd_cnt;
+      gs.score_threshold = c.score_threshold;
+      gs.soft_scale = -0.5f / sigma_tf;
+      gs.iou_threshold = iou_thr;
+      gs.soft_ignores_iou = c.soft_ignores_iou_threshold;
+      gs.emit_key = keys; gs.lv = lv; gs.C = C; gs.N = N;
+      gs.debug = getenv("RPP_GS_DEBUG") ? 1 : 0;
+      gs.out_boxes = out.boxes; gs.out_scores = out.scores; gs.out_classes = (long long*)out.classes;
+      gs.out_valid = out.valid;
+      global_soft_kernel<<<B, RPP_GS_NT, global_soft_smem(k, gs.ring_cap, gs.box_cap, M), st>>>(gs);
+      LAUNCHED();
+      stage_mark(h, "nms:global_soft", st);
+      return RPP_OK;
+    }
+    GlobalPre pre{mraw, keys, &lv, N};
+    return global_pipeline(h, ar, nullptr, 0, nullptr, nullptr, B, k, out, st, false, &pre);
+  }
+  // ... per-class modes behind the global filter: the k selected rows are transformed (sigmoid of the whole row,
+  // decoded box) and fed to GenerateDetections as in the reference
   float* row_scores = ar.take<float>((size_t)B * k * C);
   float4* row_boxes = ar.take<float4>((size_t)B * k);
   if (!ar.dry) {
@@ -769,12 +867,10 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
     if (C < 16) tpr = C;
     size_t grid = std::min<size_t>(((size_t)B * k * tpr + 255) / 256, (size_t)h->sm_count * 16);
     fused_global_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, logits, deltas, h->d_anchors, h->dp, B, N, C, k,
-                                                            /*apply_sigmoid=*/rows_as_logits ? 0 : 1, row_scores,
-                                                            row_boxes);
+                                                            /*apply_sigmoid=*/1, row_scores, row_boxes);
     LAUNCHED();
+    stage_mark(h, "rows:gather", st);
   }
-  if (rows_as_logits)   // Global*, wide rows: the gathered rows stay logits, only their maxima are scored
-    return global_pipeline(h, ar, row_scores, 1, nullptr, row_boxes, B, k, out, st, /*score_rowmax=*/true);
   return nms_dense(h, ar, row_scores, row_boxes, B, k, 1, out, st);
 }
 
@@ -867,6 +963,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   }
   h->timing = 0;
   h->timed_calls = 0;
+  h->ev_used = 0;
   {
     const char* v = getenv("RPP_OVERLAP");
     h->overlap = v ? atoi(v) : 0;   // measured slower on B200 (NMS blocks starve beside the persistent collect CTAs)
@@ -938,6 +1035,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(col_problem_kernel<RPP_CONSUME_PADDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(merge_padded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(global_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(emit_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -1007,25 +1105,63 @@ int rpp_debug_stage_timing(void* handle, int on) {
   if (!h) return fail(RPP_EINVAL, "null handle");
   h->timing = on ? 1 : 0;
   h->timed_calls = 0;
+  h->ev_used = 0;
   return RPP_OK;
 }
+
+namespace {
+// Sums the recorded segments by label (first-seen order), averaged per API call; resets the recording.
+int stage_collect(Handle* h, std::vector<std::pair<const char*, double>>& out, int* n_calls) {
+  out.clear();
+  const int n = h->timed_calls;
+  if (n_calls) *n_calls = n;
+  if (n == 0 || h->ev_used == 0) { h->ev_used = 0; h->timed_calls = 0; return RPP_OK; }
+  CUDA_OK(cudaEventSynchronize(h->events[h->ev_used - 1]));
+  for (size_t i = 1; i < h->ev_used; ++i) {
+    const char* lab = h->ev_label[i];
+    if (!lab) continue;
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, h->events[i - 1], h->events[i]));
+    size_t j = 0;
+    while (j < out.size() && strcmp(out[j].first, lab) != 0) ++j;
+    if (j == out.size()) out.push_back({lab, 0.0});
+    out[j].second += ms / n;
+  }
+  h->ev_used = 0;
+  h->timed_calls = 0;
+  return RPP_OK;
+}
+}  // namespace
 
 int rpp_debug_stage_ms(void* handle, float* h_ms, int* n_calls) {
   Handle* h = (Handle*)handle;
   if (!h || !h_ms) return fail(RPP_EINVAL, "null argument");
   for (int s = 0; s < kStages; ++s) h_ms[s] = 0.f;
-  const int n = h->timed_calls;
-  if (n_calls) *n_calls = n;
-  if (n == 0) return RPP_OK;
-  CUDA_OK(cudaEventSynchronize(h->events[(size_t)(n - 1) * (kStages + 1) + kStages]));
-  for (int c = 0; c < n; ++c)
-    for (int s = 0; s < kStages; ++s) {
-      float ms = 0.f;
-      CUDA_OK(cudaEventElapsedTime(&ms, h->events[(size_t)c * (kStages + 1) + s],
-                                   h->events[(size_t)c * (kStages + 1) + s + 1]));
-      h_ms[s] += ms / n;
-    }
-  h->timed_calls = 0;
+  std::vector<std::pair<const char*, double>> segs;
+  if (int rc = stage_collect(h, segs, n_calls)) return rc;
+  for (auto& sg : segs) {   // the four classic buckets; everything else (emission, row gathers) counts as "nms"
+    const char* l = sg.first;
+    int bkt = 2;
+    if (!strncmp(l, "sample", 6)) bkt = 0;
+    else if (!strncmp(l, "collect", 7)) bkt = 1;
+    else if (!strncmp(l, "merge", 5)) bkt = 3;
+    h_ms[bkt] += (float)sg.second;
+  }
+  return RPP_OK;
+}
+
+int rpp_debug_stage_report(void* handle, char* buf, int cap, int* n_calls) {
+  Handle* h = (Handle*)handle;
+  if (!h || !buf || cap <= 0) return fail(RPP_EINVAL, "null argument");
+  std::vector<std::pair<const char*, double>> segs;
+  if (int rc = stage_collect(h, segs, n_calls)) return rc;
+  int off = 0;
+  buf[0] = 0;
+  for (auto& sg : segs) {
+    const int w = snprintf(buf + off, (size_t)(cap - off), "%s%s=%.6f", off ? ";" : "", sg.first, sg.second);
+    if (w < 0 || w >= cap - off) return fail(RPP_EINVAL, "stage report buffer too small");
+    off += w;
+  }
   return RPP_OK;
 }
 
@@ -1107,6 +1243,7 @@ int rpp_topk(void* handle, const float* d_scores, const float* d_boxes, int B, l
     return fail(RPP_EINVAL, "bad argument");
   if (h->cfg.pre_nms_top_k <= 0) return fail(RPP_EINVAL, "pre_nms_top_k must be positive for rpp_topk");
   if (int rc = check_device(h)) return rc;
+  if (h->timing) ++h->timed_calls;
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     return topk_dense(h, ar, d_scores, (const float4*)d_boxes, B, n, d_scores_out, (float4*)d_boxes_out, d_index_out,
                       (cudaStream_t)stream);
@@ -1119,6 +1256,7 @@ int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, lo
   g_launches = 0;
   if (!h || !d_scores || !d_boxes || B <= 0 || n <= 0 || n >= 0x7fffffffL) return fail(RPP_EINVAL, "bad argument");
   if (int rc = check_device(h)) return rc;
+  if (h->timing) ++h->timed_calls;
   const rpp_config& c = h->cfg;
   if (q != 1 && q != c.num_classes) return fail(RPP_EINVAL, "boxes must be [B,n,4] or [B,n,num_classes,4]");
   if (!is_per_class_mode(c.mode) && q != 1)
@@ -1134,6 +1272,7 @@ static int detect_impl(Handle* h, const float* d_deltas, const float* d_logits, 
                        void* stream) {
   if (!h || !d_deltas || !d_logits || B <= 0) return fail(RPP_EINVAL, "bad argument");
   if (int rc = check_device(h)) return rc;
+  if (h->timing) ++h->timed_calls;
   const Outputs out{(float4*)d_boxes_out, d_scores_out, d_classes_out, d_valid_out};
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     return detect_pipeline(h, ar, (const float4*)d_deltas, d_logits, B, out, (cudaStream_t)stream);
@@ -1174,6 +1313,7 @@ int rpp_efficient_nms(void* handle, const float* d_raw_boxes, const float* d_cla
   const int C = h->cfg.num_classes, M = h->cfg.max_detections;
   const long N = h->N;
   if ((double)N * C >= 2147483647.0) return fail(RPP_EINVAL, "anchors x classes out of range");
+  if (h->timing) ++h->timed_calls;
   cudaStream_t st = (cudaStream_t)stream;
   return with_arena(ws, ws_bytes, [&](Arena& ar) {
     const long k = std::min<long>(RPP_EFFNMS_SELECTED, N * C);
@@ -1191,7 +1331,7 @@ int rpp_efficient_nms(void* handle, const float* d_raw_boxes, const float* d_cla
     ep.out_scores = d_detection_scores; ep.out_classes = d_detection_classes;
     effnms_kernel<<<B, RPP_NMS_NT, (size_t)M * 24, st>>>(ep);
     LAUNCHED();
-    stage_mark(h, 4, st);
+    stage_mark(h, "nms:effnms", st);
     return (int)RPP_OK;
   });
 }
@@ -1207,6 +1347,7 @@ int rpp_detect_typed(void* handle, int n_pieces, const void* const* d_deltas, co
   if (n_pieces != 1 && n_pieces != h->levels)
     return fail(RPP_EINVAL, "n_pieces must be 1 (fused tensors) or the number of levels (%d)", h->levels);
   if (n_pieces > RPP_MAX_LEVELS) return fail(RPP_EINVAL, "too many levels");
+  if (h->timing) ++h->timed_calls;
   Levels lv;
   memset(&lv, 0, sizeof(lv));
   lv.L = n_pieces;

@@ -338,73 +338,103 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
 }
 
 // Single-column variant (C == 1: the flat anchors x classes axis of the global filter, or the row maxima of the
-// Global* modes): x [B, n], n % 4 == 0, one threshold per image.  Same structure: streaming LDG.128, hits queued in
-// shared memory, one global atomic per tile.
-#define RPP_FLAT_QCAP 1024
+// Global* modes): x [B, n], one threshold per image, ANY n.  The batch is treated as one flat array of B * n floats
+// (only its base must be 16-byte aligned): tiles are ranges of 128-bit words of that array, so image bases that are
+// not multiples of 16 bytes (n % 4 != 0, e.g. 320x320 / 5 classes: n = 96 030; or a tensor whose own base is only
+// 4-byte aligned: `lead`) still stream with LDG.128.  A tile that
+// straddles an image boundary is processed as one segment per image; the <= 3 elements at each ragged segment edge
+// are read with scalar loads, and no 128-bit load ever crosses a segment (or the end of the array).
+// Hits are counted per thread (a 4 * UNROLL bit mask), placed in the shared queue with ONE shared atomic per warp and
+// load round (warp prefix sum), and flushed with one global atomic per (tile, image).
+#define RPP_FLAT_QCAP 2048
 template <int UNROLL>
 __global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
-collect_flat4_kernel(const float4* __restrict__ x4 /*[B, n/4]*/, const float* __restrict__ T /*[B]*/,
-                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long n4,
-                     int f4_per_tile, int tiles_per_image, u32* __restrict__ tile_counter) {
+collect_flat_kernel(const float* __restrict__ x /*16-byte aligned; element `lead` (0..3) is x[0][0]*/, int lead,
+                    const float* __restrict__ T /*[B]*/, u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP,
+                    int B, long n, long tile_elems, long n_tiles, u32* __restrict__ tile_counter) {
   __shared__ uint2 s_q[RPP_FLAT_QCAP];
   __shared__ u32 s_qn, s_base;
   __shared__ long s_tile;
-  const int tid = threadIdx.x;
-  const long n_tiles = (long)B * tiles_per_image;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long total = (long)lead + (long)B * n;   // the flat array, counted from the aligned address
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
   for (;;) {
     if (tid == 0) { s_tile = (long)atomicAdd(tile_counter, 1u); s_qn = 0u; }
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
-    const int b = (int)(tile / tiles_per_image);
-    const long f0 = (long)(tile % tiles_per_image) * f4_per_tile;
-    const long f1 = f0 + f4_per_tile < n4 ? f0 + f4_per_tile : n4;
-    const float t = __ldg(T + b);
-    const float4* src = x4 + (size_t)b * n4;
-    for (long f = f0 + tid; f < f1; f += (long)RPP_COLLECT_NT * UNROLL) {
-      float4 v[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const long ff = f + (long)u * RPP_COLLECT_NT;
-        v[u] = ff < f1 ? ld_stream_f4(src + ff) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const long ff = f + (long)u * RPP_COLLECT_NT;
-        if (ff >= f1) continue;
-        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (e[i] >= t) {
-            const u32 idx = (u32)(ff * 4 + i);
+    const long e0 = tile * tile_elems;
+    const long e1 = e0 + tile_elems < total ? e0 + tile_elems : total;
+    for (long b = (e0 > lead ? e0 - lead : 0) / n; b < B && lead + b * n < e1; ++b) {   // images of this tile
+      const long ibase = lead + b * n;
+      const long seg_lo = e0 > ibase ? e0 : ibase;
+      const long seg_hi = e1 < ibase + n ? e1 : ibase + n;
+      const float t = __ldg(T + b);
+      long v_lo = (seg_lo + 3) & ~3L, v_hi = seg_hi & ~3L;   // whole 128-bit words inside the segment
+      if (v_lo > v_hi) v_lo = v_hi = seg_hi;
+      {   // ragged edges: [seg_lo, v_lo) and [v_hi, seg_hi), at most 3 + 3 elements
+        const long head = (v_lo < seg_hi ? v_lo : seg_hi) - seg_lo;
+        const long tail = seg_hi - (v_hi > v_lo ? v_hi : v_lo);
+        if (tid < head + tail) {
+          const long e = tid < head ? seg_lo + tid : (v_hi > v_lo ? v_hi : v_lo) + (tid - head);
+          const float v = __ldg(x + e);
+          if (v >= t) {
             const u32 slot = atomicAdd(&s_qn, 1u);
-            if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(e[i]), idx);
-            else append_cand(cand_count, cand, CAP, (size_t)b, e[i], idx);
+            if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(v), (u32)(e - ibase));
+            else append_cand(cand_count, cand, CAP, (size_t)b, v, (u32)(e - ibase));
           }
         }
       }
+      const long f_lo = v_lo >> 2, f_hi = v_hi >> 2;
+      for (long f0 = f_lo; f0 < f_hi; f0 += (long)RPP_COLLECT_NT * UNROLL) {   // uniform trip count per block
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const long ff = f0 + tid + (long)u * RPP_COLLECT_NT;
+          v[u] = ff < f_hi ? ld_stream_f4(x4 + ff) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+        u32 mask = 0u;   // bit 4u + i: component i of load u passes (NaN never passes >=)
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+          mask |= ((v[u].x >= t ? 1u : 0u) | (v[u].y >= t ? 2u : 0u) | (v[u].z >= t ? 4u : 0u) |
+                   (v[u].w >= t ? 8u : 0u)) << (4 * u);
+        if (__any_sync(RPP_FULL_MASK, mask != 0u)) {
+          // warp prefix sum of the per-thread hit counts -> one shared atomic per warp
+          const u32 cnt = (u32)__popc(mask);
+          u32 incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u32 up = __shfl_up_sync(RPP_FULL_MASK, incl, o);
+            if (lane >= o) incl += up;
+          }
+          u32 wbase = 0u;
+          if (lane == 31) wbase = atomicAdd(&s_qn, incl);
+          wbase = __shfl_sync(RPP_FULL_MASK, wbase, 31);
+          u32 slot = wbase + incl - cnt;
+          while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const long ff = f0 + tid + (long)(bit >> 2) * RPP_COLLECT_NT;
+            const u32 idx = (u32)(ff * 4 + (bit & 3) - ibase);
+            const float val = __ldg(x + ff * 4 + (bit & 3));   // L1 hit: the line was just loaded by this thread
+            if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(val), idx);
+            else append_cand(cand_count, cand, CAP, (size_t)b, val, idx);
+            ++slot;
+          }
+        }
+      }
+      __syncthreads();
+      const u32 nq = s_qn < RPP_FLAT_QCAP ? s_qn : RPP_FLAT_QCAP;
+      if (tid == 0) s_base = nq ? atomicAdd(&cand_count[b], nq) : 0u;
+      __syncthreads();
+      for (u32 i = tid; i < nq; i += RPP_COLLECT_NT) {
+        const u32 slot = s_base + i;
+        if (slot < (u32)CAP) cand[(size_t)b * CAP + slot] = s_q[i];
+      }
+      __syncthreads();
+      if (tid == 0) s_qn = 0u;
+      __syncthreads();
     }
-    __syncthreads();
-    const u32 nq = s_qn < RPP_FLAT_QCAP ? s_qn : RPP_FLAT_QCAP;
-    if (tid == 0) s_base = nq ? atomicAdd(&cand_count[b], nq) : 0u;
-    __syncthreads();
-    for (u32 i = tid; i < nq; i += RPP_COLLECT_NT) {
-      const u32 slot = s_base + i;
-      if (slot < (u32)CAP) cand[(size_t)b * CAP + slot] = s_q[i];
-    }
-    __syncthreads();
-  }
-}
-
-// single column, any n / alignment: grid (chunks, B), no index arithmetic beyond the stride
-__global__ void collect_flat1_kernel(const float* __restrict__ x /*[B,n]*/, const float* __restrict__ T,
-                                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, long n) {
-  const int b = blockIdx.y;
-  const float t = __ldg(T + b);
-  const float* xb = x + (size_t)b * n;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-    const float v = __ldg(xb + i);
-    if (v >= t) append_cand(cand_count, cand, CAP, (size_t)b, v, (u32)i);
   }
 }
 

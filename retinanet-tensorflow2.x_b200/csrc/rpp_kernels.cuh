@@ -120,3 +120,4 @@ __global__ void decode_kernel(const float4* __restrict__ deltas, const float4* _
 #include "rpp_collect.cuh"   // K2  collect (the HBM-bound stream)
 #include "rpp_nms.cuh"       // K3  problems: selection, NMS consumers, probe / bound, top-k emission
 #include "rpp_outputs.cuh"   // K4-K8  merges, Global* outputs, gathers, EfficientNMS entry, COCO epilogue
+#include "rpp_global.cuh"    // K9  Global* modes behind the global filter: row resolution, block-parallel soft NMS

@@ -24,6 +24,10 @@ struct ColProblemParams {
   const float4* anchors;   // [N]
   const float4* boxes;     // dense boxes (stage-wise) or nullptr
   int q;
+  // rows that are not rows of the delta tensor (the global filter without the row gather, rpp_global.cuh): row j is
+  // anchor tie(row_keys[b][j]) / C_src of the deltas in dlv
+  const u64* row_keys; long k_rows; int C_src;
+  Levels dlv;
   DecodeParams dp;
   int clip_before;         // clip boxes to [0,1] before IoU (every mode but CombinedNMS; B6)
   float iou_threshold;
@@ -103,6 +107,10 @@ __device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int 
   if (P.boxes) {
     const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;  // boxes[:, min(q-1, c)] (:440)
     return P.boxes[((size_t)b * P.N + row) * P.q + qi];
+  }
+  if (P.row_keys) {
+    const u32 a = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C_src;
+    return decode_box(lv_delta(P.dlv, b, a), P.anchors[a], P.dp);
   }
   return decode_box(lv_delta(P.lv, b, row), P.anchors[row], P.dp);
 }
@@ -280,6 +288,8 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
 // expf_glibc reproduces libm's expf bit for bit (checked against glibc on 4.5e8 inputs): TF's kernel calls
 // Eigen::numext::exp<float> = expf.
 // ---------------------------------------------------------------------------------------------------------------
+// (the 32-entry 2^(i/32) table of glibc's expf — sysdeps/ieee754/flt-32/e_exp2f_data.c, LGPL-2.1+ — restated: these
+// are the correctly rounded binary64 values of 2^(i/32) with the exponent bits adjusted, i.e. mathematical constants)
 __constant__ u64 c_exp2f_tab[32] = {
     0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL,
     0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL,
@@ -290,7 +300,9 @@ __constant__ u64 c_exp2f_tab[32] = {
     0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL,
     0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL};
 
-__device__ __forceinline__ float expf_glibc(float x) {
+// `tab` = c_exp2f_tab or a copy of it: the index differs per lane, and the constant cache serves one address per
+// cycle, so warps that evaluate many weights at once read a shared-memory copy instead.
+__device__ __forceinline__ float expf_glibc_tab(float x, const u64* tab) {
   if (!(x > -87.0f && x < 88.0f)) return (float)exp((double)x);  // under/overflow tails: correctly rounded exp
   const double N = 32.0;
   const double InvLn2N = 0x1.71547652b82fep+0 * N, SHIFT = 0x1.8p+52;
@@ -300,7 +312,7 @@ __device__ __forceinline__ float expf_glibc(float x) {
   const u64 ki = (u64)__double_as_longlong(kd);
   kd = __dsub_rn(kd, SHIFT);
   const double r = __dsub_rn(z, kd);
-  const u64 t = c_exp2f_tab[ki & 31u] + (ki << 47);
+  const u64 t = tab[ki & 31u] + (ki << 47);
   const double sc = __longlong_as_double((long long)t);
   const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
   const double r2 = __dmul_rn(r, r);
@@ -309,6 +321,7 @@ __device__ __forceinline__ float expf_glibc(float x) {
   y = __dmul_rn(y, sc);
   return __double2float_rn(y);
 }
+__device__ __forceinline__ float expf_glibc(float x) { return expf_glibc_tab(x, c_exp2f_tab); }
 
 #define RPP_SOFT_RS 512
 

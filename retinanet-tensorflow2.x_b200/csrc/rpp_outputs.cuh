@@ -307,8 +307,11 @@ struct GlobalOutParams {
   const u64* sel_key;     // [B][M]  (score | ~row)
   const float4* sel_box;  // [B][M]
   const int* sel_cnt;     // [B]
-  const float* x;         // [B,n,C] logits or scores
+  Levels lv;              // class lookup source: logits (is_logit) or scores, [B, rows, C] (fused or per-level pieces)
   int is_logit; long n; int C;
+  // rows of the NMS input that are not rows of `lv`: row j of the filtered list is anchor tie(row_keys[b][j]) / C
+  // (the global filter without the row gather, rpp_global.cuh); nullptr: the NMS rows are the rows of `lv`
+  const u64* row_keys; long k_rows;
   const float4* deltas; const float4* anchors; const float4* boxes; DecodeParams dp;
   float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
   int tpu;                // _tpu_global_hard_nms (:402-431): int32 classes, -1 in every field beyond valid
@@ -322,15 +325,16 @@ __global__ void global_out_kernel(GlobalOutParams P) {
     const size_t o = (size_t)b * P.M + i;
     if (i < valid) {
       const u64 k = P.sel_key[o];
-      const u32 row = key_tie(k);
-      const float* xr = P.x + ((size_t)b * P.n + row) * P.C;
+      u32 row = key_tie(k);
+      if (P.row_keys) row = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C;
       // tf.argmax over scores: first class whose SCORE equals the row maximum
       float best = -INFINITY;
-      for (int c = 0; c < P.C; ++c) best = fmaxf(best, xr[c]);
+      for (int c = 0; c < P.C; ++c) best = fmaxf(best, lv_val(P.lv, b, row, P.C, c));
       const float s_best = P.is_logit ? sigmoid_f32(best) : best;
       int cls = 0;
       for (int c = 0; c < P.C; ++c) {
-        const float s = P.is_logit ? (xr[c] == best ? s_best : sigmoid_f32(xr[c])) : xr[c];
+        const float raw = lv_val(P.lv, b, row, P.C, c);
+        const float s = P.is_logit ? (raw == best ? s_best : sigmoid_f32(raw)) : raw;
         if (s == s_best) { cls = c; break; }
       }
       P.out_boxes[o] = P.sel_box[o];
@@ -342,7 +346,12 @@ __global__ void global_out_kernel(GlobalOutParams P) {
       reinterpret_cast<int*>(P.out_classes)[o] = -1;
     } else {
       // padded selected index 0 -> boxes[0] (clipped), score -1, class -1 (:258-268)
-      float4 bx = P.boxes ? P.boxes[(size_t)b * P.n] : decode_box(P.deltas[(size_t)b * P.n], P.anchors[0], P.dp);
+      u32 row0 = 0u;
+      if (P.row_keys) {
+        const u64 k0 = P.row_keys[(size_t)b * P.k_rows];
+        row0 = k0 != 0ull ? key_tie(k0) / (u32)P.C : 0u;
+      }
+      float4 bx = P.boxes ? P.boxes[(size_t)b * P.n] : decode_box(lv_delta(P.lv, b, row0), P.anchors[row0], P.dp);
       P.out_boxes[o] = clip01(bx);
       P.out_scores[o] = -1.0f;
       P.out_classes[o] = -1;

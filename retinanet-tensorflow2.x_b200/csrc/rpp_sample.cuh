@@ -93,12 +93,14 @@ sample_max_kernel(Levels lv /*[B,N,C]*/, long N, int C, int stride, int lanes,
     atomicMax(&gm[((size_t)b * G + rl + i * lanes) * C + c], ord_f32(m[i]));
 }
 
-// Single-column variant (C == 1: the flat anchors x classes axis of the global filter and of the EfficientNMS entry,
-// n % 4 == 0): every sample is one 16-byte load = four consecutive elements, so the same number of sampled elements
-// touches a quarter of the sectors (a strided sample of single floats fetches 32 bytes for every 4 it uses).
+// Single-column variant (C == 1: the flat anchors x classes axis of the global filter and of the EfficientNMS entry):
+// every sample is one 16-byte load = four consecutive elements, so the same number of sampled elements touches a
+// quarter of the sectors (a strided sample of single floats fetches 32 bytes for every 4 it uses).  Any n and any
+// 4-byte alignment: image b is sampled over the whole 128-bit words that lie inside it (the <= 3 elements at each
+// end are left out of the SAMPLE only — the collect pass sees every element).
 __global__ void __launch_bounds__(1024, 2)
-sample_max_flat4_kernel(const float4* __restrict__ x4 /*[B][n4]*/, long n4, int stride4, int lanes, int rounds4,
-                        u32* __restrict__ gm /*[B][G]*/) {
+sample_max_flat4_kernel(const float* __restrict__ x /*16-byte aligned; element `lead` is x[0][0]*/, int lead, long n,
+                        int stride4, int lanes, int rounds4, u32* __restrict__ gm /*[B][G]*/) {
   const int b = blockIdx.x, split = blockIdx.y, nsplit = gridDim.y;
   const int rl = threadIdx.x;
   if (rl >= lanes) return;
@@ -106,11 +108,16 @@ sample_max_flat4_kernel(const float4* __restrict__ x4 /*[B][n4]*/, long n4, int 
   float m[RPP_GPT];
 #pragma unroll
   for (int i = 0; i < RPP_GPT; ++i) m[i] = -INFINITY;
-  const float4* base = x4 + (size_t)b * n4;
+  const long fb = ((long)lead + (long)b * n + 3) >> 2;              // first whole word of image b
+  const long nf = (((long)lead + (long)(b + 1) * n) >> 2) - fb;     // whole words inside image b
+  const float4* base = reinterpret_cast<const float4*>(x) + fb;
   for (int r = split; r < rounds4; r += nsplit) {
     float4 v[RPP_GPT];
 #pragma unroll
-    for (int i = 0; i < RPP_GPT; ++i) v[i] = __ldg(base + (size_t)((long)r * G + rl + i * lanes) * stride4);
+    for (int i = 0; i < RPP_GPT; ++i) {
+      const long idx = ((long)r * G + rl + i * lanes) * stride4;
+      v[i] = idx < nf ? __ldg(base + idx) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
 #pragma unroll
     for (int i = 0; i < RPP_GPT; ++i) m[i] = fmaxf(m[i], fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
   }
@@ -119,7 +126,11 @@ sample_max_flat4_kernel(const float4* __restrict__ x4 /*[B][n4]*/, long n4, int 
 }
 
 #define RPP_RANK_CPB 8   // classes per block
-__global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int rank, float T_min,
+// rank_lo >= 0: when the rank_lo-th smallest group maximum is already below T_min, so few elements of the column pass
+// the score threshold that ALL of them fit in the candidate list (host: choose_plan): the threshold is T_min itself and
+// the list is complete — no exact column scan can ever be needed for that problem (trained-detector inputs: a class
+// with a few objects has some hundreds of anchors above the threshold, all of them overlapping).
+__global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int rank, int rank_lo, float T_min,
                                    float* __restrict__ T) {
   extern __shared__ u32 s_gm[];  // [G][RPP_RANK_CPB]
   const int b = blockIdx.x, c0 = blockIdx.y * RPP_RANK_CPB;
@@ -138,13 +149,20 @@ __global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int
       less += o < v;
       eq += o == v;
     }
-    if (less <= rank && rank < less + eq) T[(size_t)b * C + c0 + cc] = fmaxf(unord_f32(v), T_min);
+    if (less <= rank && rank < less + eq) {
+      // (the complete-list rule: count the group maxima below T_min directly)
+      int below = 0;
+      if (rank_lo >= 0)
+        for (int g = 0; g < G; ++g) below += unord_f32(s_gm[g * RPP_RANK_CPB + cc]) < T_min;
+      T[(size_t)b * C + c0 + cc] = (rank_lo >= 0 && below > rank_lo) ? T_min : fmaxf(unord_f32(v), T_min);
+    }
   }
 }
 
 // Same result with a 128-key register bitonic sort per (image, class): one warp per class (G <= 128).
 __global__ void __launch_bounds__(RPP_RANK_CPB * 32)
-sample_rank_sort_kernel(const u32* __restrict__ gm, int C, int G, int rank, float T_min, float* __restrict__ T) {
+sample_rank_sort_kernel(const u32* __restrict__ gm, int C, int G, int rank, int rank_lo, float T_min,
+                        float* __restrict__ T) {
   __shared__ u32 s_gm[128 * RPP_RANK_CPB];
   const int b = blockIdx.x, c0 = blockIdx.y * RPP_RANK_CPB;
   const int nc = C - c0 < RPP_RANK_CPB ? C - c0 : RPP_RANK_CPB;
@@ -191,11 +209,16 @@ sample_rank_sort_kernel(const u32* __restrict__ gm, int C, int G, int rank, floa
   }
   // ascending: element `rank` is the answer
   const int rs = rank >> 5, rl = rank & 31;
-  u32 ans = 0u;
+  u32 ans = 0u, lo = 0xffffffffu;
 #pragma unroll
-  for (int sidx = 0; sidx < 4; ++sidx)
+  for (int sidx = 0; sidx < 4; ++sidx) {
     if (sidx == rs) ans = v[sidx];
-  if (lane == rl) T[(size_t)b * C + c0 + cc] = fmaxf(unord_f32(ans), T_min);
+    if (rank_lo >= 0 && sidx == (rank_lo >> 5)) lo = v[sidx];
+  }
+  // complete-list rule (see sample_rank_kernel): element rank_lo of the ascending order below T_min
+  lo = __shfl_sync(RPP_FULL_MASK, lo, rank_lo >= 0 ? (rank_lo & 31) : 0);
+  const bool complete = rank_lo >= 0 && unord_f32(lo) < T_min;
+  if (lane == rl) T[(size_t)b * C + c0 + cc] = complete ? T_min : fmaxf(unord_f32(ans), T_min);
 }
 
 __global__ void fill_kernel(float* p, size_t n, float v) {

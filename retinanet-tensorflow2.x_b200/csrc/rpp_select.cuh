@@ -123,19 +123,33 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
       __syncthreads();  // hist is rewritten next round
     }
   }
-  // pass 3: compaction of {lo <= key < KB}
+  // pass 3: compaction of {lo <= key < KB}.  One shared-memory atomic per warp and load round (ballot + popc),
+  // not one per key: a chunk of a few thousand keys otherwise serialises on the single counter.
   if (tid == 0) sc->m = 0;
   __syncthreads();
-  for (int i0 = tid; i0 < n; i0 += 4 * NT) {
-    u64 k4[4];
+  {
+    const int lane = tid & 31;
+    const u32 lt = (1u << lane) - 1u;
+    for (int base = 0; base < n; base += 4 * NT) {   // uniform trip count: every lane takes part in the ballots
+      u64 k4[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
+      for (int u = 0; u < 4; ++u) {
+        const int i = base + u * NT + tid;
+        k4[u] = i < n ? key(i) : 0ull;
+      }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const u64 k = k4[u];
-      if (k != 0ull && k < KB && k >= lo) {
-        const u32 slot = atomicAdd(&sc->m, 1u);
-        if (slot < (u32)CC) chunk[slot] = k;
+      for (int u = 0; u < 4; ++u) {
+        const u64 k = k4[u];
+        const bool hit = k != 0ull && k < KB && k >= lo;
+        const u32 mask = __ballot_sync(RPP_FULL_MASK, hit);
+        if (mask == 0u) continue;
+        u32 slot0 = 0u;
+        if (lane == __ffs(mask) - 1) slot0 = atomicAdd(&sc->m, (u32)__popc(mask));
+        slot0 = __shfl_sync(RPP_FULL_MASK, slot0, __ffs(mask) - 1);
+        if (hit) {
+          const u32 slot = slot0 + (u32)__popc(mask & lt);
+          if (slot < (u32)CC) chunk[slot] = k;
+        }
       }
     }
   }

@@ -18,7 +18,7 @@ EXPORTS = [
     'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_nms', 'rpp_detect', 'rpp_detect_levels', 'rpp_detect_typed',
     'rpp_detect_host', 'rpp_detect_host_typed', 'rpp_coco_format', 'rpp_efficient_nms',
     'rpp_last_launch_count', 'rpp_classes_itemsize', 'rpp_debug_force_exact_scan', 'rpp_debug_stage_timing',
-    'rpp_debug_stage_ms', 'rpp_debug_sample_plan',
+    'rpp_debug_stage_ms', 'rpp_debug_stage_report', 'rpp_debug_sample_plan',
 ]
 
 
@@ -87,8 +87,22 @@ def lib():
         L.rpp_debug_sample_plan.argtypes = [cl, ci, cl, ci, ctypes.POINTER(ci)]
         L.rpp_debug_stage_timing.argtypes = [vp, ci]
         L.rpp_debug_stage_ms.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ci)]
+        L.rpp_debug_stage_report.argtypes = [vp, ctypes.c_char_p, ci, ctypes.POINTER(ci)]
         _lib = L
     return _lib
+
+
+def stage_report(handle_ptr):
+    """{label: mean ms per call} of the segments recorded since rpp_debug_stage_timing(handle, 1), and the call count."""
+    buf = ctypes.create_string_buffer(4096)
+    n = ctypes.c_int()
+    check(lib().rpp_debug_stage_report(handle_ptr, buf, len(buf), ctypes.byref(n)))
+    out = {}
+    for item in buf.value.decode().split(';'):
+        if item:
+            k, v = item.rsplit('=', 1)
+            out[k] = float(v)
+    return out, int(n.value)
 
 
 def last_error():

@@ -104,13 +104,20 @@ class _Handle:
         self._ws = {}
 
     def workspace(self, B, n, device):
-        key = (int(B), int(n), str(device))
+        """Workspace tensor for calls of this geometry on the CURRENT stream.  One tensor per (B, n, device, stream)
+        is kept for the life of the handle: a CUDA graph captured from a call bakes the tensor's address in, and two
+        streams must not share scratch memory, so an entry is never replaced or handed to another stream
+        (`release_workspaces()` frees them all when no captured graph is alive)."""
+        key = (int(B), int(n), str(device), int(torch.cuda.current_stream(device).cuda_stream))
         ws = self._ws.get(key)
         if ws is None:
             nbytes = int(_native.lib().rpp_workspace_bytes(self.ptr, int(B), int(n)))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            self._ws = {key: ws}   # keep one
+            self._ws[key] = ws
         return ws
+
+    def release_workspaces(self):
+        self._ws = {}
 
     def outputs(self, B, device):
         M = self.max_detections
@@ -439,9 +446,17 @@ class FusedPostProcessing(Layer):
                 self.call(predictions)
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
+        before = {id(h): set(h._ws) for h in self._handles.values()}
         with torch.cuda.graph(graph):
+            # the workspace this call uses is allocated here, inside the capture, from the graph's private pool (its
+            # cache key carries the capture stream): no later eager call can evict or reuse it
             outputs = self.call(predictions)
-        return graph.replay, outputs
+        # ... and it is owned by the replay closure from here on, so that it lives exactly as long as the graph
+        pinned = [h._ws.pop(k) for h in self._handles.values() for k in set(h._ws) - before.get(id(h), set())]
+
+        def replay(_graph=graph, _inputs=predictions, _pinned=pinned):
+            _graph.replay()
+        return replay, outputs
 
     _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 

@@ -1,0 +1,134 @@
+"""Global* modes behind the global filter (rpp_global.cuh: rows resolved from the sorted keys, block-parallel soft NMS)
+against the CPU oracle: full-size trained-detector-like inputs, duplicate-heavy rows, ties, the k > 8192 fallback to
+the generic problem kernel, thresholds that empty the queue, and flat axes that are not a multiple of four."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from _util import image_mismatches, make_params, oracle_detect, to_numpy
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+sys.path.insert(0, ROOT)
+
+
+def _run(ref, p, logits, deltas):
+    from retinanet.model.layers import FusedPostProcessing
+    layer = FusedPostProcessing(p)
+    got = to_numpy(layer({'class_logits': torch.from_numpy(logits).cuda(),
+                          'encoded_boxes': torch.from_numpy(deltas).cuda()}))
+    exp = oracle_detect(ref, p, logits, deltas, threads=8)
+    return got, exp
+
+
+def _anchors(ref, p):
+    H, W = p.input.input_shape
+    ap = p.anchor_params
+    return ref.anchors(H, W, 3, 7, ap.areas, ap.aspect_ratios, ap.scales)[0]
+
+
+@pytest.mark.parametrize('mode', ['GlobalSoftNMS', 'GlobalHardNMS'])
+@pytest.mark.parametrize('dist', ['clustered', 'dense', 'sparse'])
+def test_full_size_640_c80(ref, mode, dist):
+    """BASELINE configs[2] geometry, every image of a 6-image batch."""
+    from tools import synth_inputs
+    p = make_params(640, num_classes=80, mode=mode, pre_nms_top_k=5000, filter_per_class=False)
+    anchors = torch.from_numpy(_anchors(ref, p))
+    lg, dl = synth_inputs.make_inputs(dist, 6, anchors, 80, 640, 640, 'cpu', seed_logits=7, seed_deltas=8)
+    got, exp = _run(ref, p, lg.numpy(), dl.numpy())
+    assert image_mismatches(got, exp) == []
+
+
+@pytest.mark.parametrize('mode', ['GlobalSoftNMS', 'GlobalHardNMS'])
+@pytest.mark.parametrize('H,C,k', [(320, 5, 5000), (320, 5, 333), (128, 3, 1000), (96, 1, 100), (192, 2, 8192),
+                                   (192, 7, 9000)])
+def test_odd_flat_axes_duplicates_and_big_k(ref, mode, H, C, k):
+    """N*C not a multiple of 4 (320^2 x 5 classes: 96 030), few classes (many duplicate anchors among the k best
+    pairs), k at and beyond the soft kernel's 8192-row limit (generic fallback)."""
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=k, filter_per_class=False, max_detections=100)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(H * 131 + C * 7 + k)
+    logits = rng.standard_normal((3, N, C)).astype(np.float32)
+    logits[:, :, 0] += 0.5 * logits[:, :, -1]          # correlated classes -> several classes of one anchor in the top k
+    deltas = np.clip(rng.standard_normal((3, N, 4)) * 0.3, -4, 4).astype(np.float32)
+    got, exp = _run(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
+
+
+@pytest.mark.parametrize('inf', [
+    dict(score_threshold=0.6, soft_nms_sigma=0.1),      # decayed scores fall to the threshold: the queue drains
+    dict(score_threshold=0.0, soft_nms_sigma=1.5, max_detections=300),
+    dict(score_threshold=0.05, soft_nms_sigma=0.5, max_detections=1),
+    dict(score_threshold=0.3, soft_nms_sigma=0.5, max_detections=1000, pre_nms_top_k=3000),
+    dict(score_threshold=0.999, soft_nms_sigma=0.5),    # (almost) nothing above the threshold
+])
+def test_soft_parameter_edges(ref, inf):
+    p = make_params(320, num_classes=12, mode='GlobalSoftNMS', filter_per_class=False,
+                    **dict(dict(pre_nms_top_k=5000), **inf))
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(99)
+    logits = (rng.standard_normal((4, N, 12)) * 1.5 - 1.0).astype(np.float32)
+    deltas = np.clip(rng.standard_normal((4, N, 4)) * 0.2, -4, 4).astype(np.float32)   # small deltas: heavy overlap
+    got, exp = _run(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
+
+
+def test_soft_heavy_overlap_and_ties(ref):
+    """Every candidate overlaps every other (tiny deltas on few anchors' worth of boxes) and scores come from a
+    coarse grid: long rounds (hundreds of visits before the next selection), exact score ties broken by row index."""
+    p = make_params(128, num_classes=4, mode='GlobalSoftNMS', filter_per_class=False, pre_nms_top_k=5000,
+                    max_detections=100, soft_nms_sigma=0.5, score_threshold=0.05)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(5)
+    logits = (np.round(rng.standard_normal((3, N, 4)) * 4) / 4).astype(np.float32)
+    deltas = (rng.standard_normal((3, N, 4)) * 0.02).astype(np.float32)
+    got, exp = _run(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
+
+
+def test_old_tf_soft_form_global(ref):
+    """soft_ignores_iou_threshold = False (TF <= 2.2 kernel form): overlaps above the IoU threshold drop the box."""
+    from retinanet.model.layers import FusedPostProcessing
+    p = make_params(192, num_classes=6, mode='GlobalSoftNMS', filter_per_class=False, pre_nms_top_k=2000)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(17)
+    logits = rng.standard_normal((2, N, 6)).astype(np.float32)
+    deltas = (rng.standard_normal((2, N, 4)) * 0.1).astype(np.float32)
+    layer = FusedPostProcessing(p)
+    h = layer.handle(6)
+    # the flag is a handle property: rebuild the handle with it off
+    from retinanet.model.layers.postprocessing_ops import _Handle
+    inf = p.inference
+    h2 = _Handle(H=192, W=192, min_level=3, max_level=7, num_classes=6, anchor_params=p.anchor_params,
+                 mode=inf.mode, iou_threshold=inf.iou_threshold, score_threshold=inf.score_threshold,
+                 soft_nms_sigma=inf.soft_nms_sigma, pre_nms_top_k=inf.pre_nms_top_k, filter_per_class=False,
+                 max_detections=inf.max_detections, soft_ignores_iou_threshold=False)
+    layer._handles[(6, torch.cuda.current_device())] = h2
+    h.close()
+    got = to_numpy(layer({'class_logits': torch.from_numpy(logits).cuda(),
+                          'encoded_boxes': torch.from_numpy(deltas).cuda()}))
+    exp = oracle_detect(ref, p, logits, deltas, threads=8, soft_ignores_iou_threshold=False)
+    assert image_mismatches(got, exp) == []
+
+
+def test_unaligned_flat_tensor(ref):
+    """A logit tensor whose base is only 4-byte aligned (a slice of a larger buffer): the flat collect and sample
+    kernels realign their 128-bit loads."""
+    from retinanet.model.layers import FusedPostProcessing
+    p = make_params(320, num_classes=5, mode='GlobalHardNMS', filter_per_class=False, pre_nms_top_k=5000)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(3)
+    logits = rng.standard_normal((2, N, 5)).astype(np.float32)
+    deltas = np.clip(rng.standard_normal((2, N, 4)) * 0.5, -4, 4).astype(np.float32)
+    exp = oracle_detect(ref, p, logits, deltas, threads=8)
+    layer = FusedPostProcessing(p)
+    for lead in (1, 2, 3):
+        buf = torch.zeros(logits.size + 8, dtype=torch.float32, device='cuda')
+        view = buf[lead:lead + logits.size].view(logits.shape)
+        view.copy_(torch.from_numpy(logits))
+        assert view.data_ptr() % 16 == 4 * lead
+        got = to_numpy(layer({'class_logits': view, 'encoded_boxes': torch.from_numpy(deltas).cuda()}))
+        assert image_mismatches(got, exp) == [], lead
