@@ -40,6 +40,14 @@ int fail(int code, const char* fmt, ...) {
                                         cudaGetErrorString(e__));                                  \
   } while (0)
 
+// Candidate list capacity per problem of a sampled plan (env RPP_LIST_CAP, default 8192): a column whose population
+// above the score threshold is at most ~0.7 of it is collected whole (see make_plan's complete-list rule).
+static int kListCap = [] {
+  const char* v = getenv("RPP_LIST_CAP");
+  const int c = v ? atoi(v) : 8192;
+  return c >= 1024 && c <= 65536 ? c : 8192;
+}();
+
 struct SamplePlan {
   bool on;
   int stride, G, lanes, rows_per_group, rank;
@@ -149,7 +157,7 @@ SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
   s.lanes = lanes;
   s.rows_per_group = (int)g;
   s.rank = rank;
-  s.CAP = 4096;
+  s.CAP = kListCap;
   // complete-list rule: a column with at most ~0.7 * CAP elements above the score threshold is collected whole
   // (threshold = T_min).  Such a column leaves a fraction q0 = (1 - 0.7 CAP / n)^g of the groups without any element
   // above T_min; with a true population of CAP the expected fraction is far lower (> 3 sigma at G = 96), and an

@@ -135,6 +135,116 @@ __device__ __forceinline__ void bitonic_sort_desc(u64* k, int P2) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Descending sort of exactly 8192 u64 keys in shared memory by a 1024-thread block: the same bitonic network as
+// bitonic_sort_desc, but a thread keeps 8 keys in registers and most compare-exchange steps never touch shared memory.
+// An element index has 13 bits.  Two register layouts:
+//   A: bits 5-7 = register, bits 0-4 = lane, bits 8-12 = warp   -> steps j = 32..128 in registers, j = 1..16 by shuffle
+//   C: bits 8-10 = register, bits 0-2 + 11-12 = lane, bits 3-7 = warp -> j = 256..1024 in registers, 2048 / 4096 by shuffle
+// A merge phase of size >= 512 starts in C and finishes in A; the layouts are exchanged through the array itself
+// (10 exchanges instead of 91 shared-memory passes with a barrier each).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cx_keep(u64& mine, u64 other, bool take_max) {
+  const bool other_gt = other > mine;
+  if (take_max == other_gt) mine = other;
+}
+
+template <bool LAYOUT_C>
+__device__ __forceinline__ int sort8k_elem(int r, int lane, int warp) {
+  return LAYOUT_C ? ((lane & 7) | (warp << 3) | (r << 8) | ((lane >> 3) << 11)) : ((warp << 8) | (r << 5) | lane);
+}
+
+template <bool LAYOUT_C, int SIZE, int J>
+__device__ __forceinline__ void sort8k_step(u64 (&k)[8], int lane, int warp) {
+  constexpr int REG_LO = LAYOUT_C ? 256 : 32;          // smallest stride held in registers
+  if (J >= REG_LO && J < REG_LO * 8) {
+    constexpr int m = (J / REG_LO) & 7;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r & m) continue;
+      const int e = sort8k_elem<LAYOUT_C>(r, lane, warp);
+      const bool desc = (e & SIZE) == 0;
+      const u64 a = k[r], b = k[r | m];
+      if (desc ? (a < b) : (a > b)) { k[r] = b; k[r | m] = a; }
+    }
+  } else {
+    constexpr int lx = LAYOUT_C ? ((J >> 11) << 3) : J;   // lane bit of the partner
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const u64 other = __shfl_xor_sync(RPP_FULL_MASK, k[r], lx);
+      const int e = sort8k_elem<LAYOUT_C>(r, lane, warp);
+      const bool desc = (e & SIZE) == 0;
+      const bool lower = (lane & lx) == 0;
+      cx_keep(k[r], other, desc == lower);
+    }
+  }
+}
+
+template <bool LAYOUT_C>
+__device__ __forceinline__ void sort8k_load(u64 (&k)[8], const u64* a, int lane, int warp) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) k[r] = a[sort8k_elem<LAYOUT_C>(r, lane, warp)];
+}
+template <bool LAYOUT_C>
+__device__ __forceinline__ void sort8k_store(const u64 (&k)[8], u64* a, int lane, int warp) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) a[sort8k_elem<LAYOUT_C>(r, lane, warp)] = k[r];
+}
+
+template <int SIZE>
+__device__ __forceinline__ void sort8k_phase_low(u64 (&k)[8], int lane, int warp) {   // steps j = min(SIZE/2, 128) .. 1
+  if (SIZE > 128) sort8k_step<false, SIZE, 128>(k, lane, warp);
+  if (SIZE > 64) sort8k_step<false, SIZE, 64>(k, lane, warp);
+  if (SIZE > 32) sort8k_step<false, SIZE, 32>(k, lane, warp);
+  if (SIZE > 16) sort8k_step<false, SIZE, 16>(k, lane, warp);
+  if (SIZE > 8) sort8k_step<false, SIZE, 8>(k, lane, warp);
+  if (SIZE > 4) sort8k_step<false, SIZE, 4>(k, lane, warp);
+  if (SIZE > 2) sort8k_step<false, SIZE, 2>(k, lane, warp);
+  sort8k_step<false, SIZE, 1>(k, lane, warp);
+}
+
+template <int SIZE>
+__device__ __forceinline__ void sort8k_phase_high(u64 (&k)[8], u64* a, int lane, int warp) {   // SIZE >= 512
+  __syncthreads();
+  sort8k_store<false>(k, a, lane, warp);
+  __syncthreads();
+  sort8k_load<true>(k, a, lane, warp);
+  if (SIZE > 4096) sort8k_step<true, SIZE, 4096>(k, lane, warp);
+  if (SIZE > 2048) sort8k_step<true, SIZE, 2048>(k, lane, warp);
+  if (SIZE > 1024) sort8k_step<true, SIZE, 1024>(k, lane, warp);
+  if (SIZE > 512) sort8k_step<true, SIZE, 512>(k, lane, warp);
+  sort8k_step<true, SIZE, 256>(k, lane, warp);
+  __syncthreads();
+  sort8k_store<true>(k, a, lane, warp);
+  __syncthreads();
+  sort8k_load<false>(k, a, lane, warp);
+  sort8k_phase_low<SIZE>(k, lane, warp);
+}
+
+// All 1024 threads call; a[0 .. 8192) valid (pad with 0 = "no key": zeros sink to the end).
+__device__ __noinline__ void block_sort8k_desc(u64* a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  u64 k[8];
+  sort8k_load<false>(k, a, lane, warp);
+  sort8k_phase_low<2>(k, lane, warp);
+  sort8k_phase_low<4>(k, lane, warp);
+  sort8k_phase_low<8>(k, lane, warp);
+  sort8k_phase_low<16>(k, lane, warp);
+  sort8k_phase_low<32>(k, lane, warp);
+  sort8k_phase_low<64>(k, lane, warp);
+  sort8k_phase_low<128>(k, lane, warp);
+  sort8k_phase_low<256>(k, lane, warp);
+  sort8k_phase_high<512>(k, a, lane, warp);
+  sort8k_phase_high<1024>(k, a, lane, warp);
+  sort8k_phase_high<2048>(k, a, lane, warp);
+  sort8k_phase_high<4096>(k, a, lane, warp);
+  sort8k_phase_high<8192>(k, a, lane, warp);
+  __syncthreads();
+  sort8k_store<false>(k, a, lane, warp);
+  __syncthreads();
+}
+
 __device__ __forceinline__ int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;

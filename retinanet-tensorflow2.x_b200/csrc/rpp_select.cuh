@@ -28,6 +28,9 @@ struct SelectScratch {
 // Returns m in [0, CC]: chunk[0..m) = the m largest keys of {key(i) : 0 < key(i) < KB}, sorted descending; KB is
 // lowered to the smallest key returned.  m == 0 <=> the domain holds no key below KB.  m >= min(want/4, remaining).
 // All threads of the block must call; chunk must hold next_pow2(CC) keys (CC keys when sort == false).
+#ifndef RPP_SELECT_UNROLL
+#define RPP_SELECT_UNROLL 8   // independent key loads in flight per thread (the sources are L2 / HBM resident lists and columns)
+#endif
 template <int NT, class KeyFn>
 __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int CC, SelectScratch<NT>* sc,
                             bool sort = true, u32* population = nullptr) {
@@ -35,12 +38,13 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
   // pass 1: population below the bound
   u32 cnt = 0;
   u64 mx = 0ull, mn = ~0ull;
-  for (int i0 = tid; i0 < n; i0 += 4 * NT) {   // 4 independent key loads in flight per thread
-    u64 k4[4];
+  constexpr int U = RPP_SELECT_UNROLL;
+  for (int i0 = tid; i0 < n; i0 += U * NT) {   // U independent key loads in flight per thread
+    u64 k4[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
+    for (int u = 0; u < U; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const u64 k = k4[u];
       if (k != 0ull && k < KB) { ++cnt; mx = k > mx ? k : mx; mn = k < mn ? k : mn; }
     }
@@ -66,12 +70,12 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
       const int nb = 1 << bits;
       for (int i = tid; i < nb; i += NT) sc->hist[i] = 0;
       __syncthreads();
-      for (int i0 = tid; i0 < n; i0 += 4 * NT) {
-        u64 k4[4];
+      for (int i0 = tid; i0 < n; i0 += U * NT) {
+        u64 k4[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
+        for (int u = 0; u < U; ++u) k4[u] = i0 + u * NT < n ? key(i0 + u * NT) : 0ull;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const u64 k = k4[u];
           if (k != 0ull && k < KB && k >= base && (top_shift >= 64 || ((k - base) >> top_shift) == 0ull))
             atomicAdd(&sc->hist[(u32)((k - base) >> shift)], 1u);
@@ -130,15 +134,15 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
   {
     const int lane = tid & 31;
     const u32 lt = (1u << lane) - 1u;
-    for (int base = 0; base < n; base += 4 * NT) {   // uniform trip count: every lane takes part in the ballots
-      u64 k4[4];
+    for (int base = 0; base < n; base += U * NT) {   // uniform trip count: every lane takes part in the ballots
+      u64 k4[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int i = base + u * NT + tid;
         k4[u] = i < n ? key(i) : 0ull;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const u64 k = k4[u];
         const bool hit = k != 0ull && k < KB && k >= lo;
         const u32 mask = __ballot_sync(RPP_FULL_MASK, hit);
@@ -156,10 +160,14 @@ __device__ int select_chunk(KeyFn key, int n, u64& KB, int want, u64* chunk, int
   __syncthreads();
   int m = (int)sc->m;
   if (m > CC) m = CC;  // cannot happen (the cut guarantees <= CC); defensive
-  const int P2 = next_pow2(m < 2 ? 2 : m);
+  int P2 = next_pow2(m < 2 ? 2 : m);
+  // large chunks of a 1024-thread block (top-k emission): the register / shuffle sort of exactly 8192 slots
+  const bool big = sort && NT == 1024 && CC >= 8192 && P2 > 2048;
+  if (big) P2 = 8192;
   for (int i = m + tid; i < P2; i += NT) chunk[i] = 0ull;
   __syncthreads();
-  if (sort) bitonic_sort_desc<NT>(chunk, P2);
+  if (big) block_sort8k_desc(chunk);
+  else if (sort) bitonic_sort_desc<NT>(chunk, P2);
   KB = lo;
   return m;
 }
