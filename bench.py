@@ -245,6 +245,15 @@ def workload_config(wl, batch_per_gpu, dist, n_gpus, scaling):
 # ---------------------------------------------------------------------------------------------------------------
 # GPU legs
 # ---------------------------------------------------------------------------------------------------------------
+def note(rank, msg):
+    """Progress marker on stderr (a stuck run then shows where it stopped)."""
+    sys.stderr.write('[bench rank {} +{:.1f}s] {}\n'.format(rank, time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 class Bench:
     def __init__(self, args, rank, local_rank, world):
         import torch
@@ -252,6 +261,7 @@ class Bench:
         from retinanet import _native
         self.torch, self.dist, self.native = torch, dist, _native
         self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        local_rank = local_rank % torch.cuda.device_count()   # (debug runs: several ranks on one GPU over gloo)
         torch.cuda.set_device(local_rank)
         self.dev = torch.device('cuda', local_rank)
         self.L = _native.lib()
@@ -400,8 +410,13 @@ def run_ours(args, rank, local_rank, world):
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
     except Exception:
         pass
+    local_rank = local_rank % torch.cuda.device_count()
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        backend = os.environ.get('BENCH_DIST_BACKEND', 'nccl')   # gloo: debug runs with several ranks on one GPU
+        if backend == 'nccl':
+            dist.init_process_group('nccl', device_id=dev)
+        else:
+            dist.init_process_group(backend)
 
     key = args.workload
     wl = WORKLOADS[key]
@@ -425,6 +440,7 @@ def run_ours(args, rank, local_rank, world):
     flush = B * bpi < 190e6
     steps, warmup = args.steps, max(args.warmup, 3)
 
+    note(rank, 'headline {}: inputs'.format(key))
     # two distinct input sets, replayed alternately (so that the number is not the property of one tensor)
     xs = [bn.inputs(wl, params, B, args.logits, seed_offset=rank + 100 * i) for i in range(1 if flush else 2)]
     for _ in range(warmup):
@@ -432,7 +448,9 @@ def run_ours(args, rank, local_rank, world):
             out = layer(x)
     launches_per_step = int(L.rpp_last_launch_count())
     bn.barrier()
+    note(rank, 'eager timing')
     ms_eager = bn.time_steps([lambda x=x: layer(x) for x in xs], steps, flush)
+    note(rank, 'graph capture + timed region')
     replays = []
     for x in xs:
         rp, og = layer.capture(x)
@@ -452,6 +470,7 @@ def run_ours(args, rank, local_rank, world):
     ms_step = bn.max_over_ranks(ms_step_local)
     value = global_batch / (ms_step * 1e-3)
 
+    note(rank, 'stage timing')
     # per-stage times: a second K-step pass with CUDA events at the stage boundaries on the launch stream
     rep, ncalls = bn.stages(layer, h, xs[0], steps)
     collect_ms = sum(v for k, v in rep.items() if k.startswith('collect') or k.startswith('emit:collect'))
@@ -462,6 +481,7 @@ def run_ours(args, rank, local_rank, world):
     if key == 'c2' and not args.quick:
         # the same step fed with the model-side input of the path, the per-level NHWC head outputs (views of the
         # layout a detector emits): consumed in place (rpp_detect_levels) vs the reference's FuseDetections concat
+        note(rank, 'head levels / half precision / worst case')
         from retinanet.model.builder import ModelBuilder
         bounds = [0, 57600, 72000, 75600, 76500, 76725]
         heads = {'class-predictions': {}, 'box-predictions': {}}
@@ -523,6 +543,7 @@ def run_ours(args, rank, local_rank, world):
     # ---- end to end: pinned host buffers -> rpp_detect_host -> host outputs ------------------------------------
     e2e = None
     if not args.quick:
+        note(rank, 'end to end')
         e2e_steps = max(1, min(steps, 10))
         h_logits = torch.empty(logits.shape, dtype=torch.float32, pin_memory=True).copy_(logits)
         h_deltas = torch.empty(deltas.shape, dtype=torch.float32, pin_memory=True).copy_(deltas)
@@ -593,6 +614,7 @@ def run_ours(args, rank, local_rank, world):
         from retinanet.distributed import shard_range
         strong = {}
         for k2 in ('c3', 'c4'):
+            note(rank, 'strong scaling {}'.format(k2))
             w2 = WORKLOADS[k2]
             p2 = workload_params(w2)
             lay = FusedPostProcessing(p2)
@@ -633,7 +655,9 @@ def run_ours(args, rank, local_rank, world):
         configs = {}
         csteps = max(5, min(steps, 20))
         for k2 in ('c1', 'c3', 'c4', 'c5', 'c2s'):
+            note(rank, 'config {}'.format(k2))
             configs[k2] = bn.config_row(k2, WORKLOADS[k2]['batch'], csteps, args.check)
+        note(rank, 'config c2 (parity, sparse, clustered)')
         # the headline config's own parity counts + its sparse / clustered throughput
         configs['c2'] = bn.config_row('c2', B, csteps, args.check, timed_dists=('sparse', 'clustered'))
 
@@ -683,6 +707,7 @@ def run_ours(args, rank, local_rank, world):
         threads = ref.hardware_threads()
         sample = 16 if H <= 640 else 4
         dname = args.logits if args.logits != 'clustered' else 'dense'
+        note(rank, 'cpu baseline')
         rate, ms_pass, passes = cpu_oracle_rate(wl, sample, dname, threads, 12.0, 40)
         line['cpu_baseline'] = {
             'value': rate, 'unit': 'images/s', 'cores': threads, 'kind': 'port',

@@ -219,6 +219,9 @@ __device__ void gs_ring_shift_insert(GlobalSoftShared* sh, u64* ring, int mask) 
   const int head = sh->head, cnt = sh->cnt;
   // from the tail, in slabs of one element per thread: element p moves to p + #{i : pos[i] <= p}
   const int first = (int)sh->pos[0];
+  // nothing to move (every new key lands behind the ring): the barrier the slab loop would have provided — every
+  // thread has read the ring state above before thread 0 updates the count below
+  if (cnt <= first) __syncthreads();
   for (int hi = cnt; hi > first; hi -= RPP_GS_NT) {
     const int p = hi - 1 - tid;
     u64 v = 0ull;
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams
       // prefix, sorts the keys that re-enter the ring and finds their positions, all without a block barrier ---------
       if (tid < 32) {
         const int cnt0 = cnt;
-        const int nsel = sh->nsel;
+        const int nsel = sh->nsel, head0 = sh->head;   // (read by every lane before lane 0 updates them below)
         const u64 st = lane < batch ? sh->stale[lane] : 0ull;
         const u64 fr = lane < batch ? sh->fresh[lane] : 0ull;
         u64 incl = fr;                        // inclusive prefix maximum of the re-scored keys
@@ -520,11 +523,12 @@ __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams
           stay += gt && l >= cut;
         }
         const int m = __popc(__ballot_sync(RPP_FULL_MASK, mine != 0ull));
-        const int head2 = (sh->head + cut) & mask, cnt2 = cnt0 - cut;
+        const int head2 = (head0 + cut) & mask, cnt2 = cnt0 - cut;
         if (mine != 0ull) {
           sh->ins[rank] = mine;
           sh->pos[rank] = sh->pos16[lane] + (u32)stay;
         }
+        __syncwarp();
         if (lane == 0) {
           sh->n_ins = m; sh->head = head2; sh->cnt = cnt2;
           sh->cut = cut; sh->winner = winner;

@@ -605,10 +605,11 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
         const bool ok = s > P.score_threshold && (list_complete || s > s_edge);
         keys[i] = ok ? make_key(s, e.y) : 0ull;
       }
-      // long lists are converted in place (global memory): remember it for the finish pass
-      if (keys == gkeys && tid == 0) P.cand_count[p] = n_raw | 0x80000000u;
     }
     __syncthreads();
+    // long lists are converted in place (global memory): remember it for the finish pass.  (After the barrier: every
+    // thread has derived `converted` from the count word by now.)
+    if (!converted && keys == gkeys && tid == 0) P.cand_count[p] = n_raw | 0x80000000u;
     u64 KB = KB_A;
     int want = want0;
     while (!sh->done && consumed < P.k_lim) {
