@@ -1,6 +1,7 @@
 // rpp_api.cu — C ABI of libretinapost.so (include/retinapost.h): handle, workspace layout and kernel launches.
 // Host logic only; every result is computed by the kernels in rpp_kernels.cuh.  There is no CPU compute path.
 #include <algorithm>
+#include <numeric>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -35,7 +36,7 @@ int fail(int code, const char* fmt, ...) {
 #define LAUNCHED()                                                                                 \
   do {                                                                                             \
     ++g_launches;                                                                                  \
-    cudaError_t e__ = cudaPeekAtLastError();                                                       \
+    cudaError_t e__ = cudaGetLastError();   /* (clears it: a failed launch must not poison later checks) */ \
     if (e__ != cudaSuccess) return fail(RPP_ECUDA, "kernel launch (%s:%d): %s", __FILE__, __LINE__, \
                                         cudaGetErrorString(e__));                                  \
   } while (0)
@@ -337,10 +338,13 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   // Unsampled SCORE columns (dense stage inputs of a few thousand rows): a list would just be a copy of the column,
   // so the problem kernel scans the column itself (its "exact scan" phase costs no sigmoid on scores).
   const bool scan_only = h->force_scan || (!plan.on && !ps.is_logit && !emit);
+  // the vectorised column collects stage RPP_STAGE_CAP hits per class in shared memory: ~520 bytes per class
+  const bool stage_fits = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32) <= 200 * 1024;
   if (!scan_only) {
     if (lv.dtype != RPP_DT_F32) {
-      if (C % 8 != 0 || !aligned || C / 8 > RPP_COLLECT_NT)
-        return fail(RPP_EINVAL, "16-bit logits need num_classes % 8 == 0 and 16-byte aligned tensors");
+      if (C % 8 != 0 || !aligned || C / 8 > RPP_COLLECT_NT || !stage_fits)
+        return fail(RPP_EINVAL, "16-bit logits need num_classes % 8 == 0 (at most 392 classes) and 16-byte aligned "
+                                "tensors; convert to fp32 otherwise");
       const int C8 = C / 8;
       const int lanes = RPP_COLLECT_NT / C8;
       const int UNROLL = h->half_variant == 1 ? 8 : 4;
@@ -366,7 +370,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       }
 #undef RPP_LAUNCH_HALF
       LAUNCHED();
-    } else if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT) {
+    } else if (C % 4 == 0 && aligned && C / 4 <= RPP_COLLECT_NT && stage_fits) {
       const int C4 = C / 4;
       const int lanes = RPP_COLLECT_NT / C4;
       const int UNROLL = h->collect_variant == 2 ? 8 : 4;
@@ -411,7 +415,8 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
 #undef RPP_LAUNCH_COLLECT
       LAUNCHED();
     } else if (lv.L > 1) {
-      return fail(RPP_EINVAL, "per-level inputs need num_classes % 4 == 0 and 16-byte aligned level tensors");
+      return fail(RPP_EINVAL, "per-level inputs need num_classes % 4 == 0 (at most 392 classes) and 16-byte aligned "
+                              "level tensors; fuse them and call rpp_detect otherwise");
     } else if (C == 1) {
       // single column, any n and any (4-byte) alignment: the batch as one flat array of 128-bit words
       const int lead = (int)(((uintptr_t)ps.x % 16) / 4);
@@ -431,6 +436,25 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
       collect_flat_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>(ps.x - lead, lead, T, cand_count, cand, plan.CAP,
                                                                        B, n, tile_elems, n_tiles, tile_counter);
+      LAUNCHED();
+    } else if (C > 1 && aligned && stage_fits && C / std::__gcd(C, 4) <= RPP_COLLECT_NT && (double)n * C < 2147483647.0) {
+      // any num_classes: flat 128-bit words with a class-phase-preserving stride (collect_colsv_kernel)
+      const int UNROLL = 4;
+      const int Cq = C / std::__gcd(C, 4);
+      const int S = RPP_COLLECT_NT / Cq * Cq;
+      const long unit = (long)S * UNROLL;                           // words per block-wide load round
+      long rows_per_tile = plan.on ? (long)(24.0 * n / target) : 4L * unit * 4 / C + 1;
+      long tile_f4 = std::max(unit, (rows_per_tile * C / 4 + unit - 1) / unit * unit);
+      const long total_f4 = ((long)B * n * C) / 4;
+      {
+        const long want_tiles = 4L * h->sm_count * 3;
+        while (tile_f4 > unit && (total_f4 + tile_f4 - 1) / tile_f4 < want_tiles) tile_f4 -= unit;
+      }
+      const long n_tiles = std::max<long>(1, (total_f4 + tile_f4 - 1) / tile_f4);
+      const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
+      const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
+      collect_colsv_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(ps.x, T, cand_count, cand, plan.CAP, B, n, C, S,
+                                                                         tile_f4, n_tiles, tile_counter);
       LAUNCHED();
     } else {
       const size_t tot = (size_t)B * n * C;
@@ -1054,6 +1078,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(collect_cols8_half_kernel<8, RPP_DT_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_levels_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(collect_colsv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   return RPP_OK;
   }();

@@ -438,6 +438,117 @@ collect_flat_kernel(const float* __restrict__ x /*16-byte aligned; element `lead
   }
 }
 
+// Any-C variant of the column collect (num_classes % 4 != 0, e.g. 91-class or 5-class heads; fp32, fused tensor):
+// the batch is one flat array of 128-bit words again, and the word stride between a thread's consecutive loads is a
+// multiple S of C / gcd(C, 4), so the classes of a thread's four components never change ("phase invariance"): its
+// four thresholds stay in registers for a whole image segment, exactly as in collect_cols4_kernel.  Tiles start at
+// multiples of S words; a tile that straddles an image boundary is processed one image segment at a time, the <= 3
+// elements at each ragged segment edge with scalar loads.  Staging and flush as in collect_cols4_kernel.
+template <int UNROLL>
+__global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
+collect_colsv_kernel(const float* __restrict__ x /*[B*N*C], 16-byte aligned*/, const float* __restrict__ T /*[B*C]*/,
+                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C,
+                     int S /*threads that load: 4 * S % C == 0*/, long tile_f4 /*multiple of S * UNROLL*/, long n_tiles,
+                     u32* __restrict__ tile_counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);   // [C][RPP_STAGE_CAP]
+  u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);
+  u32* s_base = s_cnt + C;
+  __shared__ long s_tile;
+  __shared__ u32 s_span;
+  const int tid = threadIdx.x;
+  const long NC = N * (long)C;
+  const long total = (long)B * NC;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  int cls[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cls[i] = (int)((4L * tid + i) % C);
+  auto stage_hit = [&](size_t pbase, int c, float val, u32 row) {
+    const u32 slot = atomicAdd(&s_cnt[c], 1u);
+    if (slot < RPP_STAGE_CAP) s_stage[c * RPP_STAGE_CAP + slot] = make_uint2(__float_as_uint(val), row);
+    else append_cand(cand_count, cand, CAP, pbase + c, val, row);
+  };
+  for (;;) {
+    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
+    for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+    if (tid == 0) s_span = 0u;
+    __syncthreads();
+    const long tile = s_tile;
+    if (tile >= n_tiles) break;
+    const long f0 = tile * tile_f4;
+    const long e0 = 4 * f0;
+    long e1 = e0 + 4 * tile_f4;
+    if (e1 > total || tile == n_tiles - 1) e1 = total;          // (the last tile also takes the <= 3 tail elements)
+    for (long b = e0 / NC; b < B && b * NC < e1; ++b) {
+      const long ibase = b * NC;
+      const long seg_lo = e0 > ibase ? e0 : ibase;
+      const long seg_hi = e1 < ibase + NC ? e1 : ibase + NC;
+      const size_t pbase = (size_t)b * C;
+      long v_lo = (seg_lo + 3) & ~3L, v_hi = seg_hi & ~3L;
+      if (v_lo > v_hi) v_lo = v_hi = seg_hi;
+      {   // ragged edges
+        const long head = (v_lo < seg_hi ? v_lo : seg_hi) - seg_lo;
+        const long tail = seg_hi - (v_hi > v_lo ? v_hi : v_lo);
+        if (tid < head + tail) {
+          const long e = tid < head ? seg_lo + tid : (v_hi > v_lo ? v_hi : v_lo) + (tid - head);
+          const float v = __ldg(x + e);
+          const long eo = e - ibase;
+          const int c = (int)(eo % C);
+          if (v >= __ldg(T + pbase + c)) stage_hit(pbase, c, v, (u32)(eo / C));
+        }
+      }
+      if (tid < S) {
+        const float t0 = __ldg(T + pbase + cls[0]), t1 = __ldg(T + pbase + cls[1]);
+        const float t2 = __ldg(T + pbase + cls[2]), t3 = __ldg(T + pbase + cls[3]);
+        const long f_lo = v_lo >> 2, f_hi = v_hi >> 2;
+        // this thread's words: f = f0 + tid + it * S (the phase is counted from the tile start)
+        long f = f0 + tid;
+        if (f < f_lo) f += (f_lo - f + S - 1) / S * S;
+        for (; f < f_hi; f += (long)S * UNROLL) {
+          float4 v[UNROLL];
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u) {
+            const long ff = f + (long)u * S;
+            v[u] = ff < f_hi ? ld_stream_f4(x4 + ff) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          }
+          u32 mask = 0u;
+#pragma unroll
+          for (int u = 0; u < UNROLL; ++u)
+            mask |= ((v[u].x >= t0 ? 1u : 0u) | (v[u].y >= t1 ? 2u : 0u) | (v[u].z >= t2 ? 4u : 0u) |
+                     (v[u].w >= t3 ? 8u : 0u)) << (4 * u);
+          while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const long e = (f + (long)(bit >> 2) * S) * 4 + (bit & 3);
+            const float val = __ldg(x + e);   // L1 hit: the line was just loaded by this thread
+            stage_hit(pbase, cls[bit & 3], val, (u32)((e - ibase) / C));
+          }
+        }
+      }
+      __syncthreads();
+      for (int c = tid; c < C; c += RPP_COLLECT_NT) {
+        const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+        s_base[c] = n ? atomicAdd(&cand_count[pbase + c], n) : 0u;
+        if (n) atomicMax(&s_span, n);
+      }
+      __syncthreads();
+      const int span = (int)s_span;
+      for (int e = tid; e < C * span; e += RPP_COLLECT_NT) {
+        const int c = e / span, r = e - c * span;
+        const u32 n = s_cnt[c] < RPP_STAGE_CAP ? s_cnt[c] : RPP_STAGE_CAP;
+        if ((u32)r < n) {
+          const u32 slot = s_base[c] + (u32)r;
+          if (slot < (u32)CAP) cand[(pbase + c) * (size_t)CAP + slot] = s_stage[c * RPP_STAGE_CAP + r];
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
+      if (tid == 0) s_span = 0u;
+      __syncthreads();
+    }
+  }
+}
+
 // generic C (C % 4 != 0, or unaligned base): one element per thread step
 __global__ void collect_cols1_kernel(const float* __restrict__ x, const float* __restrict__ T,
                                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N,

@@ -468,7 +468,7 @@ class FusedPostProcessing(Layer):
             return False
         half = next(iter(dts)) != torch.float32
         C = cls[0].shape[2]
-        return (C % (8 if half else 4) == 0 and not self.mode.startswith('Global')
+        return (C % (8 if half else 4) == 0 and C <= 392 and not self.mode.startswith('Global')
                 and (inf.pre_nms_top_k <= 0 or inf.filter_per_class)
                 and all(t.is_cuda and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in cls + box))
 

@@ -132,3 +132,29 @@ def test_unaligned_flat_tensor(ref):
         assert view.data_ptr() % 16 == 4 * lead
         got = to_numpy(layer({'class_logits': view, 'encoded_boxes': torch.from_numpy(deltas).cuda()}))
         assert image_mismatches(got, exp) == [], lead
+
+
+@pytest.mark.parametrize('mode', ['PerClassHardNMS', 'CombinedNMS', 'PerClassSoftNMS'])
+@pytest.mark.parametrize('H,C,B', [(320, 5, 4), (320, 91, 2), (448, 6, 3), (320, 3, 5), (192, 7, 2)])
+def test_any_class_count_uses_vector_loads(ref, mode, H, C, B):
+    """num_classes % 4 != 0 (5-class custom heads, 91-class COCO heads): collect_colsv_kernel — flat 128-bit words
+    with a class-phase-preserving stride, image boundaries that are not 16-byte aligned, tiles that straddle images."""
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=5000, filter_per_class=True)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(H + 13 * C + B)
+    logits = rng.standard_normal((B, N, C)).astype(np.float32)
+    deltas = np.clip(rng.standard_normal((B, N, 4)) * 0.5, -4, 4).astype(np.float32)
+    got, exp = _run(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
+
+
+def test_many_classes_fall_back_to_the_generic_collect(ref):
+    """num_classes = 512: the per-class stage of the vectorised collect would need more shared memory than an SM has
+    (ADVICE r01): the generic kernel takes over instead of a failed launch."""
+    p = make_params(64, num_classes=512, mode='PerClassHardNMS', pre_nms_top_k=200, filter_per_class=True)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(512)
+    logits = (rng.standard_normal((2, N, 512)) - 2.0).astype(np.float32)
+    deltas = np.clip(rng.standard_normal((2, N, 4)) * 0.5, -4, 4).astype(np.float32)
+    got, exp = _run(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
