@@ -341,7 +341,39 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   // the vectorised column collects stage RPP_STAGE_CAP hits per class in shared memory: ~520 bytes per class
   const bool stage_fits = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32) <= 200 * 1024;
   if (!scan_only) {
-    if (lv.dtype != RPP_DT_F32) {
+    if (C == 1) {
+      // single column (the flat anchors x classes axis, or row maxima), any n and any element alignment, fp32 / f16 /
+      // bf16, fused or in per-level pieces: each piece is one flat array of 128-bit words (collect_flat_kernel)
+      for (int l = 0; l < lv.L; ++l) {
+        const long n_l = lv.off[l + 1] - lv.off[l];
+        const int es = lv.dtype == RPP_DT_F32 ? 4 : 2, EPW = 16 / es;
+        const int lead = (int)(((uintptr_t)lv.x[l] % 16) / es);
+        const char* xa = reinterpret_cast<const char*>(lv.x[l]) - (size_t)lead * es;
+        const int UNROLL = 4;
+        const long unit = (long)RPP_COLLECT_NT * UNROLL * EPW;   // elements per block-wide load round
+        long tile_elems = 4 * unit;
+        if (plan.on) {   // ~a third of the shared queue (RPP_FLAT_QCAP) expected per tile
+          const long want = (long)((RPP_FLAT_QCAP / 3.0) * (double)n / target);
+          tile_elems = std::max(unit, std::min(want / unit * unit, 16 * unit));
+        }
+        const long total = (long)lead + (long)B * n_l;
+        {   // small batches: at least ~4 tiles per resident CTA
+          const long want_tiles = 4L * h->sm_count * 3;
+          while (tile_elems > unit && (total + tile_elems - 1) / tile_elems < want_tiles) tile_elems -= unit;
+        }
+        const long n_tiles = (total + tile_elems - 1) / tile_elems;
+        const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
+        u32* tc = tile_counter + 32 + l;   // (zeroed with the counters by the memset above)
+#define RPP_LAUNCH_FLAT(DT)                                                                                      \
+        collect_flat_kernel<4, DT><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>(xa, lead, (u32)lv.off[l], T, cand_count, \
+                                                                            cand, plan.CAP, B, n_l, tile_elems, n_tiles, tc)
+        if (lv.dtype == RPP_DT_F32) RPP_LAUNCH_FLAT(RPP_DT_F32);
+        else if (lv.dtype == RPP_DT_F16) RPP_LAUNCH_FLAT(RPP_DT_F16);
+        else RPP_LAUNCH_FLAT(RPP_DT_BF16);
+#undef RPP_LAUNCH_FLAT
+        LAUNCHED();
+      }
+    } else if (lv.dtype != RPP_DT_F32) {
       if (C % 8 != 0 || !aligned || C / 8 > RPP_COLLECT_NT || !stage_fits)
         return fail(RPP_EINVAL, "16-bit logits need num_classes % 8 == 0 (at most 392 classes) and 16-byte aligned "
                                 "tensors; convert to fp32 otherwise");
@@ -417,26 +449,6 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     } else if (lv.L > 1) {
       return fail(RPP_EINVAL, "per-level inputs need num_classes % 4 == 0 (at most 392 classes) and 16-byte aligned "
                               "level tensors; fuse them and call rpp_detect otherwise");
-    } else if (C == 1) {
-      // single column, any n and any (4-byte) alignment: the batch as one flat array of 128-bit words
-      const int lead = (int)(((uintptr_t)ps.x % 16) / 4);
-      const int UNROLL = 4;
-      const long unit = (long)RPP_COLLECT_NT * UNROLL * 4;   // elements per block-wide load round (8192)
-      long tile_elems = 4 * unit;
-      if (plan.on) {   // ~a third of the shared queue (RPP_FLAT_QCAP) expected per tile
-        const long want = (long)((RPP_FLAT_QCAP / 3.0) * (double)n / target);
-        tile_elems = std::max(unit, std::min(want / unit * unit, 16 * unit));
-      }
-      const long total = (long)lead + (long)B * n;
-      {   // small batches: at least ~4 tiles per resident CTA
-        const long want_tiles = 4L * h->sm_count * 3;
-        while (tile_elems > unit && (total + tile_elems - 1) / tile_elems < want_tiles) tile_elems -= unit;
-      }
-      const long n_tiles = (total + tile_elems - 1) / tile_elems;
-      const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
-      collect_flat_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>(ps.x - lead, lead, T, cand_count, cand, plan.CAP,
-                                                                       B, n, tile_elems, n_tiles, tile_counter);
-      LAUNCHED();
     } else if (C > 1 && aligned && stage_fits && C / std::__gcd(C, 4) <= RPP_COLLECT_NT && (double)n * C < 2147483647.0) {
       // any num_classes: flat 128-bit words with a class-phase-preserving stride (collect_colsv_kernel)
       const int UNROLL = 4;
@@ -682,7 +694,7 @@ struct GlobalPre {
 // to the logits.
 int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const float4* deltas, const float4* boxes,
                     int B, long n, const Outputs& out, cudaStream_t st, bool score_rowmax = false,
-                    const GlobalPre* pre = nullptr) {
+                    const GlobalPre* pre = nullptr, const Levels* levels = nullptr) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes, M = c.max_detections;
   float* mraw = pre ? const_cast<float*>(pre->mraw) : ar.take<float>((size_t)B * n);
@@ -690,7 +702,9 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
     const size_t rows = (size_t)B * n;
     size_t grid = (rows * 32 + 255) / 256;
     if (grid > (size_t)h->sm_count * 16) grid = (size_t)h->sm_count * 16;
-    if (C <= 16) {
+    if (levels) {   // per-level pieces and / or 16-bit elements, read in place
+      rowmax_levels_kernel<<<(unsigned)grid, 256, 0, st>>>(*levels, n, C, rows, mraw);
+    } else if (C <= 16) {
       size_t g2 = std::min<size_t>((rows + 255) / 256, (size_t)h->sm_count * 16);
       rowmax_small_kernel<<<(unsigned)g2, 256, 0, st>>>(x, rows, C, mraw);
     } else {
@@ -712,6 +726,7 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   ps.x = mraw; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = 1;
   ps.deltas = deltas; ps.boxes = boxes; ps.q = 1;
   if (pre) { ps.row_keys = pre->row_keys; ps.k_rows = n; ps.C_src = C; ps.delta_lv = pre->src; }
+  else if (levels) ps.delta_lv = levels;   // x is the derived [B,n] column; the deltas stay in their pieces
   ps.k_lim = n; ps.M = M; ps.M_lim = M;
   ps.score_threshold = c.score_threshold;
   ps.T_min = is_logit ? h->T_logit : std::nextafter(c.score_threshold, INFINITY);
@@ -735,6 +750,8 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   if (pre) {
     gp.lv = *pre->src;
     gp.row_keys = pre->row_keys; gp.k_rows = n;
+  } else if (levels) {
+    gp.lv = *levels;
   } else {
     gp.lv.L = 1; gp.lv.off[1] = n; gp.lv.x[0] = x; gp.lv.d[0] = deltas;
   }
@@ -750,9 +767,10 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
 
 // Sorted top-k keys of every column of x [B,n,C] (C = 1 with n = rows*classes for the global filter).
 int topk_keys(Handle* h, Arena& ar, const float* x, int is_logit, int B, long n, int C, long k, u64** emit_key,
-              cudaStream_t st) {
+              cudaStream_t st, const Levels* levels = nullptr) {
   ProblemSet ps{};
   ps.x = x; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = C;
+  ps.levels = levels;
   ps.q = 1;
   ps.consumer = RPP_CONSUME_EMIT;
   ps.k_lim = k; ps.M = 1; ps.M_lim = 1;
@@ -800,7 +818,8 @@ int topk_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, i
   return RPP_OK;
 }
 
-// add_post_processing_stage fused: logits + deltas -> detections
+// add_post_processing_stage fused: logits + deltas -> detections.  The inputs are either the fused fp32 tensors
+// (logits / deltas) or `levels`: the per-level pieces and / or 16-bit elements, read where they lie.
 int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* logits, int B, const Outputs& out,
                     cudaStream_t st, const Levels* levels = nullptr) {
   const rpp_config& c = h->cfg;
@@ -808,30 +827,35 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   const long N = h->N;
   const bool filtered = c.pre_nms_top_k > 0;
   const bool per_class = is_per_class_mode(c.mode);
-  if (levels) {
-    if (!per_class || (filtered && !c.filter_per_class) || C % 4 != 0)
-      return fail(RPP_EINVAL, "rpp_detect_levels / rpp_detect_typed cover CombinedNMS / PerClass*NMS with the "
-                              "per-class filter or no filter and num_classes % 4 == 0 (% 8 for 16-bit inputs); "
-                              "fuse / convert and call rpp_detect otherwise");
-    const long k = filtered ? std::min<long>(c.pre_nms_top_k, N) : N;
-    return per_class_pipeline(h, ar, nullptr, 1, nullptr, nullptr, 1, B, N, k, filtered ? 1 : 0, filtered ? 1 : 0, out,
-                              st, levels);
-  }
   if (!per_class && filtered && c.filter_per_class)
     return fail(RPP_ECOMBO, "Global* NMS modes need inference.filter_per_class=false (per-class filtered boxes are "
                             "4-D; the reference fails with a rank error)");
-  if (!filtered)   // TransformBoxesAndScores -> GenerateDetections on all N rows
-    return per_class ? per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, N, 0, 0, out, st)
-                     : global_pipeline(h, ar, logits, 1, deltas, nullptr, B, N, out, st);
+  if (levels && per_class && (!filtered || c.filter_per_class) &&
+      (C % (levels->dtype == RPP_DT_F32 ? 4 : 8) != 0 || C > 392))
+    return fail(RPP_EINVAL, "rpp_detect_levels / rpp_detect_typed with the per-class filter or no filter need "
+                            "num_classes % 4 == 0 (% 8 for 16-bit inputs) and at most 392 classes; fuse / convert and "
+                            "call rpp_detect otherwise");
+  if (!filtered) {   // TransformBoxesAndScores -> GenerateDetections on all N rows
+    if (per_class) return per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, N, 0, 0, out, st, levels);
+    return global_pipeline(h, ar, logits, 1, deltas, nullptr, B, N, out, st, false, nullptr, levels);
+  }
   if (c.filter_per_class) {
     const long k = std::min<long>(c.pre_nms_top_k, N);
-    return per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, k, 1, 1, out, st);
+    return per_class_pipeline(h, ar, logits, 1, deltas, nullptr, 1, B, N, k, 1, 1, out, st, levels);
   }
   // global filter (:149-161): top-k over the flat (anchor, class) axis on raw logits ...
   if ((double)N * C >= 2147483647.0) return fail(RPP_EINVAL, "anchors x classes must stay below 2^31 for the global filter");
   const long k = std::min<long>(c.pre_nms_top_k, N * C);
+  // the source as Levels (class lookups, box deltas) and as its flat view (one column of N * C elements per image)
+  Levels lv, flat;
+  memset(&lv, 0, sizeof(lv));
+  if (levels) lv = *levels;
+  else { lv.L = 1; lv.off[1] = N; lv.x[0] = logits; lv.d[0] = deltas; }
+  flat = lv;
+  for (int l = 0; l <= lv.L; ++l) flat.off[l] = lv.off[l] * C;
+  for (int l = 0; l < RPP_MAX_LEVELS; ++l) flat.d[l] = nullptr;
   u64* keys = nullptr;
-  int rc = topk_keys(h, ar, logits, 1, B, N * C, 1, k, &keys, st);
+  int rc = topk_keys(h, ar, levels ? nullptr : logits, 1, B, N * C, 1, k, &keys, st, levels ? &flat : nullptr);
   if (rc) return rc;
   if (!per_class) {
     // ... Global*: the rows the reference gathers are never materialised (rpp_global.cuh): row maxima, boxes and the
@@ -840,15 +864,13 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
     nms_v5_args(c, &iou_thr, &sigma_tf);
     const int M = c.max_detections;
     const bool soft = sigma_tf > 0.0f && !tpu_branch(c) && k <= RPP_GS_MAXK;
+    const bool top_only = sigma_tf == 0.0f && !tpu_branch(c) && M <= 1024;   // GlobalHardNMS: no suppression (B1)
     u32* first = ar.take<u32>((size_t)B * N);
     float* mraw = ar.take<float>((size_t)B * k);
     float4* box_spill = soft ? ar.take<float4>((size_t)B * k) : nullptr;
-    u64* skey = soft ? ar.take<u64>((size_t)B * k) : nullptr;
-    u64* dkey = soft ? ar.take<u64>((size_t)B * k) : nullptr;
-    int* sd_cnt = soft ? ar.take<int>((size_t)B * 2) : nullptr;
-    Levels lv;
-    memset(&lv, 0, sizeof(lv));
-    lv.L = 1; lv.off[1] = N; lv.x[0] = logits; lv.d[0] = deltas;
+    u64* skey = (soft || top_only) ? ar.take<u64>((size_t)B * k) : nullptr;
+    u64* dkey = (soft || top_only) ? ar.take<u64>((size_t)B * k) : nullptr;
+    int* sd_cnt = (soft || top_only) ? ar.take<int>((size_t)B * 2) : nullptr;
     if (!ar.dry) {
       CUDA_OK(cudaMemsetAsync(first, 0xff, (size_t)B * N * sizeof(u32), st));
       GlobalRowsParams rp{};
@@ -886,6 +908,18 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       stage_mark(h, "nms:global_soft", st);
       return RPP_OK;
     }
+    if (top_only) {
+      if (ar.dry) return RPP_OK;
+      GlobalTopParams tp{};
+      tp.k = k; tp.M = M; tp.skey = skey; tp.dkey = dkey; tp.sd_cnt = sd_cnt;
+      tp.emit_key = keys; tp.lv = lv; tp.C = C; tp.N = N; tp.anchors = h->d_anchors; tp.dp = h->dp;
+      tp.out_boxes = out.boxes; tp.out_scores = out.scores; tp.out_classes = (long long*)out.classes;
+      tp.out_valid = out.valid;
+      global_top_kernel<<<B, RPP_GTOP_NT, 0, st>>>(tp);
+      LAUNCHED();
+      stage_mark(h, "nms:global_top", st);
+      return RPP_OK;
+    }
     GlobalPre pre{mraw, keys, &lv, N};
     return global_pipeline(h, ar, nullptr, 0, nullptr, nullptr, B, k, out, st, false, &pre);
   }
@@ -898,7 +932,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
     while (tpr < C && tpr < 32) tpr <<= 1;
     if (C < 16) tpr = C;
     size_t grid = std::min<size_t>(((size_t)B * k * tpr + 255) / 256, (size_t)h->sm_count * 16);
-    fused_global_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, logits, deltas, h->d_anchors, h->dp, B, N, C, k,
+    fused_global_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, lv, h->d_anchors, h->dp, B, N, C, k,
                                                             /*apply_sigmoid=*/1, row_scores, row_boxes);
     LAUNCHED();
     stage_mark(h, "rows:gather", st);

@@ -347,17 +347,49 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
 // Hits are counted per thread (a 4 * UNROLL bit mask), placed in the shared queue with ONE shared atomic per warp and
 // load round (warp prefix sum), and flushed with one global atomic per (tile, image).
 #define RPP_FLAT_QCAP 2048
-template <int UNROLL>
+// element k of a 128-bit word as fp32: 4 floats, or 8 f16 / bf16 values (converted exactly)
+template <int DT> struct FlatWord;
+template <> struct FlatWord<RPP_DT_F32> {
+  static constexpr int EPW = 4;
+  static __device__ __forceinline__ float get(const uint4& w, int k) {
+    return __uint_as_float(k == 0 ? w.x : k == 1 ? w.y : k == 2 ? w.z : w.w);
+  }
+  static __device__ __forceinline__ float load(const void* x, long e) { return __ldg(reinterpret_cast<const float*>(x) + e); }
+};
+template <int DT> struct FlatWordHalf {
+  static constexpr int EPW = 8;
+  static __device__ __forceinline__ float get(const uint4& w, int k) {
+    const u32 v = (k >> 1) == 0 ? w.x : (k >> 1) == 1 ? w.y : (k >> 1) == 2 ? w.z : w.w;
+    return half_bits_to_f32((unsigned short)((k & 1) ? (v >> 16) : (v & 0xffffu)), DT);
+  }
+  static __device__ __forceinline__ float load(const void* x, long e) {
+    return half_bits_to_f32(__ldg(reinterpret_cast<const unsigned short*>(x) + e), DT);
+  }
+};
+template <> struct FlatWord<RPP_DT_F16> : FlatWordHalf<RPP_DT_F16> {};
+template <> struct FlatWord<RPP_DT_BF16> : FlatWordHalf<RPP_DT_BF16> {};
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// x: 16-byte aligned address; element `lead` (0 .. EPW-1) of it is x[0][0].  idx_off: added to the stored indices (a
+// per-level piece of a longer axis: rpp_detect_levels / rpp_detect_typed with the global filter).
+template <int UNROLL, int DT>
 __global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
-collect_flat_kernel(const float* __restrict__ x /*16-byte aligned; element `lead` (0..3) is x[0][0]*/, int lead,
-                    const float* __restrict__ T /*[B]*/, u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP,
-                    int B, long n, long tile_elems, long n_tiles, u32* __restrict__ tile_counter) {
+collect_flat_kernel(const void* __restrict__ x, int lead, u32 idx_off, const float* __restrict__ T /*[B]*/,
+                    u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long n, long tile_elems,
+                    long n_tiles, u32* __restrict__ tile_counter) {
+  typedef FlatWord<DT> W;
+  constexpr int EPW = W::EPW;
   __shared__ uint2 s_q[RPP_FLAT_QCAP];
   __shared__ u32 s_qn, s_base;
   __shared__ long s_tile;
   const int tid = threadIdx.x, lane = tid & 31;
   const long total = (long)lead + (long)B * n;   // the flat array, counted from the aligned address
-  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  const uint4* __restrict__ x4 = reinterpret_cast<const uint4*>(x);
   for (;;) {
     if (tid == 0) { s_tile = (long)atomicAdd(tile_counter, 1u); s_qn = 0u; }
     __syncthreads();
@@ -370,34 +402,37 @@ collect_flat_kernel(const float* __restrict__ x /*16-byte aligned; element `lead
       const long seg_lo = e0 > ibase ? e0 : ibase;
       const long seg_hi = e1 < ibase + n ? e1 : ibase + n;
       const float t = __ldg(T + b);
-      long v_lo = (seg_lo + 3) & ~3L, v_hi = seg_hi & ~3L;   // whole 128-bit words inside the segment
+      long v_lo = (seg_lo + EPW - 1) / EPW * EPW, v_hi = seg_hi / EPW * EPW;   // whole 128-bit words inside the segment
       if (v_lo > v_hi) v_lo = v_hi = seg_hi;
-      {   // ragged edges: [seg_lo, v_lo) and [v_hi, seg_hi), at most 3 + 3 elements
+      {   // ragged edges: [seg_lo, v_lo) and [v_hi, seg_hi), at most EPW-1 elements each
         const long head = (v_lo < seg_hi ? v_lo : seg_hi) - seg_lo;
         const long tail = seg_hi - (v_hi > v_lo ? v_hi : v_lo);
         if (tid < head + tail) {
           const long e = tid < head ? seg_lo + tid : (v_hi > v_lo ? v_hi : v_lo) + (tid - head);
-          const float v = __ldg(x + e);
+          const float v = W::load(x, e);
           if (v >= t) {
             const u32 slot = atomicAdd(&s_qn, 1u);
-            if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(v), (u32)(e - ibase));
-            else append_cand(cand_count, cand, CAP, (size_t)b, v, (u32)(e - ibase));
+            if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(v), (u32)(e - ibase) + idx_off);
+            else append_cand(cand_count, cand, CAP, (size_t)b, v, (u32)(e - ibase) + idx_off);
           }
         }
       }
-      const long f_lo = v_lo >> 2, f_hi = v_hi >> 2;
+      const long f_lo = v_lo / EPW, f_hi = v_hi / EPW;
       for (long f0 = f_lo; f0 < f_hi; f0 += (long)RPP_COLLECT_NT * UNROLL) {   // uniform trip count per block
-        float4 v[UNROLL];
+        uint4 v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
           const long ff = f0 + tid + (long)u * RPP_COLLECT_NT;
-          v[u] = ff < f_hi ? ld_stream_f4(x4 + ff) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          v[u] = ff < f_hi ? ld_stream_u4(x4 + ff) : make_uint4(0u, 0u, 0u, 0u);
         }
-        u32 mask = 0u;   // bit 4u + i: component i of load u passes (NaN never passes >=)
+        u32 mask = 0u;   // bit EPW * u + i: element i of load u passes (NaN never passes >=)
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-          mask |= ((v[u].x >= t ? 1u : 0u) | (v[u].y >= t ? 2u : 0u) | (v[u].z >= t ? 4u : 0u) |
-                   (v[u].w >= t ? 8u : 0u)) << (4 * u);
+        for (int u = 0; u < UNROLL; ++u) {
+          const bool in = f0 + tid + (long)u * RPP_COLLECT_NT < f_hi;
+#pragma unroll
+          for (int i = 0; i < EPW; ++i)
+            if (in && W::get(v[u], i) >= t) mask |= 1u << (EPW * u + i);
+        }
         if (__any_sync(RPP_FULL_MASK, mask != 0u)) {
           // warp prefix sum of the per-thread hit counts -> one shared atomic per warp
           const u32 cnt = (u32)__popc(mask);
@@ -414,9 +449,9 @@ collect_flat_kernel(const float* __restrict__ x /*16-byte aligned; element `lead
           while (mask) {
             const int bit = __ffs(mask) - 1;
             mask &= mask - 1u;
-            const long ff = f0 + tid + (long)(bit >> 2) * RPP_COLLECT_NT;
-            const u32 idx = (u32)(ff * 4 + (bit & 3) - ibase);
-            const float val = __ldg(x + ff * 4 + (bit & 3));   // L1 hit: the line was just loaded by this thread
+            const long e = (f0 + tid + (long)(bit / EPW) * RPP_COLLECT_NT) * EPW + (bit % EPW);
+            const u32 idx = (u32)(e - ibase) + idx_off;
+            const float val = W::load(x, e);   // L1 hit: the line was just loaded by this thread
             if (slot < RPP_FLAT_QCAP) s_q[slot] = make_uint2(__float_as_uint(val), idx);
             else append_cand(cand_count, cand, CAP, (size_t)b, val, idx);
             ++slot;

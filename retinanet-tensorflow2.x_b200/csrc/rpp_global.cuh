@@ -118,6 +118,99 @@ __global__ void __launch_bounds__(RPP_GROWS_NT) global_rows_kernel(GlobalRowsPar
 }
 
 // ===============================================================================================================
+// global_top_kernel — GlobalHardNMS behind the global filter, non-TPU branch.  The reference passes iou_threshold = 1.0
+// to NonMaxSuppressionV5 there (postprocessing_ops.py:253), and an IoU computed as
+// inter / (area_a + area_b - inter) in IEEE arithmetic never exceeds 1 (inter <= min(area_a, area_b), and rounding is
+// monotone), so nothing is ever suppressed: the output is the first max_detections rows above the score threshold in
+// (row maximum desc, row index asc) order — duplicates of an anchor included (B12).  Candidates: the first M
+// first-occurrence rows (already in order) and every duplicate row; one selection of the M best.
+// ===============================================================================================================
+#define RPP_GTOP_NT 256
+
+struct GlobalTopParams {
+  long k; int M;
+  const u64* skey; const u64* dkey; const int* sd_cnt;
+  const u64* emit_key; Levels lv; int C; long N;
+  const float4* anchors; DecodeParams dp;
+  float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
+};
+
+struct GlobalTopShared {
+  SelectScratch<RPP_GTOP_NT> sel;
+  u64 chunk[1024];
+  u64 top[1024];
+};
+
+__global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams P) {
+  __shared__ GlobalTopShared sh;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.x;
+  const int ns = P.sd_cnt[2 * b], nd = P.sd_cnt[2 * b + 1];
+  const int n1 = ns < P.M ? ns : P.M;
+  const u64* sk = P.skey + (size_t)b * P.k;
+  const u64* dk = P.dkey + (size_t)b * P.k;
+  u64 KB = ~0ull;
+  int got = 0;
+  while (got < P.M) {   // (a chunk may come back shorter than asked for: the radix cut is exact, not its size)
+    const int m = select_chunk<RPP_GTOP_NT>([&](int i) { return i < n1 ? sk[i] : dk[i - n1]; }, n1 + nd, KB,
+                                            P.M - got, sh.chunk, 1024, &sh.sel);
+    if (m == 0) break;
+    const int take = m < P.M - got ? m : P.M - got;
+    for (int i = tid; i < take; i += RPP_GTOP_NT) sh.top[got + i] = sh.chunk[i];
+    got += take;
+    __syncthreads();
+  }
+  const int valid = got;
+  if (tid == 0) P.out_valid[b] = valid;
+  for (int i = tid >> 5; i < P.M; i += RPP_GTOP_NT / 32) {   // one warp per output row (as in global_soft_kernel)
+    const size_t o = (size_t)b * P.M + i;
+    if (i < valid) {
+      const u64 key = sh.top[i];
+      const u32 j = key_tie(key);
+      const u32 a = key_tie(P.emit_key[(size_t)b * P.k + j]) / (u32)P.C;
+      float best = -INFINITY;
+      int cls = 0x7fffffff;
+      for (int c = lane; c < P.C; c += 32) {
+        const float raw = lv_val(P.lv, b, a, P.C, c);
+        if (raw > best) { best = raw; cls = c; }
+      }
+#pragma unroll
+      for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        const float ob = __shfl_xor_sync(RPP_FULL_MASK, best, ofs);
+        const int oc = __shfl_xor_sync(RPP_FULL_MASK, cls, ofs);
+        if (ob > best || (ob == best && oc < cls)) { best = ob; cls = oc; }
+      }
+      bool near = false;
+      for (int c = lane; c < cls; c += 32) {
+        const float raw = lv_val(P.lv, b, a, P.C, c);
+        near = near || raw > best - 1.0f || best > 15.0f || best < -80.0f;
+      }
+      if (__any_sync(RPP_FULL_MASK, near)) {
+        const float s_best = sigmoid_f32(best);
+        int c2 = 0x7fffffff;
+        for (int c = lane; c < cls; c += 32)
+          if (sigmoid_f32(lv_val(P.lv, b, a, P.C, c)) == s_best && c < c2) c2 = c;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) c2 = min(c2, __shfl_xor_sync(RPP_FULL_MASK, c2, ofs));
+        if (c2 < cls) cls = c2;
+      }
+      if (lane == 0) {
+        P.out_boxes[o] = clip01(decode_box(lv_delta(P.lv, b, a), P.anchors[a], P.dp));
+        P.out_scores[o] = key_score(key);
+        P.out_classes[o] = cls;
+      }
+    } else if (lane == 0) {
+      // padded selected index 0 -> boxes[0] (clipped), score -1, class -1 (:258-268)
+      const u64 k0 = P.emit_key[(size_t)b * P.k];
+      const u32 a0 = k0 != 0ull ? key_tie(k0) / (u32)P.C : 0u;
+      P.out_boxes[o] = clip01(decode_box(lv_delta(P.lv, b, a0), P.anchors[a0], P.dp));
+      P.out_scores[o] = -1.0f;
+      P.out_classes[o] = -1;
+    }
+  }
+}
+
+// ===============================================================================================================
 // global_soft_kernel — NonMaxSuppressionV5 with soft_nms_sigma > 0 for ONE image per block, with the
 // block's 16 warps working on one image instead of one warp popping a priority queue.
 //

@@ -27,7 +27,7 @@ struct ColProblemParams {
   // rows that are not rows of the delta tensor (the global filter without the row gather, rpp_global.cuh): row j is
   // anchor tie(row_keys[b][j]) / C_src of the deltas in dlv
   const u64* row_keys; long k_rows; int C_src;
-  Levels dlv;
+  Levels dlv;              // dlv.L > 0 without row_keys: the deltas of row r are dlv's row r (x is a derived column)
   DecodeParams dp;
   int clip_before;         // clip boxes to [0,1] before IoU (every mode but CombinedNMS; B6)
   float iou_threshold;
@@ -112,6 +112,7 @@ __device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int 
     const u32 a = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C_src;
     return decode_box(lv_delta(P.dlv, b, a), P.anchors[a], P.dp);
   }
+  if (P.dlv.L > 0) return decode_box(lv_delta(P.dlv, b, row), P.anchors[row], P.dp);
   return decode_box(lv_delta(P.lv, b, row), P.anchors[row], P.dp);
 }
 

@@ -302,6 +302,22 @@ __global__ void rowmax_kernel(const float* __restrict__ x, size_t rows, int C, f
   }
 }
 
+// [B,N,C] in per-level pieces and / or 16-bit elements -> [B,N] row maxima (one warp per row)
+__global__ void rowmax_levels_kernel(Levels lv, long N, int C, size_t rows, float* __restrict__ out) {
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t r = warp; r < rows; r += nwarps) {
+    const int b = (int)(r / (size_t)N);
+    const long row = (long)(r - (size_t)b * N);
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, lv_val(lv, b, row, C, c));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(RPP_FULL_MASK, m, o));
+    if (lane == 0) out[r] = m;
+  }
+}
+
 struct GlobalOutParams {
   int M;
   const u64* sel_key;     // [B][M]  (score | ~row)
@@ -527,10 +543,10 @@ __global__ void topk_gather_global_kernel(const u64* __restrict__ emit_key /*[B]
 
 // fused global filter: rows selected on raw logits -> materialise the reference's intermediates
 // scores [B,k,C] = sigmoid(logit rows), boxes [B,k,4] = decoded anchors (TransformBoxesAndScores on k rows only)
-__global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][k]*/, const float* __restrict__ logits,
-                                         const float4* __restrict__ deltas, const float4* __restrict__ anchors,
-                                         DecodeParams dp, int B, long N, int C, long k, int apply_sigmoid,
-                                         float* __restrict__ scores_out, float4* __restrict__ boxes_out) {
+__global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][k]*/, Levels lv /*logits + deltas*/,
+                                         const float4* __restrict__ anchors, DecodeParams dp, int B, long N, int C,
+                                         long k, int apply_sigmoid, float* __restrict__ scores_out,
+                                         float4* __restrict__ boxes_out) {
   if (C < 16) {   // narrow rows: one thread per element
     const size_t tot = (size_t)B * k * C;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
@@ -538,9 +554,9 @@ __global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][
       const size_t bj = e / C;
       const int b = (int)(bj / k);
       const u32 a = key_tie(emit_key[bj]) / (u32)C;
-      const float raw = logits[((size_t)b * N + a) * C + c];
+      const float raw = lv_val(lv, b, a, C, c);
       scores_out[e] = apply_sigmoid ? sigmoid_f32(raw) : raw;
-      if (c == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
+      if (c == 0) boxes_out[bj] = decode_box(lv_delta(lv, b, a), anchors[a], dp);
     }
     return;
   }
@@ -556,14 +572,12 @@ __global__ void fused_global_rows_kernel(const u64* __restrict__ emit_key /*[B][
   for (size_t bj = warp; bj < rows; bj += nwarps) {
     const int b = (int)(bj / k);
     const u32 a = key_tie(emit_key[bj]) / (u32)C;
-    const float* src = logits + ((size_t)b * N + a) * C;
     float* dst = scores_out + bj * C;
-    // apply_sigmoid = 0 (Global* modes): the rows stay logits; only the row maxima are scored (global_pipeline)
     for (int c = lane; c < C; c += tpr) {
-      const float raw = __ldg(src + c);
+      const float raw = lv_val(lv, b, a, C, c);
       dst[c] = apply_sigmoid ? sigmoid_f32(raw) : raw;
     }
-    if (lane == 0) boxes_out[bj] = decode_box(deltas[(size_t)b * N + a], anchors[a], dp);
+    if (lane == 0) boxes_out[bj] = decode_box(lv_delta(lv, b, a), anchors[a], dp);
   }
 }
 

@@ -461,16 +461,21 @@ class FusedPostProcessing(Layer):
     _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
     def _native_pieces(self, cls, box):
-        """Can rpp_detect_typed read these tensors where they lie (per-level pieces and / or 16-bit elements)?"""
+        """Can rpp_detect_typed read these tensors where they lie (per-level pieces and / or 16-bit elements)?
+        Every mode / filter combination can; the staged column collect of the per-class filter (or no filter) in the
+        per-class modes needs num_classes % 4 == 0 (% 8 for 16-bit elements) and at most 392 classes."""
         inf = self._params.inference
         dts = {t.dtype for t in cls + box}
         if len(dts) != 1 or next(iter(dts)) not in self._DTYPES:
             return False
         half = next(iter(dts)) != torch.float32
         C = cls[0].shape[2]
-        return (C % (8 if half else 4) == 0 and C <= 392 and not self.mode.startswith('Global')
-                and (inf.pre_nms_top_k <= 0 or inf.filter_per_class)
-                and all(t.is_cuda and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in cls + box))
+        columns = not self.mode.startswith('Global') and (inf.pre_nms_top_k <= 0 or inf.filter_per_class)
+        if columns and (C % (8 if half else 4) != 0 or C > 392):
+            return False
+        if self.mode.startswith('Global') and inf.pre_nms_top_k > 0 and inf.filter_per_class:
+            return False    # (invalid combination: the fused call reports it)
+        return all(t.is_cuda and t.is_contiguous() and t.data_ptr() % 16 == 0 for t in cls + box)
 
     def _call_pieces(self, cls, box):
         """Head outputs in place (rpp_detect_typed): per-level pieces without the FuseDetections concat, f16 / bf16

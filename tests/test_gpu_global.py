@@ -158,3 +158,41 @@ def test_many_classes_fall_back_to_the_generic_collect(ref):
     deltas = np.clip(rng.standard_normal((2, N, 4)) * 0.5, -4, 4).astype(np.float32)
     got, exp = _run(ref, p, logits, deltas)
     assert image_mismatches(got, exp) == []
+
+
+def _level_heads(rng, H, C, B, dtype):
+    cls, box = {}, {}
+    for level in range(3, 8):
+        f = int(np.ceil(H / 2 ** level))
+        cls[str(level)] = torch.from_numpy(rng.standard_normal((B, f, f, 9 * C)).astype(np.float32)).to(dtype)
+        box[str(level)] = torch.from_numpy(
+            np.clip(rng.standard_normal((B, f, f, 36)) * 0.5, -4, 4).astype(np.float32)).to(dtype)
+    return cls, box
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'bfloat16', 'float16'])
+@pytest.mark.parametrize('mode,k,fpc,C', [
+    ('GlobalSoftNMS', 3000, False, 8), ('GlobalHardNMS', 3000, False, 8), ('GlobalSoftNMS', -1, False, 8),
+    ('GlobalHardNMS', -1, False, 5), ('PerClassHardNMS', 3000, False, 8), ('CombinedNMS', 3000, False, 5),
+    ('GlobalSoftNMS', 5000, False, 5), ('GlobalHardNMS', 5000, False, 3)])
+def test_every_mode_reads_head_outputs_in_place(ref, monkeypatch, dtype, mode, k, fpc, C):
+    """SURVEY §8f-1 for the Global* modes and the global filter: per-level pieces and f16 / bf16 elements go through
+    rpp_detect_typed (no torch.cat, no .to(float32)); the result equals the oracle on the values the reference sees
+    after its tf.cast (:111-112), and the fused fp32 route."""
+    from retinanet.model.builder import ModelBuilder
+    from retinanet.model.layers import postprocessing_ops as ops
+    H, B = 320, 3
+    tdt = getattr(torch, dtype)
+    p = make_params(H, num_classes=C, mode=mode, pre_nms_top_k=k, filter_per_class=fpc, max_detections=60)
+    cls, box = _level_heads(np.random.default_rng(77 + C), H, C, B, tdt)
+    heads = {'class-predictions': {k_: v.cuda() for k_, v in cls.items()},
+             'box-predictions': {k_: v.cuda() for k_, v in box.items()}}
+    model = ModelBuilder(p).add_post_processing_stage(None)
+    # the native route must be taken: the eager fallbacks (cast / concat) are made to fail
+    monkeypatch.setattr(ops, '_as_f32', lambda t: (_ for _ in ()).throw(AssertionError('eager cast / concat used')))
+    got = to_numpy(model(heads))
+    monkeypatch.undo()
+    logits = np.concatenate([cls[str(l)].float().numpy().reshape(B, -1, C) for l in range(3, 8)], 1)
+    deltas = np.concatenate([box[str(l)].float().numpy().reshape(B, -1, 4) for l in range(3, 8)], 1)
+    exp = oracle_detect(ref, p, logits, deltas)
+    assert image_mismatches(got, exp) == []
