@@ -69,6 +69,7 @@ struct Handle {
   int force_scan;
   int warp_probe;        // env RPP_WARP_PROBE (default 1): warp-per-problem probe kernel for the hard modes
   int probe_extra;       // env RPP_PROBE_EXTRA: boxes per class kept by the probe beyond ceil(M / C)
+  int pdl;               // env RPP_PDL (default 1): programmatic dependent launch between the kernels of a pipeline
   int two_pass;          // env RPP_TWO_PASS (default 1): probe / bound / finish scheme of the per-class modes
   int collect_ctas;      // env RPP_COLLECT_CTAS: CTAs per SM of the collect kernel (0 = automatic)
   int overlap_hint;
@@ -121,9 +122,27 @@ inline void stage_mark(Handle* h, const char* label, cudaStream_t st) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Kernel launch through cudaLaunchKernelEx, optionally with programmatic dependent launch (see pdl_enter in
+// rpp_common.cuh): used for every kernel of a pipeline that directly follows another kernel in the stream.
+template <class... Params, class... Args>
+inline void launch_k(bool pdl, void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+
 // Pre-threshold plan for columns of n rows and C classes: aim at ~`target` candidates per problem with list
 // capacity 4096; small columns are collected whole (no sampling).
-SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
+SamplePlan make_plan(long n, int C, int target, int lane_cap = 12, double q_plan = 0.0) {
   SamplePlan s{};
   s.on = false;
   s.rank_lo = -1;
@@ -139,7 +158,10 @@ SamplePlan make_plan(long n, int C, int target, int lane_cap = 12) {
     const double q = v ? atof(v) : 0.7;
     return -std::log(q > 0.05 && q < 0.97 ? q : 0.7);
   }();
-  int S = (int)std::floor(target / (neg_ln_q * G));
+  // (q_plan: the fine emission plans have 4x the groups and can afford a sparser sample: quantile 0.8, 1.6x fewer loads,
+  // the list length's 1-sigma goes from 9 % to 11 % with both tails still > 4 sigma away)
+  const double nlq = q_plan > 0.0 ? -std::log(q_plan) : neg_ln_q;
+  int S = (int)std::floor(target / (nlq * G));
   if (S < 1) S = 1;
   long g = n / ((long)S * G);
   if (g < 8) {   // the target is a large fraction of the column: sample denser, accept a lower quantile
@@ -183,7 +205,7 @@ SamplePlan choose_plan(long n, int C, bool emit, long k_lim, int nms_target, int
   const int target = emit ? (int)std::min<long>(emit_fine ? 2 * k_lim + 256 : k_lim + k_lim / 2 + 512, 1 << 28)
                           : nms_target;
   SamplePlan plan = make_plan(n, C, emit_short && emit ? (int)std::max<long>(64, k_lim / 2) : target,
-                              emit_fine ? emit_lanes : 12);
+                              emit_fine ? emit_lanes : 12, emit_fine ? 0.8 : 0.0);
   if (plan.on && emit) { plan.CAP = emit_fine ? target + target / 2 + 1024 : 2 * target; plan.rank_lo = -1; }
   if (emit_fine_out) *emit_fine_out = emit_fine;
   if (target_out) *target_out = target;
@@ -321,11 +343,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
                                                                           plan.rows_per_group, gm);
     LAUNCHED();
     if (plan.G <= 128) {
-      sample_rank_sort_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), RPP_RANK_CPB * 32, 0, st>>>(
+      launch_k(h->pdl, sample_rank_sort_kernel, dim3(dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB)), dim3(RPP_RANK_CPB * 32), 0, st, 
           gm, C, plan.G, plan.rank, plan.rank_lo, ps.T_min, T);
     } else {
       const size_t smem = (size_t)plan.G * RPP_RANK_CPB * sizeof(u32);
-      sample_rank_kernel<<<dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB), 256, smem, st>>>(gm, C, plan.G, plan.rank,
+      launch_k(h->pdl, sample_rank_kernel, dim3(dim3(B, (C + RPP_RANK_CPB - 1) / RPP_RANK_CPB)), dim3(256), smem, st, gm, C, plan.G, plan.rank,
                                                                                           plan.rank_lo, ps.T_min, T);
     }
     LAUNCHED();
@@ -365,8 +387,8 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
         const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
         u32* tc = tile_counter + 32 + l;   // (zeroed with the counters by the memset above)
 #define RPP_LAUNCH_FLAT(DT)                                                                                      \
-        collect_flat_kernel<4, DT><<<(unsigned)grid, RPP_COLLECT_NT, 0, st>>>(xa, lead, (u32)lv.off[l], T, cand_count, \
-                                                                            cand, plan.CAP, B, n_l, tile_elems, n_tiles, tc)
+        launch_k(h->pdl, collect_flat_kernel<4, DT>, dim3((unsigned)grid), dim3(RPP_COLLECT_NT), 0, st,            \
+                 (const void*)xa, lead, (u32)lv.off[l], T, cand_count, cand, plan.CAP, B, n_l, tile_elems, n_tiles, tc)
         if (lv.dtype == RPP_DT_F32) RPP_LAUNCH_FLAT(RPP_DT_F32);
         else if (lv.dtype == RPP_DT_F16) RPP_LAUNCH_FLAT(RPP_DT_F16);
         else RPP_LAUNCH_FLAT(RPP_DT_BF16);
@@ -392,9 +414,9 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       const long n_tiles = (long)B * tiles_per_image;
       const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
 #define RPP_LAUNCH_HALF(U, DT, MB)                                                                               \
-      collect_cols8_half_kernel<U, DT, MB><<<(unsigned)std::min<long>((long)h->sm_count * MB, n_tiles),           \
-                                            RPP_COLLECT_NT, smem, st>>>(                                          \
-          lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter)
+      launch_k(h->pdl, collect_cols8_half_kernel<U, DT, MB>,                                                     \
+               dim3((unsigned)std::min<long>((long)h->sm_count * MB, n_tiles)), dim3(RPP_COLLECT_NT), smem, st,   \
+               lv, T, cand_count, cand, plan.CAP, B, n, C8, lanes, (int)rows_per_tile, tiles_per_image, tile_counter)
       if (h->half_variant == 1) {
         if (lv.dtype == RPP_DT_F16) RPP_LAUNCH_HALF(8, RPP_DT_F16, 2); else RPP_LAUNCH_HALF(8, RPP_DT_BF16, 2);
       } else {
@@ -435,11 +457,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       if (grid > n_tiles) grid = n_tiles;
       const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
 #define RPP_LAUNCH_COLLECT(U, MB)                                                                               \
-      collect_cols4_kernel<U, MB><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(                                \
-          (const float4*)lv.x[0], T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,           \
-          tiles_per_image, tile_counter)
+      launch_k(h->pdl, collect_cols4_kernel<U, MB>, dim3((unsigned)grid), dim3(RPP_COLLECT_NT), smem, st,        \
+               (const float4*)lv.x[0], T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile,       \
+               tiles_per_image, tile_counter)
       if (lv.L > 1)
-        collect_cols4_levels_kernel<4, 3><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(
+        launch_k(h->pdl, collect_cols4_levels_kernel<4, 3>, dim3((unsigned)grid), dim3(RPP_COLLECT_NT), smem, st, 
             lv, T, cand_count, cand, plan.CAP, B, n, C4, lanes, (int)rows_per_tile, tiles_per_image, tile_counter);
       else if (h->collect_variant == 0) RPP_LAUNCH_COLLECT(4, 3);
       else if (h->collect_variant == 1) RPP_LAUNCH_COLLECT(4, 2);
@@ -465,7 +487,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
       const long n_tiles = std::max<long>(1, (total_f4 + tile_f4 - 1) / tile_f4);
       const long grid = std::min<long>((long)h->sm_count * 3, n_tiles);
       const size_t smem = (size_t)C * RPP_STAGE_CAP * sizeof(uint2) + 2 * (size_t)C * sizeof(u32);
-      collect_colsv_kernel<4><<<(unsigned)grid, RPP_COLLECT_NT, smem, st>>>(ps.x, T, cand_count, cand, plan.CAP, B, n, C, S,
+      launch_k(h->pdl, collect_colsv_kernel<4>, dim3((unsigned)grid), dim3(RPP_COLLECT_NT), smem, st, ps.x, T, cand_count, cand, plan.CAP, B, n, C, S,
                                                                          tile_f4, n_tiles, tile_counter);
       LAUNCHED();
     } else {
@@ -515,13 +537,13 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     // worklist launches (finish pass): a few persistent blocks per SM instead of one block per problem
     const unsigned grid = pp.work_items ? (unsigned)std::min<size_t>(P, (size_t)h->sm_count * 4) : (unsigned)P;
     if (ps.consumer == RPP_CONSUME_HARD)
-      col_problem_kernel<RPP_CONSUME_HARD><<<grid, RPP_NMS_NT, smem_nms, st>>>(pp);
+      launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_HARD>, dim3(grid), dim3(RPP_NMS_NT), smem_nms, st, pp);
     else if (ps.consumer == RPP_CONSUME_PADDED)
-      col_problem_kernel<RPP_CONSUME_PADDED><<<grid, RPP_NMS_NT, smem_nms, st>>>(pp);
+      launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_PADDED>, dim3(grid), dim3(RPP_NMS_NT), smem_nms, st, pp);
     else if (ps.consumer == RPP_CONSUME_SOFT)
-      col_problem_kernel<RPP_CONSUME_SOFT><<<grid, RPP_NMS_NT, smem_nms + sizeof(SoftShared), st>>>(pp);
+      launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_SOFT>, dim3(grid), dim3(RPP_NMS_NT), smem_nms + sizeof(SoftShared), st, pp);
     else
-      col_problem_kernel<RPP_CONSUME_EMIT><<<grid, RPP_NMS_NT, smem_nms, st>>>(pp);
+      launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_EMIT>, dim3(grid), dim3(RPP_NMS_NT), smem_nms, st, pp);
   };
   pp.pass = 0; pp.M_cap = pp.M_lim; pp.want0 = 248;   // ~250 keys: a 256-wide bitonic sort
   pp.bound = bound; pp.stop_L = stop_L;
@@ -529,13 +551,13 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     const int m1 = ps.two_pass_m1;
     pp.pass = 1; pp.M_cap = m1; pp.want0 = std::max(24, 6 * m1);
     if (ps.consumer == RPP_CONSUME_HARD && m1 <= RPP_PROBE_MAXCAP && h->warp_probe)
-      probe_warp_kernel<<<(unsigned)((P + RPP_PROBE_WARPS - 1) / RPP_PROBE_WARPS), RPP_PROBE_WARPS * 32, 0, st>>>(pp, P);
+      launch_k(h->pdl, probe_warp_kernel, dim3((unsigned)((P + RPP_PROBE_WARPS - 1) / RPP_PROBE_WARPS)), dim3(RPP_PROBE_WARPS * 32), 0, st, pp, P);
     else
       launch();
     LAUNCHED();
     const int bthreads = (int)std::min<size_t>(1024, align_up((size_t)C * m1, 32));
     u32* work_ctl = tile_counter + 16;   // zeroed with the counters by the memset above
-    perclass_bound_kernel<<<B, bthreads, (size_t)C * m1 * sizeof(float), st>>>(ps.sel_key, ps.sel_cnt, C, ps.M, m1,
+    launch_k(h->pdl, perclass_bound_kernel, dim3(B), dim3(bthreads), (size_t)C * m1 * sizeof(float), st, ps.sel_key, ps.sel_cnt, C, ps.M, m1,
                                                                               ps.M, stop_L, bound, work_items,
                                                                               work_ctl);
     LAUNCHED();
@@ -543,7 +565,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     pp.work_items = work_items; pp.work_ctl = work_ctl;
   }
   if (emit) {   // whole-list sort in shared memory where it applies; the generic kernel takes the rest
-    emit_sort_kernel<<<(unsigned)P, RPP_EMIT_NT, sizeof(EmitShared), st>>>(pp);
+    launch_k(h->pdl, emit_sort_kernel, dim3((unsigned)P), dim3(RPP_EMIT_NT), sizeof(EmitShared), st, pp);
     LAUNCHED();
   }
   launch();
@@ -618,7 +640,7 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
     mq.pad_score = ps.pad_score; mq.pad_box = ps.pad_box;
     mq.out_boxes = out.boxes; mq.out_scores = out.scores; mq.out_classes = (int*)out.classes;
     mq.out_valid = out.valid;
-    merge_padded_kernel<<<B, RPP_MERGE_NT, sizeof(MergeShared), st>>>(mq);
+    launch_k(h->pdl, merge_padded_kernel, dim3(B), dim3(RPP_MERGE_NT), sizeof(MergeShared), st, mq);
     LAUNCHED();
     stage_mark(h, "merge", st);
     return RPP_OK;
@@ -638,7 +660,7 @@ int per_class_chunk(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   size_t merge_smem = sizeof(MergeShared) + (size_t)C * M * sizeof(u64);
   mp.keys_in_smem = merge_smem <= 200 * 1024;
   if (!mp.keys_in_smem) merge_smem = sizeof(MergeShared);
-  merge_kernel<<<B, RPP_MERGE_NT, merge_smem, st>>>(mp);
+  launch_k(h->pdl, merge_kernel, dim3(B), dim3(RPP_MERGE_NT), merge_smem, st, mp);
   LAUNCHED();
   stage_mark(h, "merge", st);
   return RPP_OK;
@@ -759,7 +781,7 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
   gp.deltas = deltas; gp.anchors = h->d_anchors; gp.boxes = boxes; gp.dp = h->dp;
   gp.out_boxes = out.boxes; gp.out_scores = out.scores; gp.out_classes = (long long*)out.classes;
   gp.out_valid = out.valid;
-  global_out_kernel<<<B, 128, 0, st>>>(gp);
+  launch_k(h->pdl, global_out_kernel, dim3(B), dim3(128), 0, st, gp);
   LAUNCHED();
   stage_mark(h, "merge:global_out", st);
   return RPP_OK;
@@ -877,7 +899,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       rp.emit_key = keys; rp.k = k; rp.C = C; rp.N = N;
       rp.first = first; rp.mraw = mraw; rp.skey = skey; rp.dkey = dkey; rp.sd_cnt = sd_cnt;
       rp.score_threshold = c.score_threshold;
-      global_rows_kernel<<<B, RPP_GROWS_NT, 0, st>>>(rp);
+      launch_k(false /* follows a memset, not a kernel */, global_rows_kernel, dim3(B), dim3(RPP_GROWS_NT), 0, st, rp);
       LAUNCHED();
       stage_mark(h, "rows:resolve", st);
     }
@@ -903,7 +925,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       gs.debug = getenv("RPP_GS_DEBUG") ? 1 : 0;
       gs.out_boxes = out.boxes; gs.out_scores = out.scores; gs.out_classes = (long long*)out.classes;
       gs.out_valid = out.valid;
-      global_soft_kernel<<<B, RPP_GS_NT, global_soft_smem(k, gs.ring_cap, gs.box_cap, M), st>>>(gs);
+      launch_k(h->pdl, global_soft_kernel, dim3(B), dim3(RPP_GS_NT), global_soft_smem(k, gs.ring_cap, gs.box_cap, M), st, gs);
       LAUNCHED();
       stage_mark(h, "nms:global_soft", st);
       return RPP_OK;
@@ -915,7 +937,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       tp.emit_key = keys; tp.lv = lv; tp.C = C; tp.N = N; tp.anchors = h->d_anchors; tp.dp = h->dp;
       tp.out_boxes = out.boxes; tp.out_scores = out.scores; tp.out_classes = (long long*)out.classes;
       tp.out_valid = out.valid;
-      global_top_kernel<<<B, RPP_GTOP_NT, 0, st>>>(tp);
+      launch_k(h->pdl, global_top_kernel, dim3(B), dim3(RPP_GTOP_NT), 0, st, tp);
       LAUNCHED();
       stage_mark(h, "nms:global_top", st);
       return RPP_OK;
@@ -1046,6 +1068,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     if (h->probe_extra < 1) h->probe_extra = 1;
     v = getenv("RPP_TWO_PASS");
     h->two_pass = v ? atoi(v) : 1;
+    v = getenv("RPP_PDL");
+    h->pdl = v ? atoi(v) : 1;
     v = getenv("RPP_COLLECT_CTAS");
     h->collect_ctas = v ? atoi(v) : 0;
     h->overlap_hint = 0;

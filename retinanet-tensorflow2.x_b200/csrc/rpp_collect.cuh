@@ -33,6 +33,7 @@ collect_cols4_kernel(const float4* __restrict__ x4 /*[B,N,C/4]*/, const float* _
                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C4,
                      int lanes /*row lanes per block*/, int rows_per_tile, int tiles_per_image,
                      u32* __restrict__ tile_counter) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = C4 * 4;
   uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);   // [C][RPP_STAGE_CAP] staged (logit bits, row)
@@ -118,6 +119,7 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C4,
                      int lanes /*row lanes per block*/, int rows_per_tile, int tiles_per_image,
                      u32* __restrict__ tile_counter) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = C4 * 4;
   uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);   // [C][RPP_STAGE_CAP] staged (logit bits, row)
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(RPP_COLLECT_NT, MINB)
 collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32* __restrict__ cand_count,
                           uint2* __restrict__ cand, int CAP, int B, long N, int C8, int lanes, int rows_per_tile,
                           int tiles_per_image, u32* __restrict__ tile_counter) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = C8 * 8;
   uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);
@@ -382,6 +385,7 @@ __global__ void __launch_bounds__(RPP_COLLECT_NT, 3)
 collect_flat_kernel(const void* __restrict__ x, int lead, u32 idx_off, const float* __restrict__ T /*[B]*/,
                     u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long n, long tile_elems,
                     long n_tiles, u32* __restrict__ tile_counter) {
+  pdl_enter();
   typedef FlatWord<DT> W;
   constexpr int EPW = W::EPW;
   __shared__ uint2 s_q[RPP_FLAT_QCAP];
@@ -485,6 +489,7 @@ collect_colsv_kernel(const float* __restrict__ x /*[B*N*C], 16-byte aligned*/, c
                      u32* __restrict__ cand_count, uint2* __restrict__ cand, int CAP, int B, long N, int C,
                      int S /*threads that load: 4 * S % C == 0*/, long tile_f4 /*multiple of S * UNROLL*/, long n_tiles,
                      u32* __restrict__ tile_counter) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint2* s_stage = reinterpret_cast<uint2*>(smem_raw);   // [C][RPP_STAGE_CAP]
   u32* s_cnt = reinterpret_cast<u32*>(s_stage + (size_t)C * RPP_STAGE_CAP);

@@ -14,6 +14,15 @@ typedef unsigned int u32;
 
 #define RPP_FULL_MASK 0xffffffffu
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until the predecessor has completed
+// and its memory is visible (a no-op for a normal launch), pdl_launch() lets the successor's blocks be scheduled as
+// soon as SM resources free up.  Every kernel of a fused pipeline calls both first thing, so stream order is kept and
+// only launch latency, block scheduling and kernel prologues overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_launch(); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // keys: a candidate is ordered by (score descending, tie index ascending) — the total order of TF's TopKV2
 //  and of NonMaxSuppressionV5's priority queue (A.2).  One u64, larger = better, 0 = invalid.

@@ -41,6 +41,7 @@ __device__ __forceinline__ u64 grow_key(float score, u32 j) { return make_key(sc
 #define RPP_GROWS_RPT 8   // consecutive rows per thread
 
 __global__ void __launch_bounds__(RPP_GROWS_NT) global_rows_kernel(GlobalRowsParams P) {
+  pdl_enter();
   __shared__ int s_wsum[RPP_GROWS_NT / 32];
   __shared__ int s_run, s_nd;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,6 +143,7 @@ struct GlobalTopShared {
 };
 
 __global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams P) {
+  pdl_enter();
   __shared__ GlobalTopShared sh;
   const int tid = threadIdx.x, lane = tid & 31;
   const int b = blockIdx.x;
@@ -261,6 +263,8 @@ struct __align__(16) GlobalSoftShared {
   u64 ins[RPP_GS_WMAX];       // keys to insert, sorted descending
   u32 pos[RPP_GS_WMAX];       // ring elements greater than ins[i]
   u32 pos16[RPP_GS_NT / 32];  // narrow batches: rank of fresh[i] among the ring elements beyond the batch
+  u32 omask[RPP_GS_NT / 32];  // narrow batches: batch slots whose box overlaps slot i's
+  long long rdbg[8];          // debug (RPP_GS_DEBUG): cycle counts inside the re-scoring of batch slot 1
   int head, cnt;              // ring
   int s_pos, s_n;             // sorted stream of unvisited first-occurrence rows
   int nsel;
@@ -419,6 +423,9 @@ __device__ __forceinline__ void gs_refresh_warp(const GlobalSoftParams& P, Globa
                                                 const unsigned short* begin, const float4* gboxes, int batch, int cnt) {
   const int ci = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (ci >= batch) return;
+  const bool dbgw = P.debug && blockIdx.x == 0 && ci == 1 && lane == 0;
+  long long tq = dbgw ? clock64() : 0;
+#define RDBG(slot) do { if (dbgw) { const long long t__ = clock64(); sh->rdbg[slot] += t__ - tq; tq = t__; } } while (0)
   const int head = sh->head;
   const u64 st = ring[(head + ci) & mask];
   const u32 j = key_tie(st);
@@ -433,6 +440,7 @@ __device__ __forceinline__ void gs_refresh_warp(const GlobalSoftParams& P, Globa
   }
   const float thr = P.score_threshold;
   bool dropped = false;
+  RDBG(0);
   for (int top = nsel - 1; top >= bg && !dropped; top -= 128) {
     u32 m[4];
 #pragma unroll
@@ -447,6 +455,7 @@ __device__ __forceinline__ void gs_refresh_warp(const GlobalSoftParams& P, Globa
     }
     const int c0 = __popc(m[0]), c1 = __popc(m[1]), c2 = __popc(m[2]), c3 = __popc(m[3]);
     const int total = c0 + c1 + c2 + c3;
+    RDBG(1);
     for (int base = 0; base < total && !dropped; base += 32) {
       const int n = base + lane;
       float w = 1.0f;
@@ -468,14 +477,28 @@ __device__ __forceinline__ void gs_refresh_warp(const GlobalSoftParams& P, Globa
       }
     }
   }
+  RDBG(2);
   const u64 fk = (dropped || !(score > thr)) ? 0ull : make_key(score, j);
   u32 r16 = 0u;
   if (fk != 0ull && fk != st) r16 = gs_ring_rank_warp(ring, mask, (head + batch) & mask, cnt - batch, fk);
-  if (lane == 0) { sh->stale[ci] = st; sh->fresh[ci] = fk; sh->pos16[ci] = r16; }
+  RDBG(3);
+  // which other slots of the batch overlap this one (their weight against it can differ from 1)
+  bool ov = false;
+  if (lane < batch && lane != ci) {
+    float4 ob = gs_load_box(P, boxes, gboxes, key_tie(ring[(head + lane) & mask]));
+    float oa;
+    const float4 oc = canon_box(ob, oa);
+    ov = oa > 0.0f && fminf(box.z, oc.z) > fmaxf(box.x, oc.x) && fminf(box.w, oc.w) > fmaxf(box.y, oc.y);
+  }
+  const u32 om = __ballot_sync(RPP_FULL_MASK, ov);
+  if (lane == 0) { sh->stale[ci] = st; sh->fresh[ci] = fk; sh->pos16[ci] = r16; sh->omask[ci] = om; }
+  RDBG(4);
+#undef RDBG
 }
 
 #define GS_T(slot) do { if (P.debug && blockIdx.x == 0 && threadIdx.x == 0) { const long long t__ = clock64(); dbg[slot] += t__ - tlast; tlast = t__; } } while (0)
 __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams P) {
+  pdl_enter();
   long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
   int n_batches = 0, n_wide = 0, n_merge = 0;
@@ -506,6 +529,7 @@ __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams
   while (P2 < nd) P2 <<= 1;
   for (int i = tid; i < P2 && nd > 0; i += RPP_GS_NT) ring[i] = i < nd ? P.dkey[(size_t)b * P.k + i] : 0ull;
   if (tid < 32) sh->exp_tab[tid] = c_exp2f_tab[tid];
+  if (tid < 8) sh->rdbg[tid] = 0;
   if (tid == 0) {
     const int ns = P.sd_cnt[2 * b];
     sh->head = 0; sh->cnt = nd;
@@ -555,58 +579,86 @@ __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams
       // ---- 3 + 4 (narrow batches, <= 16 candidates): warp 0 finds the cut and the winner, commits the visited
       // prefix, sorts the keys that re-enter the ring and finds their positions, all without a block barrier ---------
       if (tid < 32) {
+        // Lane = batch slot.  The warp replays the TF kernel's pops over the batch as far as the re-scored keys of
+        // pass 2 stay valid: a candidate's re-scoring (against the boxes selected before the batch) is still its
+        // re-scoring at the time of its pop when no box selected INSIDE the batch since then overlaps it (weight
+        // exactly 1) — so one batch usually carries several selections; it ends at the first pop that would need
+        // a weight the batch does not have, at the end of the batch, or with the selected list full.
         const int cnt0 = cnt;
-        const int nsel = sh->nsel, head0 = sh->head;   // (read by every lane before lane 0 updates them below)
+        const int nsel0 = sh->nsel, head0 = sh->head;   // (read by every lane before lane 0 updates them below)
         const u64 st = lane < batch ? sh->stale[lane] : 0ull;
         const u64 fr = lane < batch ? sh->fresh[lane] : 0ull;
-        u64 incl = fr;                        // inclusive prefix maximum of the re-scored keys
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const u64 up = __shfl_up_sync(RPP_FULL_MASK, incl, o);
-          if (lane >= o && up > incl) incl = up;
-        }
-        u64 excl = __shfl_up_sync(RPP_FULL_MASK, incl, 1);
-        if (lane == 0) excl = 0ull;
-        const u32 mb = __ballot_sync(RPP_FULL_MASK, lane < batch && excl > st);    // the queue maximum is a re-scored key
-        const u32 mu = __ballot_sync(RPP_FULL_MASK, lane < batch && fr == st);     // score unchanged: selected
-        const int ib = mb ? __ffs(mb) - 1 : 32, iu = mu ? __ffs(mu) - 1 : 32;
-        int cut = batch, winner = -1;
-        if (iu < ib) { cut = iu + 1; winner = iu; }
-        else if (ib < 32 || all) {
-          cut = ib < 32 ? ib : batch;
-          u64 wmx = lane < cut ? fr : 0ull;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const u64 other = __shfl_xor_sync(RPP_FULL_MASK, wmx, o);
-            wmx = other > wmx ? other : wmx;
+        const u32 om = lane < batch ? sh->omask[lane] : 0u;
+        const u64 st_last = __shfl_sync(RPP_FULL_MASK, st, batch - 1);
+        int status = 0;          // 0 not visited, 1 visited and back in the queue, 2 selected, 3 dropped
+        int vbeg = 0, ord = -1;  // selected.size() at the visit; selection order inside the batch
+        u32 sbv = 0u;            // boxes of the batch selected before this slot's visit
+        u32 Sb = 0u;             // boxes of the batch selected so far
+        int nsel_cur = nsel0, nselb = 0, next_unv = 0;
+        u64 vmax = 0ull;         // queue maximum among the slots that are back in the queue
+        int vslot = -1;
+        for (;;) {
+          if (nsel_cur >= P.M) break;
+          const u64 ukey = next_unv < batch ? __shfl_sync(RPP_FULL_MASK, st, next_unv) : 0ull;
+          bool pop_v;
+          if (next_unv >= batch) {
+            // the next never-visited candidate lies beyond the batch (its key is below the batch's last)
+            if (vmax == 0ull) break;
+            if (!all && vmax < st_last) break;
+            pop_v = true;
+          } else {
+            pop_v = vmax > ukey;
           }
-          if (wmx != 0ull) {
-            const u32 who = __ballot_sync(RPP_FULL_MASK, lane < cut && fr == wmx);
-            winner = __ffs(who) - 1;
-          } else if (lane == 0) {
-            sh->finished = 1;                 // everything that was left fell to the threshold
+          if (pop_v) {
+            const u32 om_y = __shfl_sync(RPP_FULL_MASK, om, vslot), sbv_y = __shfl_sync(RPP_FULL_MASK, sbv, vslot);
+            if (om_y & Sb & ~sbv_y) break;        // a box selected since its visit overlaps it: a real re-scoring
+            if (lane == vslot) { status = 2; ord = nselb; }
+            Sb |= 1u << vslot; ++nselb; ++nsel_cur;
+            u64 mx = status == 1 ? fr : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const u64 other = __shfl_xor_sync(RPP_FULL_MASK, mx, o);
+              mx = other > mx ? other : mx;
+            }
+            vmax = mx;
+            const u32 who = __ballot_sync(RPP_FULL_MASK, status == 1 && fr == mx);
+            vslot = (mx != 0ull) ? __ffs(who) - 1 : -1;
+          } else {
+            const int x = next_unv;
+            if (__shfl_sync(RPP_FULL_MASK, om, x) & Sb) break;   // overlaps a box selected inside the batch
+            const u64 fr_x = __shfl_sync(RPP_FULL_MASK, fr, x);
+            if (fr_x == ukey) {                    // score unchanged: selected
+              if (lane == x) { status = 2; ord = nselb; }
+              Sb |= 1u << x; ++nselb; ++nsel_cur;
+            } else if (fr_x == 0ull) {             // fell to the threshold
+              if (lane == x) status = 3;
+            } else {                               // back into the queue, re-scored
+              if (lane == x) { status = 1; vbeg = nsel_cur; sbv = Sb; }
+              if (fr_x > vmax) { vmax = fr_x; vslot = x; }
+            }
+            ++next_unv;
           }
         }
-        // commit the visited prefix
+        const int cut = next_unv;
+        // commit
         u64 mine = 0ull;
-        if (lane < cut) {
+        if (lane < batch && status != 0) {
           const u32 j = key_tie(st);
-          begin[j] = (unsigned short)nsel;    // suppress_begin_index = selected.size() at the visit
-          if (lane == winner) {
+          if (status == 2) {
             float4 box = gs_load_box(P, boxes, gboxes, j);
             float area;
             const float4 cb = canon_box(box, area);
-            kbox[nsel] = area > 0.0f ? cb : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
-            karea[nsel] = area > 0.0f ? area : 0.0f;
-            sel[nsel] = fr;
-          } else {
+            kbox[nsel0 + ord] = area > 0.0f ? cb : make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+            karea[nsel0 + ord] = area > 0.0f ? area : 0.0f;
+            sel[nsel0 + ord] = fr;
+          } else if (status == 1) {
+            begin[j] = (unsigned short)vbeg;      // suppress_begin_index = selected.size() at the visit
             mine = fr;
           }
         }
         // The keys that re-enter the ring: rank among themselves (sorted descending; keys are unique) and position
         // among the ring elements that stay = rank beyond the batch (found by the candidate's warp during the
-        // re-scoring) + the unvisited rest of the batch.  One loop over the batch slots' keys after the commit:
-        // re-scored (visited, not the winner), stale (not visited), none (winner / dropped).
+        // re-scoring) + the unvisited rest of the batch.
         const u64 pk = lane < batch ? (lane < cut ? mine : st) : 0ull;
         int rank = 0, stay = 0;
         for (int l = 0; l < batch; ++l) {
@@ -624,8 +676,8 @@ __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams
         __syncwarp();
         if (lane == 0) {
           sh->n_ins = m; sh->head = head2; sh->cnt = cnt2;
-          sh->cut = cut; sh->winner = winner;
-          if (winner >= 0) sh->nsel = nsel + 1;
+          sh->cut = cut; sh->winner = nselb > 0 ? 0 : -1;
+          sh->nsel = nsel_cur;
         }
       }
       __syncthreads();
@@ -809,5 +861,8 @@ __global__ void __launch_bounds__(RPP_GS_NT) global_soft_kernel(GlobalSoftParams
     if (threadIdx.x == 0)
       printf("global_soft: batches %d (wide %d) merges %d nsel %d | cycles prologue %lld stage1 %lld refresh %lld decide %lld shift %lld loop-exit %lld epilogue %lld\n",
              n_batches, n_wide, n_merge, sh->nsel, dbg[0], dbg[1], dbg[2], dbg[3], dbg[4], dbg[5], dbg[6]);
+    if (threadIdx.x == 0)
+      printf("global_soft refresh(slot 1): setup %lld flags %lld pairs+product %lld rank %lld overlap-mask %lld\n",
+             sh->rdbg[0], sh->rdbg[1], sh->rdbg[2], sh->rdbg[3], sh->rdbg[4]);
   }
 }

@@ -103,16 +103,20 @@ __device__ __forceinline__ float col_score(const ColProblemParams& P, float raw)
   return P.is_logit ? sigmoid_f32(raw) : raw;
 }
 
+// MAPPED = false: the caller knows the rows are rows of the delta tensor itself (the per-class modes' warp probe)
+template <bool MAPPED = true>
 __device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int c, u32 row) {
   if (P.boxes) {
     const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;  // boxes[:, min(q-1, c)] (:440)
     return P.boxes[((size_t)b * P.N + row) * P.q + qi];
   }
-  if (P.row_keys) {
-    const u32 a = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C_src;
-    return decode_box(lv_delta(P.dlv, b, a), P.anchors[a], P.dp);
+  if (MAPPED) {
+    if (P.row_keys) {
+      const u32 a = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C_src;
+      return decode_box(lv_delta(P.dlv, b, a), P.anchors[a], P.dp);
+    }
+    if (P.dlv.L > 0) return decode_box(lv_delta(P.dlv, b, row), P.anchors[row], P.dp);
   }
-  if (P.dlv.L > 0) return decode_box(lv_delta(P.dlv, b, row), P.anchors[row], P.dp);
   return decode_box(lv_delta(P.lv, b, row), P.anchors[row], P.dp);
 }
 
@@ -651,6 +655,7 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
 
 template <int MODE>
 __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParams P) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NmsShared* sh = reinterpret_cast<NmsShared*>(smem_raw);
   SoftShared* ss = reinterpret_cast<SoftShared*>(smem_raw + ((nms_shared_bytes(P.M_lim) + 15) & ~(size_t)15));
@@ -675,6 +680,7 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
 __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int* __restrict__ sel_cnt, int C, int M,
                                       int m1, int Mtop, float* __restrict__ stop_L, const float* __restrict__ bound,
                                       u32* __restrict__ work_items, u32* __restrict__ work_ctl) {
+  pdl_enter();
   extern __shared__ float s_sc[];  // [C * m1]
   __shared__ int s_n;
   __shared__ float s_L;
@@ -742,6 +748,7 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
 }
 
 __global__ void __launch_bounds__(RPP_PROBE_WARPS * 32) probe_warp_kernel(ColProblemParams P, size_t n_problems) {
+  pdl_enter();
   __shared__ ProbeWarpShared s_all[RPP_PROBE_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t p = (size_t)blockIdx.x * RPP_PROBE_WARPS + warp;
@@ -836,7 +843,7 @@ __global__ void __launch_bounds__(RPP_PROBE_WARPS * 32) probe_warp_kernel(ColPro
     float4 bx = make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
     float area = 0.0f;
     if (alive) {
-      orig = col_box(P, b, c, key_tie(key));
+      orig = col_box<false>(P, b, c, key_tie(key));
       if (P.clip_before) orig = clip01(orig);
       const float4 cb = canon_box(orig, area);
       if (area > 0.0f) bx = cb; else area = 0.0f;
@@ -893,6 +900,7 @@ struct EmitShared {
   int valid;
 };
 __global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams P) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
   const int tid = threadIdx.x;

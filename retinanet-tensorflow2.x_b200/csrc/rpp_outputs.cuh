@@ -36,6 +36,7 @@ struct MergeShared {
 };
 
 __global__ void __launch_bounds__(RPP_MERGE_NT) merge_kernel(MergeParams P) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MergeShared* sh = reinterpret_cast<MergeShared*>(smem_raw);
   const int tid = threadIdx.x;
@@ -226,6 +227,7 @@ struct MergePaddedParams {
 };
 
 __global__ void __launch_bounds__(RPP_MERGE_NT) merge_padded_kernel(MergePaddedParams P) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MergeShared* sh = reinterpret_cast<MergeShared*>(smem_raw);
   const int tid = threadIdx.x;
@@ -334,6 +336,7 @@ struct GlobalOutParams {
 };
 
 __global__ void global_out_kernel(GlobalOutParams P) {
+  pdl_enter();
   const int b = blockIdx.x;
   const int valid = P.sel_cnt[b];
   if (threadIdx.x == 0) P.out_valid[b] = valid;

@@ -132,6 +132,7 @@ sample_max_flat4_kernel(const float* __restrict__ x /*16-byte aligned; element `
 // with a few objects has some hundreds of anchors above the threshold, all of them overlapping).
 __global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int rank, int rank_lo, float T_min,
                                    float* __restrict__ T) {
+  pdl_enter();
   extern __shared__ u32 s_gm[];  // [G][RPP_RANK_CPB]
   const int b = blockIdx.x, c0 = blockIdx.y * RPP_RANK_CPB;
   const int nc = C - c0 < RPP_RANK_CPB ? C - c0 : RPP_RANK_CPB;
@@ -163,6 +164,7 @@ __global__ void sample_rank_kernel(const u32* __restrict__ gm, int C, int G, int
 __global__ void __launch_bounds__(RPP_RANK_CPB * 32)
 sample_rank_sort_kernel(const u32* __restrict__ gm, int C, int G, int rank, int rank_lo, float T_min,
                         float* __restrict__ T) {
+  pdl_enter();
   __shared__ u32 s_gm[128 * RPP_RANK_CPB];
   const int b = blockIdx.x, c0 = blockIdx.y * RPP_RANK_CPB;
   const int nc = C - c0 < RPP_RANK_CPB ? C - c0 : RPP_RANK_CPB;

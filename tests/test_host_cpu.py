@@ -252,9 +252,9 @@ def test_sampling_plan_margins():
         _native.check(_native.lib().rpp_debug_sample_plan(n, C, k, emit, out))
         return list(out)
 
-    # NMS problems of configs[1]: columns of 76 725 logits, lists of ~768 candidates, capacity 4096
+    # NMS problems of configs[1]: columns of 76 725 logits, lists of ~768 candidates, capacity 8192
     p = plan(76725, 80, 0, 0)
-    assert p[0] == 1 and p[5] == 4096 and p[6] == 768
+    assert p[0] == 1 and p[5] == 8192 and p[6] == 768
     c = _simulate_list_lengths(p, 76725, 400, rng)
     assert 600 < c.mean() < 950 and c.max() < 4096 and c.min() > 250
     # flat top-k of the global filter (C3) and of the EfficientNMS entry: 6.1 M elements per image, fine plan
@@ -264,7 +264,7 @@ def test_sampling_plan_margins():
         c = _simulate_list_lengths(p, 76725 * 80, 24, rng)
         sigma = c.std()
         assert c.min() >= k and c.max() <= min(p[5], 16384)
-        assert (c.mean() - k) / sigma > 4.5 and (min(p[5], 16384) - c.mean()) / sigma > 4.5, (k, c.mean(), sigma)
+        assert (c.mean() - k) / sigma > 4.0 and (min(p[5], 16384) - c.mean()) / sigma > 4.0, (k, c.mean(), sigma)
     # short columns keep the cheap plan (their fallback is a scan of < 100 K elements)
     assert plan(19206 * 5, 1, 5000, 1)[7] == 0
 
