@@ -6,6 +6,7 @@ reference (slice by valid_detections, rescale, int32 truncation, xyxy -> xywh, c
 import ctypes
 import json
 
+import numpy as np
 import torch
 
 from retinanet import _native
@@ -32,7 +33,7 @@ class COCOEvaluator:
 
     def _handle(self, mode, num_classes, max_detections):
         from retinanet.model.layers.postprocessing_ops import _Handle
-        key = (mode, num_classes, max_detections)
+        key = (mode, num_classes, max_detections, torch.cuda.current_device())   # a handle belongs to its device
         if key not in self._handles:
             self._handles[key] = _Handle(H=self._input_shape[0], W=self._input_shape[1], num_classes=num_classes,
                                          mode=mode, max_detections=max_detections)
@@ -45,15 +46,44 @@ class COCOEvaluator:
     def accumulate_results(self, results, rescale_detections=True):
         image_ids = results['image_id']
         det = results['detections']
-        boxes, scores, classes, valid = det['boxes'], det['scores'], det['classes'], det['valid_detections']
+        # the reference takes numpy / TF host arrays here (:111-116); the kernel reads device memory, so everything is
+        # brought to one CUDA device, made contiguous and given the dtypes the kernel expects before its raw pointers
+        # are handed over (host tensors, e.g. the result of gather_detections(...).cpu(), are copied)
+        def as_tensor(v):
+            return v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v))
+        boxes, scores, classes, valid = (as_tensor(det[k]) for k in ('boxes', 'scores', 'classes', 'valid_detections'))
+        dev = next((t.device for t in (boxes, scores, classes, valid) if t.is_cuda),
+                   torch.device('cuda', torch.cuda.current_device()))
+        if classes.dtype not in (torch.float32, torch.int64, torch.int32):
+            raise TypeError('classes must be float32 (CombinedNMS), int64 (Global*) or int32 (PerClass*), got {}'
+                            .format(classes.dtype))
+        boxes = boxes.to(device=dev, dtype=torch.float32).contiguous()
+        scores = scores.to(device=dev, dtype=torch.float32).contiguous()
+        classes = classes.to(device=dev).contiguous()
+        valid = valid.to(device=dev, dtype=torch.int32).contiguous()
+        if scores.dim() != 2 or tuple(boxes.shape) != tuple(scores.shape) + (4,) or classes.shape != scores.shape \
+                or valid.shape != scores.shape[:1]:
+            raise ValueError('detections must be boxes [B,M,4], scores [B,M], classes [B,M], valid_detections [B]; got '
+                             '{}, {}, {}, {}'.format(tuple(boxes.shape), tuple(scores.shape), tuple(classes.shape),
+                                                     tuple(valid.shape)))
         B, M = scores.shape
+        if len(image_ids) != B:
+            raise ValueError('{} image ids for {} images'.format(len(image_ids), B))
         mode = {torch.float32: 'CombinedNMS', torch.int64: 'GlobalHardNMS', torch.int32: 'PerClassHardNMS'}[classes.dtype]
         num_classes = len(self._class_id_map) if self._class_id_map else 1
+        with torch.cuda.device(dev):
+            return self._accumulate_on_device(results, image_ids, boxes, scores, classes, valid, B, M, mode, num_classes,
+                                              dev, rescale_detections)
+
+    def _accumulate_on_device(self, results, image_ids, boxes, scores, classes, valid, B, M, mode, num_classes, dev,
+                              rescale_detections):
         h = self._handle(mode, num_classes, M)
-        dev = boxes.device
         scale = None
         if rescale_detections:
-            scale = torch.as_tensor(results['resize_scale'], dtype=torch.float32, device=dev).reshape(B, 2).contiguous()
+            scale = torch.as_tensor(np.asarray(results['resize_scale']), dtype=torch.float32).to(dev)
+            if scale.numel() != 2 * B:
+                raise ValueError('resize_scale must hold [B,2] values')
+            scale = scale.reshape(B, 2).contiguous()
         cmap = None
         if self._remap_class_ids and self._class_id_map:
             cmap = torch.tensor(self._class_id_map, dtype=torch.int32, device=dev)
@@ -63,8 +93,8 @@ class COCOEvaluator:
         img = torch.empty((B * M,), dtype=torch.int32, device=dev)
         total = torch.zeros((1,), dtype=torch.int32, device=dev)
         _native.check(_native.lib().rpp_coco_format(
-            h.ptr, boxes.contiguous().data_ptr(), scores.contiguous().data_ptr(), classes.contiguous().data_ptr(),
-            valid.contiguous().data_ptr(), B, scale.data_ptr() if scale is not None else None,
+            h.ptr, boxes.data_ptr(), scores.data_ptr(), classes.data_ptr(), valid.data_ptr(), B,
+            scale.data_ptr() if scale is not None else None,
             cmap.data_ptr() if cmap is not None else None, bbox.data_ptr(), cat.data_ptr(), sc.data_ptr(),
             img.data_ptr(), total.data_ptr(), torch.cuda.current_stream().cuda_stream))
         t = int(total.item())

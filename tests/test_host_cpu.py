@@ -344,3 +344,55 @@ def test_abi_smoke_runs_from_plain_c(tmp_path):
     out = subprocess.run([_build_abi_smoke(tmp_path)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert 'abi_smoke ok' in out.stdout
+
+
+def test_serving_signature_rekeying():
+    """export.py:233-253: positional re-keying of the sorted frozen outputs, including the
+    mis-named keys of the skip_nms (onnx_tensorrt) case."""
+    from retinanet.export import InferenceModule, frozen_outputs, make_inference_module
+    det = {'scores': 's', 'boxes': 'b', 'classes': 'c', 'valid_detections': 'v'}
+    assert frozen_outputs(det) == ['b', 'c', 's', 'v']
+    m = InferenceModule(lambda **kw: det, skip_nms=False)
+    assert m.run_inference({}) == {'boxes': 'b', 'scores': 's', 'classes': 'c', 'valid_detections': 'v'}
+    fused = {'class_logits': 'L', 'encoded_boxes': 'E'}
+    m = InferenceModule(lambda **kw: fused, skip_nms=True)
+    assert m.run_inference({}) == {'boxes': 'L', 'scores': 'E'}          # B22: the reference's mis-named keys
+    m = make_inference_module(lambda x: dict(det, seen=None) and det, mode='tf')
+    assert m.run_inference({'predictions': 1})['valid_detections'] == 'v'
+    assert make_inference_module(lambda x: fused, mode='onnx_tensorrt').skip_nms
+
+
+def test_clustered_synthetic_inputs_are_seeded_and_peaked():
+    """tools/synth_inputs.py (bench.py's third logit distribution): same seed -> same tensors; a background floor with
+    a small fraction of anchors above the score threshold, clustered on the objects' classes."""
+    import torch
+    from oracle import ref as _ref
+    sys.path.insert(0, ROOT)
+    from tools import synth_inputs
+    ap = REFERENCE_CONFIG['anchor_params']
+    anchors, _ = _ref.anchors(128, 128, 3, 7, ap['areas'], ap['aspect_ratios'], ap['scales'])
+    a = synth_inputs.clustered_inputs(2, torch.from_numpy(anchors), 8, 128, 128, 'cpu', seed=5)
+    b = synth_inputs.clustered_inputs(2, torch.from_numpy(anchors), 8, 128, 128, 'cpu', seed=5)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    frac = float((torch.sigmoid(a[0]) > 0.05).float().mean())
+    assert 0.0005 < frac < 0.2
+    assert float(a[1].abs().max()) <= 4.0
+    assert synth_inputs.make_inputs('sparse', 1, torch.from_numpy(anchors), 8, 128, 128, 'cpu')[0].mean() < -3
+
+
+def test_bench_workloads_match_baseline_configs():
+    """bench.py's workload table = BASELINE.json `configs`: shapes, modes, batch sizes, byte counts."""
+    sys.path.insert(0, ROOT)
+    import bench
+    w = bench.WORKLOADS
+    assert (w['c2']['H'], w['c2']['C'], w['c2']['batch'], w['c2']['mode']) == (640, 80, 64, 'PerClassHardNMS')
+    assert (w['c3']['mode'], w['c3']['per_class'], w['c3']['scaling']) == ('GlobalSoftNMS', False, 'strong')
+    assert (w['c4']['H'], w['c4']['batch'], w['c4']['mode']) == (1024, 32, 'CombinedNMS')
+    assert (w['c5']['H'], w['c5']['C'], w['c5']['batch'], w['c5']['mode']) == (320, 5, 512, 'GlobalHardNMS')
+    assert w['c1']['batch'] == 1 and w['c1']['mode'] == 'CombinedNMS'
+    assert bench.num_anchors(640) == 76725 and bench.num_anchors(1024) == 196416 and bench.num_anchors(320) == 19206
+    assert bench.path_bytes_per_image(w['c2']) == 25782004
+    assert bench.path_bytes_per_image(w['c4']) == 65998180 and bench.path_bytes_per_image(w['c5']) == 693820
+    p = bench.workload_params(w['c3'])
+    assert p.inference.mode == 'GlobalSoftNMS' and p.inference.filter_per_class is False
+    assert p.inference.pre_nms_top_k == 5000 and p.inference.soft_nms_sigma == 0.5

@@ -109,3 +109,15 @@ def test_padded_nms_select_from_three_clusters(ref):
     # derived: with a score threshold of 0.4 box 5 is filtered (scores and boxes zeroed before the sort)
     idx, valid = ref.nms_padded(BOXES, SCORES, 3, 0.5, 0.4)
     assert valid == 2 and idx.tolist() == [3, 0, 0]
+
+
+def test_topk_v2_vectors(ref):
+    # topk_op_test.py TopKTest.testTop3Vector / testTop2 (and the tf.math.top_k docstring example); ties go to the
+    # lower index (testTensorStableSort / "stable" in the op's documentation: derived vector below)
+    v = np.array([[3, 6, 15, 18, 6, 12, 1, 17, 3, 0, 4, 19, 1, 6]], np.float32)
+    assert ref.topk(v, 3).tolist() == [[11, 3, 7]]
+    v = np.array([[0.1, 0.3, 0.2, 0.4], [0.1, 0.3, 0.4, 0.2]], np.float32)
+    assert ref.topk(v, 2).tolist() == [[3, 1], [2, 1]]
+    v = np.array([[5, 7, 7, 5, 7, 1]], np.float32)           # derived: ties -> lower index first
+    assert ref.topk(v, 4).tolist() == [[1, 2, 4, 0]]
+    assert ref.topk(v, 6).tolist() == [[1, 2, 4, 0, 3, 5]]   # k == num_cols: fully sorted

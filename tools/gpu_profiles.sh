@@ -1,0 +1,32 @@
+#!/bin/bash
+# Round profiles (usage: tools/gpu_profiles.sh r02): launch lists per BASELINE config + ncu --set full captures of the
+# dominant kernels, summarised into gpurun_out/<TAG>_*.txt (copied into profiles/ by hand).
+TAG=${1:-r02}
+KREG='regex:sample|collect|probe|perclass|col_problem|merge|emit|global|rowmax|fill_|topk|fused|sigmoid_k|decode_k|effnms|coco'
+for w in c1 c2 c3 c4 c5 c2s c2:clustered c3:clustered; do
+  timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -c 120 --csv \
+    --log-file gpurun_out/${TAG}_launches_${w/:/_}.csv python bench.py --workload ${w%%:*} \
+    $( [[ $w == *:* ]] && echo --logits ${w#*:} ) --quick --steps 3 --warmup 3 > gpurun_out/${TAG}_ncu_${w/:/_}.log 2>&1
+  echo "== $w"; python tools/launch_summary.py gpurun_out/${TAG}_launches_${w/:/_}.csv | tail -n +2
+done > gpurun_out/${TAG}_launch_summary.txt 2>&1
+full() {  # workload kernel-regex
+  timeout 300 ncu --set full --import-source on --clock-control none -k "regex:$2" -c 1 -f \
+    -o gpurun_out/${TAG}_full_$1_$3 python bench.py --workload ${1%%:*} $( [[ $1 == *:* ]] && echo --logits ${1#*:} ) \
+    --quick --steps 2 --warmup 3 > gpurun_out/${TAG}_fullncu_$3.log 2>&1
+  python tools/ncu_summary.py gpurun_out/${TAG}_full_$1_$3.ncu-rep >> gpurun_out/${TAG}_ncu_summary.txt 2>&1
+  python tools/ncu_lines.py gpurun_out/${TAG}_full_$1_$3.ncu-rep "$2" 25 > gpurun_out/${TAG}_ncu_lines_$3.txt 2>&1
+  rm -f gpurun_out/${TAG}_full_$1_$3.ncu-rep   # (the merge back is capped at 64 MiB: keep the text, drop the report)
+}
+rm -f gpurun_out/${TAG}_ncu_summary.txt
+full c2 collect_cols4_kernel collect_cols4
+full c2 probe_warp_kernel probe_warp
+full c2 'col_problem_kernel' col_problem_finish
+full c2 merge_kernel merge
+full c2 'sample_max_kernel' sample_max
+full c3 collect_flat_kernel collect_flat
+full c3 emit_sort_kernel emit_sort
+full c3 global_rows_kernel global_rows
+full c3 global_soft_kernel global_soft
+full c5 global_top_kernel global_top
+full c4 collect_cols4_kernel collect_cols4_c4
+tail -5 gpurun_out/${TAG}_launch_summary.txt; wc -l gpurun_out/${TAG}_ncu_summary.txt
