@@ -110,14 +110,20 @@ __device__ __forceinline__ float4 col_box(const ColProblemParams& P, int b, int 
     const int qi = P.q > 1 ? (c < P.q - 1 ? c : P.q - 1) : 0;  // boxes[:, min(q-1, c)] (:440)
     return P.boxes[((size_t)b * P.N + row) * P.q + qi];
   }
+  // (one decode_box per call site: the row / delta source is selected first — three inlined copies of the binary64
+  // exp code per site cost the soft per-class kernel 70 % of its speed)
+  bool use_dlv = false;
   if (MAPPED) {
     if (P.row_keys) {
-      const u32 a = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C_src;
-      return decode_box(lv_delta(P.dlv, b, a), P.anchors[a], P.dp);
+      row = key_tie(P.row_keys[(size_t)b * P.k_rows + row]) / (u32)P.C_src;
+      use_dlv = true;
+    } else if (P.dlv.L > 0) {
+      use_dlv = true;
     }
-    if (P.dlv.L > 0) return decode_box(lv_delta(P.dlv, b, row), P.anchors[row], P.dp);
   }
-  return decode_box(lv_delta(P.lv, b, row), P.anchors[row], P.dp);
+  float4 d;
+  if (MAPPED && use_dlv) d = lv_delta(P.dlv, b, row); else d = lv_delta(P.lv, b, row);
+  return decode_box(d, P.anchors[row], P.dp);
 }
 
 // Greedy hard NMS over one sorted chunk (m keys in sh->chunk).  The chunk is walked in groups of RPP_NMS_NT
