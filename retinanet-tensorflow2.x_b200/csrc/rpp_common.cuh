@@ -47,9 +47,11 @@ __device__ __forceinline__ u32 key_tie(u64 k) { return 0xffffffffu - (u32)k; }
 // ---------------------------------------------------------------------------------------------------------------
 // tf.nn.sigmoid (postprocessing_ops.py:114): the exact logistic evaluated in binary64 and rounded once to
 // binary32 (DESIGN.md "Numerics").  Only evaluated for candidates that survive the raw-logit pre-threshold.
-__device__ __forceinline__ float sigmoid_f32(float x) { return (float)(1.0 / (1.0 + exp(-(double)x))); }
+// (not inlined: the binary64 exp is ~150 instructions and the problem kernels call it from a dozen sites; measured
+// -7 us on the NMS stage of configs[1].  decode_box stays inlined: as a call it costs the soft per-class kernel 25 %.)
+__device__ __noinline__ float sigmoid_f32(float x) { return (float)(1.0 / (1.0 + exp(-(double)x))); }
 // tf.math.exp (postprocessing_ops.py:97)
-__device__ __forceinline__ float exp_f32(float x) { return (float)exp((double)x); }
+__device__ __noinline__ float exp_f32(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 __device__ __forceinline__ float4 clip01(float4 b) {
   return make_float4(clip01(b.x), clip01(b.y), clip01(b.z), clip01(b.w));
