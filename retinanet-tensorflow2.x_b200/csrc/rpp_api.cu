@@ -69,6 +69,7 @@ struct Handle {
   int force_scan;
   int warp_probe;        // env RPP_WARP_PROBE (default 1): warp-per-problem probe kernel for the hard modes
   int probe_extra;       // env RPP_PROBE_EXTRA: boxes per class kept by the probe beyond ceil(M / C)
+  int top_direct;        // env RPP_TOP_DIRECT (default 1): GlobalHardNMS behind the global filter straight from the lists
   int pdl;               // env RPP_PDL (default 1): programmatic dependent launch between the kernels of a pipeline
   int two_pass;          // env RPP_TWO_PASS (default 1): probe / bound / finish scheme of the per-class modes
   int collect_ctas;      // env RPP_COLLECT_CTAS: CTAs per SM of the collect kernel (0 = automatic)
@@ -250,7 +251,9 @@ struct ProblemSet {
   int two_pass_m1;         // > 0: probe with this many kept per class, bound per image, finish (per-class modes)
   int padded;              // RPP_CONSUME_PADDED: 1 global (score filter inside), 2 per class (no score filter inside)
   int row0_mode;
+  const GlobalTopDirectParams* direct;   // emission for GlobalHardNMS behind the global filter: global_top_direct_kernel first
   // out (workspace)
+  int* emit_done;
   u64* sel_key; float4* sel_box; int* sel_cnt; u64* emit_key;
   float* pad_score; float4* pad_box;
 };
@@ -283,6 +286,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   if (emit) {
     ps.emit_key = ar.take<u64>(P * (size_t)ps.k_lim);
     emit_done = ar.take<int>(P);
+    ps.emit_done = emit_done;
   } else {
     ps.sel_cnt = ar.take<int>(P);
     ps.sel_key = ar.take<u64>(P * (size_t)ps.M);
@@ -564,6 +568,12 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 96;   // re-run classes usually need a few dozen boxes
     pp.work_items = work_items; pp.work_ctl = work_ctl;
   }
+  if (emit && ps.direct && C == 1) {   // detections straight from the lists; what follows only does the images it left
+    pp.emit_direct = 1;
+    launch_k(h->pdl, global_top_direct_kernel, dim3((unsigned)P), dim3(RPP_EMIT_NT), sizeof(EmitShared), st, pp, *ps.direct);
+    LAUNCHED();
+    stage_mark(h, "nms:global_top_direct", st);
+  }
   if (emit) {   // whole-list sort in shared memory where it applies; the generic kernel takes the rest
     launch_k(h->pdl, emit_sort_kernel, dim3((unsigned)P), dim3(RPP_EMIT_NT), sizeof(EmitShared), st, pp);
     LAUNCHED();
@@ -789,8 +799,10 @@ int global_pipeline(Handle* h, Arena& ar, const float* x, int is_logit, const fl
 
 // Sorted top-k keys of every column of x [B,n,C] (C = 1 with n = rows*classes for the global filter).
 int topk_keys(Handle* h, Arena& ar, const float* x, int is_logit, int B, long n, int C, long k, u64** emit_key,
-              cudaStream_t st, const Levels* levels = nullptr) {
+              cudaStream_t st, const Levels* levels = nullptr, const GlobalTopDirectParams* direct = nullptr,
+              int** emit_done = nullptr) {
   ProblemSet ps{};
+  ps.direct = direct;
   ps.x = x; ps.is_logit = is_logit; ps.B = B; ps.n = n; ps.C = C;
   ps.levels = levels;
   ps.q = 1;
@@ -800,6 +812,7 @@ int topk_keys(Handle* h, Arena& ar, const float* x, int is_logit, int B, long n,
   ps.T_min = -INFINITY;
   int rc = run_problem_set(h, ar, ps, st);
   *emit_key = ps.emit_key;
+  if (emit_done) *emit_done = ps.emit_done;
   return rc;
 }
 
@@ -877,16 +890,29 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   for (int l = 0; l <= lv.L; ++l) flat.off[l] = lv.off[l] * C;
   for (int l = 0; l < RPP_MAX_LEVELS; ++l) flat.d[l] = nullptr;
   u64* keys = nullptr;
-  int rc = topk_keys(h, ar, levels ? nullptr : logits, 1, B, N * C, 1, k, &keys, st, levels ? &flat : nullptr);
+  float iou_thr = 0.0f, sigma_tf = 0.0f;
+  if (!per_class) nms_v5_args(c, &iou_thr, &sigma_tf);
+  const int M = c.max_detections;
+  const bool top_only = !per_class && sigma_tf == 0.0f && !tpu_branch(c) && M <= 1024;   // GlobalHardNMS: no suppression (B1)
+  // GlobalHardNMS: one block per image turns the candidate list into the detections (global_top_direct_kernel); the
+  // emission / rows / top kernels below only see the images it could not serve
+  const bool direct = top_only && h->top_direct && (long)C * std::min<long>(M, k) <= RPP_GTD_CAND;
+  GlobalTopDirectParams gd{};
+  int* skip = nullptr;
+  if (direct) {
+    gd.src = lv; gd.C = C; gd.N = N; gd.M = M; gd.anchors = h->d_anchors; gd.dp = h->dp;
+    gd.score_threshold = c.score_threshold;
+    gd.debug = getenv("RPP_GTD_DEBUG") ? 1 : 0;
+    gd.out_boxes = out.boxes; gd.out_scores = out.scores; gd.out_classes = (long long*)out.classes;
+    gd.out_valid = out.valid;
+  }
+  int rc = topk_keys(h, ar, levels ? nullptr : logits, 1, B, N * C, 1, k, &keys, st, levels ? &flat : nullptr,
+                     direct ? &gd : nullptr, direct ? &skip : nullptr);
   if (rc) return rc;
   if (!per_class) {
     // ... Global*: the rows the reference gathers are never materialised (rpp_global.cuh): row maxima, boxes and the
     // NonMaxSuppressionV5 order come straight from the sorted keys
-    float iou_thr, sigma_tf;
-    nms_v5_args(c, &iou_thr, &sigma_tf);
-    const int M = c.max_detections;
     const bool soft = sigma_tf > 0.0f && !tpu_branch(c) && k <= RPP_GS_MAXK;
-    const bool top_only = sigma_tf == 0.0f && !tpu_branch(c) && M <= 1024;   // GlobalHardNMS: no suppression (B1)
     u32* first = ar.take<u32>((size_t)B * N);
     float* mraw = ar.take<float>((size_t)B * k);
     float4* box_spill = soft ? ar.take<float4>((size_t)B * k) : nullptr;
@@ -894,12 +920,13 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
     u64* dkey = (soft || top_only) ? ar.take<u64>((size_t)B * k) : nullptr;
     int* sd_cnt = (soft || top_only) ? ar.take<int>((size_t)B * 2) : nullptr;
     if (!ar.dry) {
-      CUDA_OK(cudaMemsetAsync(first, 0xff, (size_t)B * N * sizeof(u32), st));
+      if (!direct) CUDA_OK(cudaMemsetAsync(first, 0xff, (size_t)B * N * sizeof(u32), st));
       GlobalRowsParams rp{};
+      rp.skip = skip; rp.init_first = direct ? 1 : 0;
       rp.emit_key = keys; rp.k = k; rp.C = C; rp.N = N;
       rp.first = first; rp.mraw = mraw; rp.skey = skey; rp.dkey = dkey; rp.sd_cnt = sd_cnt;
       rp.score_threshold = c.score_threshold;
-      launch_k(false /* follows a memset, not a kernel */, global_rows_kernel, dim3(B), dim3(RPP_GROWS_NT), 0, st, rp);
+      launch_k(direct && h->pdl /* otherwise it follows a memset, not a kernel */, global_rows_kernel, dim3(B), dim3(RPP_GROWS_NT), 0, st, rp);
       LAUNCHED();
       stage_mark(h, "rows:resolve", st);
     }
@@ -937,6 +964,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       tp.emit_key = keys; tp.lv = lv; tp.C = C; tp.N = N; tp.anchors = h->d_anchors; tp.dp = h->dp;
       tp.out_boxes = out.boxes; tp.out_scores = out.scores; tp.out_classes = (long long*)out.classes;
       tp.out_valid = out.valid;
+      tp.skip = skip;
       launch_k(h->pdl, global_top_kernel, dim3(B), dim3(RPP_GTOP_NT), 0, st, tp);
       LAUNCHED();
       stage_mark(h, "nms:global_top", st);
@@ -1070,6 +1098,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     h->two_pass = v ? atoi(v) : 1;
     v = getenv("RPP_PDL");
     h->pdl = v ? atoi(v) : 1;
+    v = getenv("RPP_TOP_DIRECT");
+    h->top_direct = v ? atoi(v) : 1;
     v = getenv("RPP_COLLECT_CTAS");
     h->collect_ctas = v ? atoi(v) : 0;
     h->overlap_hint = 0;
@@ -1127,6 +1157,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(merge_padded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(global_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(emit_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(global_top_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -33,6 +33,8 @@ struct GlobalRowsParams {
   u64* dkey;             // [B][k]
   int* sd_cnt;           // [B][2] = {ns, nd}
   float score_threshold;
+  const int* skip;       // [B] or nullptr: 2 = global_top_direct_kernel already did the image
+  int init_first;        // the block presets its image's `first` itself (no memset ahead of the kernel)
 };
 
 // candidate key of the Global* NMS: (score, row index j) with the row's payload slot free in the low bits
@@ -49,6 +51,11 @@ __global__ void __launch_bounds__(RPP_GROWS_NT) global_rows_kernel(GlobalRowsPar
   const u64* ek = P.emit_key + (size_t)b * P.k;
   u32* fr = P.first + (size_t)b * P.N;
   const long span = (long)RPP_GROWS_NT * RPP_GROWS_RPT;
+  if (P.skip && P.skip[b] == 2) return;
+  if (P.init_first) {
+    for (long i = tid; i < P.N; i += RPP_GROWS_NT) fr[i] = 0xffffffffu;
+    __syncthreads();
+  }
   // pass A: first[anchor] = lowest row index of the anchor (loads first, then the reductions: nothing waits)
   for (long j0 = 0; j0 < P.k; j0 += span) {
     u64 key[RPP_GROWS_RPT];
@@ -134,6 +141,7 @@ struct GlobalTopParams {
   const u64* emit_key; Levels lv; int C; long N;
   const float4* anchors; DecodeParams dp;
   float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
+  const int* skip;       // [B] or nullptr: 2 = global_top_direct_kernel already did the image
 };
 
 struct GlobalTopShared {
@@ -147,6 +155,7 @@ __global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams
   __shared__ GlobalTopShared sh;
   const int tid = threadIdx.x, lane = tid & 31;
   const int b = blockIdx.x;
+  if (P.skip && P.skip[b] == 2) return;
   const int ns = P.sd_cnt[2 * b], nd = P.sd_cnt[2 * b + 1];
   const int n1 = ns < P.M ? ns : P.M;
   const u64* sk = P.skey + (size_t)b * P.k;
@@ -210,6 +219,203 @@ __global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams
       P.out_classes[o] = -1;
     }
   }
+}
+
+// ===============================================================================================================
+// global_top_direct_kernel — the whole GlobalHardNMS-behind-the-global-filter stage of one image in ONE block, straight
+// from the image's candidate list: no sorted top-k emission, no row resolution.  (configs[4]: the 8 192-key sort was
+// half of the step.)  With nothing suppressed (see global_top_kernel) the detections are the first M rows in
+// (row maximum desc, row index asc) order, and a row's index is the rank of its own (anchor, class) pair in the top k:
+//   * K_cut = the k-th best pair key (exact radix descent over the scored list in shared memory, counting only);
+//   * an output row's anchor has its best pair among the M best pairs (the pairs ahead of an anchor's best pair all
+//     precede that pair's row in the output order), so: the M best pairs, sorted (select_chunk);
+//   * for each distinct anchor among them, all C classes are looked up in the logits: the pairs with key >= K_cut are
+//     exactly the anchor's rows (its duplicates, B12), each keyed (anchor's best score, own pair key);
+//   * the M best of those candidates (rank by counting: a few hundred at most) are written out.
+// A block that cannot serve its image (short list beyond the in-block re-collection, candidate overflow) leaves
+// emit_done = 0 and the emission / rows / top kernels that follow do the image; they skip the images marked 2.
+// ===============================================================================================================
+#define RPP_GTD_CAND 4096
+
+struct GlobalTopDirectParams {
+  Levels src;              // the [B, N, C] logits + deltas (class lookups, boxes)
+  int C; long N; int M;
+  const float4* anchors; DecodeParams dp;
+  float score_threshold;   // of the NMS (the emission problem's own threshold is -inf: tf.nn.top_k has none)
+  int debug;               // env RPP_GTD_DEBUG: block 0 prints its per-phase cycle counts
+  float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
+};
+
+// k-th largest (1-based) of the non-zero unique keys in shared memory; at least kth of them exist.
+__device__ u64 block_kth_key(const u64* keys, int n, u32 kth, SelectScratch<RPP_EMIT_NT>* sc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u32 cnt = 0;
+  u64 mx = 0ull, mn = ~0ull;
+  for (int i = tid; i < n; i += RPP_EMIT_NT) {
+    const u64 k = keys[i];
+    if (k != 0ull) { ++cnt; mx = k > mx ? k : mx; mn = k < mn ? k : mn; }
+  }
+  block_cnt_max_min<RPP_EMIT_NT>(cnt, mx, mn, &sc->bs);
+  if (mn == mx) return mx;
+  int top_shift = 64 - __clzll((long long)(mn ^ mx));   // bits >= top_shift are common to every key
+  u64 base = top_shift >= 64 ? 0ull : ((mx >> top_shift) << top_shift);
+  u32 remaining = kth;
+  for (;;) {
+    const int bits = top_shift < RPP_RADIX_BITS ? top_shift : RPP_RADIX_BITS;
+    const int shift = top_shift - bits;
+    sc->hist[tid] = 0;   // RPP_RADIX_BINS == RPP_EMIT_NT
+    __syncthreads();
+    for (int i = tid; i < n; i += RPP_EMIT_NT) {
+      const u64 k = keys[i];
+      if (k != 0ull && k >= base && (top_shift >= 64 || ((k - base) >> top_shift) == 0ull))
+        atomicAdd(&sc->hist[(u32)((k - base) >> shift)], 1u);
+    }
+    __syncthreads();
+    // thread t owns bin t: inclusive suffix count over the bins >= t
+    const u32 h = sc->hist[tid];
+    u32 v = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_down_sync(RPP_FULL_MASK, v, o);
+      if (lane + o < 32) v += t;
+    }
+    if (lane == 0) sc->part[warp] = v;
+    __syncthreads();
+    u32 above = v - h;
+    for (int w = warp + 1; w < RPP_EMIT_NT / 32; ++w) above += sc->part[w];
+    if (above < remaining && above + h >= remaining) { sc->d_star = (u32)tid; sc->cum_above = above; sc->cnt_bin = h; }
+    __syncthreads();
+    const u32 d = sc->d_star;
+    remaining -= sc->cum_above;
+    const u32 cnt_bin = sc->cnt_bin;
+    base += (u64)d << shift;
+    top_shift = shift;
+    if (shift == 0) return base;
+    if (cnt_bin == 1) {   // the only key left under the prefix
+      __syncthreads();
+      for (int i = tid; i < n; i += RPP_EMIT_NT) {
+        const u64 k = keys[i];
+        if (k != 0ull && k >= base && ((k - base) >> top_shift) == 0ull) sc->bs.ra = k;
+      }
+      __syncthreads();
+      return sc->bs.ra;
+    }
+    __syncthreads();   // hist / d_star are rewritten next round
+  }
+}
+
+static_assert(RPP_RADIX_BINS == RPP_EMIT_NT, "block_kth_key: one bin per thread");
+static_assert(RPP_EMIT_CHUNK * 8 >= (1024 + 1024) * 8 + RPP_GTD_CAND * 12, "global_top_direct_kernel: scratch layout");
+
+__global__ void __launch_bounds__(RPP_EMIT_NT) global_top_direct_kernel(ColProblemParams P, GlobalTopDirectParams G) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
+  __shared__ int s_ncand, s_over;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;   // C == 1: one emission problem per image
+  const size_t p = blockIdx.x;
+  u64* selchunk = sh->chunk;                 // [1024] select_chunk's output
+  u64* top = sh->chunk + 1024;               // [1024] the M best pairs, sorted
+  u64* cown = sh->chunk + 2048;              // [RPP_GTD_CAND] candidate rows: own pair key ...
+  u32* cfirst = reinterpret_cast<u32*>(sh->chunk + 2048 + RPP_GTD_CAND);   // ... and the slot of the anchor's best pair in top[]
+  if (tid == 0) { P.emit_done[p] = 0; s_ncand = 0; s_over = 0; }
+  long long tdbg[6];
+  int ndbg = 0;
+#define GTD_T() do { if (G.debug) tdbg[ndbg++] = clock64(); } while (0)
+  GTD_T();
+  int n_keys = 0;
+  const int nv = emit_prepare(P, sh, p, b, 0, n_keys);
+  if (nv < 0) return;
+  GTD_T();
+  const u64 K_cut = block_kth_key(sh->keys, n_keys, (u32)P.k_lim, &sh->sel);
+  GTD_T();
+  // the M best pairs (a chunk may come back shorter than asked for: loop)
+  const int Mp = (long)G.M < P.k_lim ? G.M : (int)P.k_lim;
+  int got = 0;
+  {
+    u64 KB = ~0ull;
+    while (got < Mp) {
+      const int m = select_chunk<RPP_EMIT_NT>([&](int i) { return sh->keys[i]; }, n_keys, KB, Mp - got, selchunk, 1024,
+                                              &sh->sel);
+      if (m == 0) break;
+      const int take = m < Mp - got ? m : Mp - got;
+      for (int i = tid; i < take; i += RPP_EMIT_NT) top[got + i] = selchunk[i];
+      got += take;
+      __syncthreads();
+    }
+  }
+  GTD_T();
+  // candidate rows: one warp per distinct anchor of the best pairs
+  for (int i = warp; i < got; i += RPP_EMIT_NT / 32) {
+    const u64 kb = top[i];
+    const u32 a = key_tie(kb) / (u32)G.C;
+    bool dup = false;
+    for (int j = lane; j < i; j += 32) dup = dup || key_tie(top[j]) / (u32)G.C == a;
+    if (__any_sync(RPP_FULL_MASK, dup)) continue;           // the anchor's best pair came earlier
+    if (!(key_score(kb) > G.score_threshold)) continue;     // NonMaxSuppressionV5 never sees the row (A.2)
+    for (int c0 = 0; c0 < G.C; c0 += 32) {
+      const int c = c0 + lane;
+      bool in = false;
+      u64 key = 0ull;
+      if (c < G.C) {
+        const float raw = lv_val(G.src, b, a, G.C, c);
+        if (raw >= P.T_min) {
+          key = make_key(col_score(P, raw), a * (u32)G.C + (u32)c);
+          in = key >= K_cut;
+        }
+      }
+      const u32 mask = __ballot_sync(RPP_FULL_MASK, in);
+      if (mask == 0u) continue;
+      int slot0 = 0;
+      if (lane == 0) slot0 = atomicAdd(&s_ncand, __popc(mask));
+      slot0 = __shfl_sync(RPP_FULL_MASK, slot0, 0);
+      if (in) {
+        const int slot = slot0 + __popc(mask & ((1u << lane) - 1u));
+        if (slot < RPP_GTD_CAND) { cown[slot] = key; cfirst[slot] = (u32)i; } else s_over = 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_over) return;   // (cannot happen with C * M <= RPP_GTD_CAND) the kernels that follow do the image
+  GTD_T();
+  const int nc = s_ncand;
+  const int valid = nc < G.M ? nc : G.M;
+  if (tid == 0) { G.out_valid[b] = valid; P.emit_done[p] = 2; }
+  // rank by counting on (anchor's best score desc, own pair key desc) = (row maximum desc, row index asc)
+  for (int i = tid; i < nc; i += RPP_EMIT_NT) {
+    const u64 own = cown[i];
+    const u64 best = top[cfirst[i]];
+    const u32 sb = (u32)(best >> 32);
+    int rank = 0;
+    for (int j = 0; j < nc; ++j) {
+      const u32 sj = (u32)(top[cfirst[j]] >> 32);
+      rank += (sj > sb) || (sj == sb && cown[j] > own);
+    }
+    if (rank < G.M) {
+      const size_t o = (size_t)b * G.M + rank;
+      const u32 a = key_tie(own) / (u32)G.C;
+      G.out_boxes[o] = clip01(decode_box(lv_delta(G.src, b, a), G.anchors[a], G.dp));
+      G.out_scores[o] = key_score(best);
+      G.out_classes[o] = (long long)(key_tie(best) % (u32)G.C);   // tf.argmax of the row: the anchor's best pair
+    }
+  }
+  // padded selected index 0 -> boxes[0] (clipped), score -1, class -1 (:258-268)
+  for (int i = valid + tid; i < G.M; i += RPP_EMIT_NT) {
+    const size_t o = (size_t)b * G.M + i;
+    const u32 a0 = got > 0 ? key_tie(top[0]) / (u32)G.C : 0u;
+    G.out_boxes[o] = clip01(decode_box(lv_delta(G.src, b, a0), G.anchors[a0], G.dp));
+    G.out_scores[o] = -1.0f;
+    G.out_classes[o] = -1;
+  }
+  if (G.debug) {
+    __syncthreads();
+    GTD_T();
+    if (tid == 0 && (b == 0 || b == 300))
+      printf("gtd b=%d n_keys=%d nv=%d nc=%d prepare=%lld kth=%lld topM=%lld cand=%lld out=%lld\n", b, n_keys, nv, nc,
+             tdbg[1] - tdbg[0], tdbg[2] - tdbg[1], tdbg[3] - tdbg[2], tdbg[4] - tdbg[3], tdbg[5] - tdbg[4]);
+  }
+#undef GTD_T
 }
 
 // ===============================================================================================================

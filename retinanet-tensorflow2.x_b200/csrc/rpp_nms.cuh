@@ -69,7 +69,9 @@ struct ColProblemParams {
   long r_cap;
   // top-k emission (FilterTopKDetections): sorted keys of the k_lim best rows
   u64* emit_key;           // [P][k_lim]
-  int* emit_done;          // [P] 1 = emit_sort_kernel already wrote this problem's keys
+  int* emit_done;          // [P] 1 = emit_sort_kernel already wrote this problem's keys; 2 = global_top_direct_kernel
+                           // already wrote the image's detections (nothing downstream has work for it)
+  int emit_direct;         // emit_done was initialised by global_top_direct_kernel
   // tf.image.non_max_suppression_padded semantics (the TPU branches, postprocessing_ops.py:288-432; consumer
   // RPP_CONSUME_PADDED): 1 = _tpu_global_hard_nms (score filter inside), 2 = _tpu_per_class_hard_nms (every row is
   // a candidate; score_threshold / T_min of this struct are -inf and stop_score holds the config threshold)
@@ -905,19 +907,19 @@ struct EmitShared {
   u64 chunk[RPP_EMIT_CHUNK];
   int valid;
 };
-__global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams P) {
-  pdl_enter();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
+// Scored keys of one emission problem in sh->keys[0 .. n_keys): the candidate list (or, when it cannot serve k rows,
+// an in-block exact re-collection of the column).  Returns the number of VALID keys (strictly above everything that is
+// not in sh->keys) — at least k_lim — or -1 when the block cannot serve the problem (the generic kernel takes it).
+__device__ __forceinline__ int emit_prepare(const ColProblemParams& P, EmitShared* sh, size_t p, int b, int c,
+                                            int& n_keys) {
   const int tid = threadIdx.x;
-  const size_t p = blockIdx.x;
-  const int b = (int)(p / P.C), c = (int)(p % P.C);
-  if (tid == 0) { P.emit_done[p] = 0; sh->valid = 0; }
+  if (tid == 0) sh->valid = 0;
+  n_keys = 0;       // scored keys in sh->keys[0 .. n_keys)
   const u32 n_raw = P.cand_count[p];
-  if (n_raw & 0x80000000u) return;
+  if (n_raw & 0x80000000u) return -1;
   const bool list_ok = !(P.force_scan || n_raw > (u32)P.CAP || n_raw > RPP_EMIT_CAP || n_raw == 0);
-  int n_keys = 0;   // scored keys in sh->keys[0 .. n_keys)
-  int nv = 0;       // of which valid (strictly above everything that is not in sh->keys)
+  int nv = 0;       // of which valid
+  __syncthreads();
   if (list_ok) {
     n_keys = (int)n_raw;
     const float T = P.T[p];
@@ -943,12 +945,12 @@ __global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams
     // of the global filter), collect again INSIDE the block with an exact cut: one radix select over the column's
     // RAW keys (value bits | ~row; no sigmoid) delivers its best ~1.1 k .. 16 K rows, everything else is below the
     // cut; the selected rows are scored and, by the edge rule, those strictly above the score of the cut are complete.
-    if (P.force_scan) return;   // debug: the generic kernel's exact scan is what is being tested
+    if (P.force_scan) return -1;   // debug: the generic kernel's exact scan is what is being tested
     __syncthreads();
     u64 KBr = ~0ull;
     u32 population = 0u;
     long want = P.k_lim + P.k_lim / 8 + 64;
-    if (want > RPP_EMIT_CAP) return;   // more than one block's worth: the generic kernel takes it
+    if (want > RPP_EMIT_CAP) return -1;   // more than one block's worth: the generic kernel takes it
     const int m = select_chunk<RPP_EMIT_NT>(
         [&](int i) -> u64 {
           const float raw = lv_val(P.lv, b, i, P.C, c);
@@ -972,8 +974,22 @@ __global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams
     __syncthreads();
     n_keys = m;
     nv = sh->valid;
-    if ((long)nv < P.k_lim) return;   // a huge tie group at the cut, or a coarse radix cut: the generic kernel decides
+    if ((long)nv < P.k_lim) return -1;   // a huge tie group at the cut, or a coarse radix cut: the generic kernel decides
   }
+  return nv;
+}
+
+__global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams P) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
+  const int tid = threadIdx.x;
+  const size_t p = blockIdx.x;
+  const int b = (int)(p / P.C), c = (int)(p % P.C);
+  if (P.emit_direct && P.emit_done[p] == 2) return;   // global_top_direct_kernel already wrote the image's detections
+  if (tid == 0) P.emit_done[p] = 0;
+  int n_keys = 0;
+  if (emit_prepare(P, sh, p, b, c, n_keys) < 0) return;
   // the k best keys, in order: usually ONE exact radix cut to [k, 8192] keys and one bitonic sort of that chunk
   u64 KB = ~0ull;
   long emitted = 0;
