@@ -69,6 +69,7 @@ struct Handle {
   int force_scan;
   int warp_probe;        // env RPP_WARP_PROBE (default 1): warp-per-problem probe kernel for the hard modes
   int probe_extra;       // env RPP_PROBE_EXTRA: boxes per class kept by the probe beyond ceil(M / C)
+  int finish_argmax;     // env RPP_FINISH_ARGMAX (default 1): argmax-iterate consumer in the finish pass of the hard modes
   int top_direct;        // env RPP_TOP_DIRECT (default 1): GlobalHardNMS behind the global filter straight from the lists
   int pdl;               // env RPP_PDL (default 1): programmatic dependent launch between the kernels of a pipeline
   int two_pass;          // env RPP_TWO_PASS (default 1): probe / bound / finish scheme of the per-class modes
@@ -541,7 +542,8 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     // worklist launches (finish pass): a few persistent blocks per SM instead of one block per problem
     const unsigned grid = pp.work_items ? (unsigned)std::min<size_t>(P, (size_t)h->sm_count * 4) : (unsigned)P;
     if (ps.consumer == RPP_CONSUME_HARD)
-      launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_HARD>, dim3(grid), dim3(RPP_NMS_NT), smem_nms, st, pp);
+      launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_HARD>, dim3(grid), dim3(RPP_NMS_NT),
+               smem_nms + (pp.argmax ? RPP_LIST_SMEM * sizeof(float4) : 0), st, pp);
     else if (ps.consumer == RPP_CONSUME_PADDED)
       launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_PADDED>, dim3(grid), dim3(RPP_NMS_NT), smem_nms, st, pp);
     else if (ps.consumer == RPP_CONSUME_SOFT)
@@ -566,6 +568,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
                                                                               work_ctl);
     LAUNCHED();
     pp.pass = 2; pp.M_cap = pp.M_lim; pp.want0 = 96;   // re-run classes usually need a few dozen boxes
+    pp.argmax = ps.consumer == RPP_CONSUME_HARD && h->finish_argmax;
     pp.work_items = work_items; pp.work_ctl = work_ctl;
   }
   if (emit && ps.direct && C == 1) {   // detections straight from the lists; what follows only does the images it left
@@ -1098,6 +1101,8 @@ int rpp_create(const rpp_config* cfg, void** handle) {
     h->two_pass = v ? atoi(v) : 1;
     v = getenv("RPP_PDL");
     h->pdl = v ? atoi(v) : 1;
+    v = getenv("RPP_FINISH_ARGMAX");
+    h->finish_argmax = v ? atoi(v) : 1;
     v = getenv("RPP_TOP_DIRECT");
     h->top_direct = v ? atoi(v) : 1;
     v = getenv("RPP_COLLECT_CTAS");

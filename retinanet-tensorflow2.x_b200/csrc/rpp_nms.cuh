@@ -39,6 +39,8 @@ struct ColProblemParams {
   // kernel turns the probes of an image into stop_L = a lower bound of the image's M-th best final score; pass 2
   // re-runs only the classes whose bound >= stop_L, stopping at the first candidate below stop_L.
   int pass;                // 0 single pass, 1 probe, 2 finish
+  int argmax;              // finish pass of the hard modes: argmax-iterate consumer (dynamic shared memory holds
+                           // RPP_LIST_SMEM candidate boxes behind the kept arrays)
   int M_cap;               // kept limit of this pass
   int want0;               // size of the first chunk
   float* bound;            // [P]
@@ -292,6 +294,97 @@ __device__ void hard_nms_consume(const ColProblemParams& P, NmsShared* sh, int b
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Argmax-iterate hard NMS over one UNSORTED chunk (finish pass of the hard per-class modes).  The classes the finish
+// pass re-runs are the hot ones of a trained detector: hundreds to thousands of anchors of a few objects above the
+// bound, nearly all of them suppressed by the first box of their object, a handful kept.  Sorting them and resolving
+// them tile by tile (hard_nms_consume) spends its time on candidates that die anyway; here every round
+//   * the block takes the best alive key (the next box greedy NMS keeps — same total order, same result),
+//   * every alive candidate tests itself against that ONE box and tracks the best survivor of its thread,
+// so a round is one pass over the chunk's alive slots and two barriers, and the number of rounds is the number of
+// boxes kept.  keys[0..m): scored keys (0 = dead); abox[0..m): their boxes as emitted (decoded here).  Stops (sh->done)
+// at M_cap kept boxes or at the first best key below the image's bound L; returns with the chunk exhausted otherwise.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 canon_or_empty(float4 orig, float& area) {
+  const float4 cb = canon_box(orig, area);
+  if (area > 0.0f) return cb;
+  area = 0.0f;
+  return make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
+}
+
+__device__ void hard_nms_argmax(const ColProblemParams& P, NmsShared* sh, float4* abox, u64* keys, int m, int b, int c,
+                                size_t p, float L) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float4* kbox = nms_kbox(sh);
+  float* karea = nms_karea(sh, P.M_lim);
+  const float thr = P.iou_threshold;
+  int nk = sh->nkept;   // (uniform: written before the barrier that precedes this call)
+  // boxes of the chunk; candidates that a box kept earlier (previous chunks) suppresses die right away
+  u64 best = 0ull;
+  int best_i = -1;
+  for (int i = tid; i < m; i += RPP_NMS_NT) {
+    const u64 k = keys[i];
+    if (k == 0ull) continue;
+    float4 orig = col_box(P, b, c, key_tie(k));
+    if (P.clip_before) orig = clip01(orig);
+    abox[i] = orig;
+    float area;
+    const float4 bx = canon_or_empty(orig, area);
+    bool alive = true;
+    for (int q = 0; q < nk; ++q)
+      if (iou_gt(bx, area, kbox[q], karea[q], thr)) { alive = false; break; }
+    if (!alive) { keys[i] = 0ull; continue; }
+    if (k > best) { best = k; best_i = i; }
+  }
+  u64* red = reinterpret_cast<u64*>(sh->carea);   // [RPP_NMS_NT / 32] per-warp maxima (carea is free in this consumer)
+  for (;;) {
+    u64 wb = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const u64 t = __shfl_xor_sync(RPP_FULL_MASK, wb, o);
+      wb = t > wb ? t : wb;
+    }
+    __syncthreads();   // the previous round's readers of red[] / kbox[nk - 1] are through
+    if (lane == 0) red[warp] = wb;
+    __syncthreads();
+    u64 bk = red[0];
+#pragma unroll
+    for (int w = 1; w < RPP_NMS_NT / 32; ++w) bk = red[w] > bk ? red[w] : bk;
+    if (bk == 0ull) return;                                  // chunk exhausted
+    if (key_score(bk) < L) {                                 // nothing below the image's bound can reach the top M
+      if (tid == 0) sh->done = 1;
+      __syncthreads();
+      return;
+    }
+    if (best == bk) {                                        // exactly one owner: keys are unique
+      const float4 orig = abox[best_i];
+      float area;
+      kbox[nk] = canon_or_empty(orig, area);
+      karea[nk] = area;
+      P.sel_key[p * P.M + nk] = bk;
+      P.sel_box[p * P.M + nk] = orig;
+      keys[best_i] = 0ull;
+      sh->nkept = nk + 1;
+      if (nk + 1 >= P.M_cap) sh->done = 1;
+    }
+    __syncthreads();
+    ++nk;
+    if (nk >= P.M_cap) return;
+    const float4 nb = kbox[nk - 1];
+    const float na = karea[nk - 1];
+    best = 0ull;
+    best_i = -1;
+    for (int i = tid; i < m; i += RPP_NMS_NT) {
+      const u64 k = keys[i];
+      if (k == 0ull) continue;
+      float area;
+      const float4 bx = canon_or_empty(abox[i], area);
+      if (iou_gt(bx, area, nb, na, thr)) { keys[i] = 0ull; continue; }
+      if (k > best) { best = k; best_i = i; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Soft NMS consumer: NonMaxSuppressionV5 with soft_nms_sigma > 0, lazily re-scored exactly as the
 // TF kernel does it.  The priority queue is split in two: candidates never popped yet are the not-yet-consumed part
 // of the sorted stream (their order is static), and candidates popped, decayed and pushed back live in R (shared
@@ -527,6 +620,7 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
     sh->nkept = 0;
     sh->done = 0;
     sh->need_all = 0;
+    sh->nk_slot[0] = 0;
     if (MODE == RPP_CONSUME_SOFT) ss->rcount = 0;
     if (MODE == RPP_CONSUME_PADDED && P.padded == 2) {
       float s0 = -INFINITY;
@@ -571,6 +665,69 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
   // sorted and consumed here; if the consumer wants more, phase A continues below the bound e0 with the full list.
   u64 KB_A = ~0ull;          // phase A consumes keys below this bound
   bool skip_A = false;
+  // ---- finish pass of the hard modes: argmax-iterate over the whole list (hard_nms_argmax) -------------------
+  if (MODE == RPP_CONSUME_HARD && P.pass == 2 && P.argmax && n_list > 0 && (long)n_list <= P.k_lim) {
+    float4* abox = reinterpret_cast<float4*>(ss);
+    const float L = P.stop_L[b];
+    uint2* lst = P.cand + p * (size_t)P.CAP;
+    u64* gkeys = reinterpret_cast<u64*>(lst);
+    const bool in_smem = n_list <= RPP_LIST_SMEM;
+    u64* keys = in_smem ? sh->lkeys : gkeys;
+    // scored keys of the consumable candidates at or above the bound (a logit clearly below the bound's pre-image is
+    // dropped without evaluating the sigmoid); `below` = some consumable candidate was dropped for being below L
+    float raw_lo = -INFINITY;
+    if (P.is_logit && L > 0.0f && L < 1.0f) {
+      const float x = __logf(L / (1.0f - L));
+      raw_lo = x - 1e-3f * (1.0f + fabsf(x));
+    }
+    int below = 0, n_valid = 0;
+    for (int i = tid; i < n_list; i += RPP_NMS_NT) {
+      u64 k = 0ull;
+      if (converted) {
+        k = gkeys[i];
+        if (k != 0ull && key_score(k) < L) { k = 0ull; below = 1; }
+      } else {
+        const uint2 e = lst[i];
+        const float raw = __uint_as_float(e.x);
+        if (P.is_logit && raw < raw_lo) {
+          below = 1;   // (its score is below L; whether it was consumable at all does not matter: it only cuts)
+        } else {
+          const float s = col_score(P, raw);
+          if (s > P.score_threshold && (list_complete || s > s_edge)) {
+            if (s < L) below = 1; else k = make_key(s, e.y);
+          }
+        }
+      }
+      if (in_smem || converted) { if (in_smem) sh->lkeys[i] = k; else if (k == 0ull) gkeys[i] = 0ull; }
+      else gkeys[i] = k;
+      n_valid += k != 0ull;
+    }
+    if (n_valid) atomicAdd(&sh->nk_slot[0], n_valid);   // (zeroed with the other per-problem state above)
+    below = __syncthreads_or(below);
+    n_valid = sh->nk_slot[0];
+    if (!converted && !in_smem && tid == 0) P.cand_count[p] = n_raw | 0x80000000u;
+    if (in_smem) {
+      hard_nms_argmax(P, sh, abox, sh->lkeys, n_list, b, c, p, L);
+    } else {
+      u64 KB = ~0ull;
+      while (!sh->done) {
+        const int m = select_chunk<RPP_NMS_NT>([&](int i) { return gkeys[i]; }, n_list, KB, RPP_LIST_SMEM, sh->lkeys,
+                                               RPP_LIST_SMEM, &sh->sel, /*sort=*/false);
+        if (m == 0) break;
+        hard_nms_argmax(P, sh, abox, sh->lkeys, m, b, c, p, L);
+        __syncthreads();
+      }
+    }
+    consumed += n_valid;
+    // the list is exhausted: what was left out of it scores at most s_edge — if that (or anything dropped above) is
+    // below the bound, the class is finished; otherwise phase B continues below the edge
+    if (!sh->done && (below || list_complete || s_edge < L)) {
+      __syncthreads();
+      if (tid == 0) sh->done = 1;
+    }
+    __syncthreads();
+    skip_A = true;
+  } else
   if (MODE != RPP_CONSUME_EMIT && P.is_logit && n_list > 0 && n_list <= RPP_LIST_SMEM && !converted) {
     const uint2* lst = P.cand + p * (size_t)P.CAP;
     for (int i = tid; i < n_list; i += RPP_NMS_NT) {
