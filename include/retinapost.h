@@ -106,6 +106,21 @@ int rpp_topk(void* handle, const float* d_scores_BnC, const float* d_boxes_Bn4, 
              float* d_scores_out, float* d_boxes_out, int* d_index_out,
              void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* FilterTopKDetections applied PER PYRAMID LEVEL (optional extension; BASELINE.json north_star "per-level top-k
+ * pre-selection", configs[1] "top-1000/level").  The reference has no such mode — its filter runs over the fused
+ * anchor axis (postprocessing_ops.py:128-161) — so the contract is defined by composition: the
+ * reference's filter on every segment [anchor_boundaries[l], anchor_boundaries[l+1]) of the fused axis
+ * (dataloader/anchor_generator.py:42-49), results concatenated along the row axis in level order.
+ *   d_scores_levels[l] [B,n_l,C], d_boxes_levels[l] [B,n_l,4]  (contiguous per level, e.g. the head outputs)
+ *   per class : scores_out [B,K,C], boxes_out [B,K,C,4], K = sum_l min(k, n_l);  index_out [B,C,K]
+ *   global    : scores_out [B,K,C], boxes_out [B,K,4],   K = sum_l min(k, n_l*C); index_out [B,K] (flat)
+ * Indices are positions on the FUSED axis (level offsets added).  Workspace: the largest
+ * rpp_workspace_bytes(B, n_l) over the levels (short unsampled levels can need more than long sampled ones). */
+int rpp_topk_levels(void* handle, int n_levels, const float* const* d_scores_levels,
+                    const float* const* d_boxes_levels, const long* n_rows, int B,
+                    float* d_scores_out, float* d_boxes_out, int* d_index_out,
+                    void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* GenerateDetections.call (postprocessing_ops.py:537-561), non-TPU branches, with the handle's mode/thresholds.
  *   scores [B,n,C]; boxes [B,n,q,4] with q = 1 (3-D boxes) or q = C (after the per-class filter).
  *   outputs: boxes [B,M,4] f32, scores [B,M] f32, classes [B,M] (f32 Combined / int64 Global* / int32 PerClass*),

@@ -128,6 +128,26 @@ def filter_global(scores, boxes, k, sorted=True, threads=1):
     return so, bo, idx
 
 
+def filter_per_level(scores, boxes, k, anchor_boundaries, per_class=True, sorted=True, threads=1):
+    """FilterTopKDetections applied to every pyramid level's segment of the fused anchor axis (anchor_boundaries of
+    dataloader/anchor_generator.py:42-49) and concatenated in level order — the optional per-level pre-selection of
+    BASELINE.json's north_star.  The reference has no such mode: this is its own filter (:128-161), composed.
+    Indices are positions on the fused axis."""
+    s = _f32(scores)
+    b = _f32(boxes)
+    C = s.shape[2]
+    so, bo, io = [], [], []
+    for lo, hi in zip(anchor_boundaries[:-1], anchor_boundaries[1:]):
+        if hi <= lo:
+            continue
+        f = filter_per_class if per_class else filter_global
+        s_l, b_l, i_l = f(s[:, lo:hi], b[:, lo:hi], k, sorted=sorted, threads=threads)
+        so.append(s_l)
+        bo.append(b_l)
+        io.append(i_l + (lo if per_class else lo * C))
+    return np.concatenate(so, axis=1), np.concatenate(bo, axis=1), np.concatenate(io, axis=-1)
+
+
 def iou(a, b):
     a = _f32(a)
     b = _f32(b)

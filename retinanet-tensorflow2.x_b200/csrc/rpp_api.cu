@@ -828,30 +828,33 @@ int nms_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, in
 }
 
 // FilterTopKDetections on dense scores / boxes
+// (K_out / j_off / idx_off: see the gather kernels; K_out = 0 means "the call's own k")
 int topk_dense(Handle* h, Arena& ar, const float* scores, const float4* boxes, int B, long n, float* scores_out,
-               float4* boxes_out, int* idx_out, cudaStream_t st) {
+               float4* boxes_out, int* idx_out, cudaStream_t st, long K_out = 0, long j_off = 0, int idx_off = 0) {
   const rpp_config& c = h->cfg;
   const int C = c.num_classes;
   u64* keys = nullptr;
   if (c.filter_per_class) {
     const long k = std::min<long>(c.pre_nms_top_k, n);
+    if (K_out <= 0) K_out = k;
     int rc = topk_keys(h, ar, scores, 0, B, n, C, k, &keys, st);
     if (rc || ar.dry) return rc;
     const size_t tot = (size_t)B * k * C;
     size_t grid = std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
     topk_gather_per_class_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, boxes, B, n, C, k, scores_out, boxes_out,
-                                                                idx_out);
+                                                                idx_out, K_out, j_off, idx_off);
     LAUNCHED();
     return RPP_OK;
   }
   if ((double)n * C >= 2147483647.0) return fail(RPP_EINVAL, "rows x classes must stay below 2^31 for the global filter");
   const long k = std::min<long>(c.pre_nms_top_k, n * C);
+  if (K_out <= 0) K_out = k;
   int rc = topk_keys(h, ar, scores, 0, B, n * C, 1, k, &keys, st);
   if (rc || ar.dry) return rc;
   const size_t tot = (size_t)B * k * C;
   size_t grid = std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
   topk_gather_global_kernel<<<(unsigned)grid, 256, 0, st>>>(keys, scores, boxes, B, n, C, k, scores_out, boxes_out,
-                                                           idx_out);
+                                                           idx_out, K_out, j_off, idx_off);
   LAUNCHED();
   return RPP_OK;
 }
@@ -1375,6 +1378,44 @@ int rpp_topk(void* handle, const float* d_scores, const float* d_boxes, int B, l
     return topk_dense(h, ar, d_scores, (const float4*)d_boxes, B, n, d_scores_out, (float4*)d_boxes_out, d_index_out,
                       (cudaStream_t)stream);
   });
+}
+
+int rpp_topk_levels(void* handle, int n_levels, const float* const* d_scores_levels,
+                    const float* const* d_boxes_levels, const long* n_rows, int B, float* d_scores_out,
+                    float* d_boxes_out, int* d_index_out, void* ws, size_t ws_bytes, void* stream) {
+  Handle* h = (Handle*)handle;
+  g_launches = 0;
+  if (!h || !d_scores_levels || !d_boxes_levels || !n_rows || !d_scores_out || !d_boxes_out || B <= 0 ||
+      n_levels <= 0 || n_levels > RPP_MAX_LEVELS)
+    return fail(RPP_EINVAL, "bad argument");
+  if (h->cfg.pre_nms_top_k <= 0) return fail(RPP_EINVAL, "pre_nms_top_k must be positive for rpp_topk_levels");
+  if (int rc = check_device(h)) return rc;
+  const rpp_config& c = h->cfg;
+  long K = 0, n_tot = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    if (!d_scores_levels[l] || !d_boxes_levels[l] || n_rows[l] <= 0 || n_rows[l] >= 0x7fffffffL)
+      return fail(RPP_EINVAL, "bad level %d", l);
+    K += std::min<long>(c.pre_nms_top_k, c.filter_per_class ? n_rows[l] : n_rows[l] * c.num_classes);
+    n_tot += n_rows[l];
+  }
+  if ((double)n_tot * c.num_classes >= 2147483647.0) return fail(RPP_EINVAL, "rows x classes must stay below 2^31");
+  if (h->timing) ++h->timed_calls;
+  int launches = 0;
+  long j_off = 0, idx_off = 0;
+  for (int l = 0; l < n_levels; ++l) {   // one filter per segment, stream-ordered over the same scratch
+    const long n = n_rows[l];
+    int rc = with_arena(ws, ws_bytes, [&](Arena& ar) {
+      return topk_dense(h, ar, d_scores_levels[l], (const float4*)d_boxes_levels[l], B, n, d_scores_out,
+                        (float4*)d_boxes_out, d_index_out, (cudaStream_t)stream, K, j_off, (int)idx_off);
+    });
+    if (rc) return rc;
+    launches += g_launches;
+    g_launches = 0;
+    j_off += std::min<long>(c.pre_nms_top_k, c.filter_per_class ? n : n * c.num_classes);
+    idx_off += n;
+  }
+  g_launches = launches;
+  return RPP_OK;
 }
 
 int rpp_nms(void* handle, const float* d_scores, const float* d_boxes, int B, long n, int q, float* d_boxes_out,

@@ -507,9 +507,12 @@ __global__ void __launch_bounds__(RPP_NMS_NT) effnms_kernel(EffNmsParams P) {
 // K6  FilterTopKDetections outputs (postprocessing_ops.py:128-161) from the emitted sorted keys.
 // ===============================================================================================================
 // per class: scores_out [B,k,C], boxes_out [B,k,C,4], idx_out [B,C,k]
+// (K_out / j_off / idx_off: the outputs are rows [j_off, j_off + k) of tensors with K_out rows per image, and the
+// indices are offset by idx_off — the per-level segments of rpp_topk_levels; K_out = k, 0, 0 otherwise)
 __global__ void topk_gather_per_class_kernel(const u64* __restrict__ emit_key /*[B*C][k]*/, const float4* __restrict__ boxes,
                                              int B, long n, int C, long k, float* __restrict__ scores_out,
-                                             float4* __restrict__ boxes_out, int* __restrict__ idx_out) {
+                                             float4* __restrict__ boxes_out, int* __restrict__ idx_out, long K_out,
+                                             long j_off, int idx_off) {
   const size_t tot = (size_t)B * k * C;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
@@ -518,9 +521,10 @@ __global__ void topk_gather_per_class_kernel(const u64* __restrict__ emit_key /*
     const int b = (int)(bj / k);
     const u64 key = emit_key[((size_t)b * C + c) * k + j];
     const u32 row = key_tie(key);
-    scores_out[e] = key_score(key);
-    boxes_out[e] = boxes[(size_t)b * n + row];
-    if (idx_out) idx_out[((size_t)b * C + c) * k + j] = (int)row;
+    const size_t eo = ((size_t)b * K_out + j_off + j) * C + c;
+    scores_out[eo] = key_score(key);
+    boxes_out[eo] = boxes[(size_t)b * n + row];
+    if (idx_out) idx_out[((size_t)b * C + c) * K_out + j_off + j] = (int)row + idx_off;
   }
 }
 
@@ -528,7 +532,7 @@ __global__ void topk_gather_per_class_kernel(const u64* __restrict__ emit_key /*
 __global__ void topk_gather_global_kernel(const u64* __restrict__ emit_key /*[B][k]*/, const float* __restrict__ scores,
                                           const float4* __restrict__ boxes, int B, long n, int C, long k,
                                           float* __restrict__ scores_out, float4* __restrict__ boxes_out,
-                                          int* __restrict__ idx_out) {
+                                          int* __restrict__ idx_out, long K_out, long j_off, int idx_off) {
   const size_t tot = (size_t)B * k * C;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % C);
@@ -536,10 +540,11 @@ __global__ void topk_gather_global_kernel(const u64* __restrict__ emit_key /*[B]
     const int b = (int)(bj / k);
     const u32 flat = key_tie(emit_key[bj]);
     const u32 a = flat / (u32)C;  // indices // num_classes (:156)
-    scores_out[e] = scores[((size_t)b * n + a) * C + c];
+    const size_t ro = (size_t)b * K_out + j_off + (bj - (size_t)b * k);
+    scores_out[ro * C + c] = scores[((size_t)b * n + a) * C + c];
     if (c == 0) {
-      boxes_out[bj] = boxes[(size_t)b * n + a];
-      if (idx_out) idx_out[bj] = (int)flat;
+      boxes_out[ro] = boxes[(size_t)b * n + a];
+      if (idx_out) idx_out[ro] = (int)flat + idx_off * C;
     }
   }
 }

@@ -15,7 +15,7 @@ RPP_OK, RPP_EINVAL, RPP_EMODE, RPP_ECOMBO, RPP_EWORKSPACE, RPP_ECUDA = 0, -1, -2
 
 EXPORTS = [
     'rpp_create', 'rpp_destroy', 'rpp_last_error', 'rpp_num_anchors', 'rpp_num_levels', 'rpp_anchor_boundaries',
-    'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_nms', 'rpp_detect', 'rpp_detect_levels', 'rpp_detect_typed',
+    'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_topk_levels', 'rpp_nms', 'rpp_detect', 'rpp_detect_levels', 'rpp_detect_typed',
     'rpp_detect_host', 'rpp_detect_host_typed', 'rpp_coco_format', 'rpp_efficient_nms',
     'rpp_last_launch_count', 'rpp_classes_itemsize', 'rpp_debug_force_exact_scan', 'rpp_debug_stage_timing',
     'rpp_debug_stage_ms', 'rpp_debug_stage_report', 'rpp_debug_sample_plan',
@@ -69,6 +69,9 @@ def lib():
         L.rpp_workspace_bytes.restype = ctypes.c_size_t
         L.rpp_decode.argtypes = [vp, vp, vp, ci, vp, vp, vp]
         L.rpp_topk.argtypes = [vp, vp, vp, ci, cl, vp, vp, vp, vp, ctypes.c_size_t, vp]
+        if hasattr(L, 'rpp_topk_levels'):
+            L.rpp_topk_levels.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(cl), ci, vp, vp,
+                                          vp, vp, ctypes.c_size_t, vp]
         L.rpp_nms.argtypes = [vp, vp, vp, ci, cl, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.rpp_detect.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         if hasattr(L, 'rpp_detect_levels'):   # absent only in old tuning builds loaded through RPP_LIB

@@ -7,7 +7,7 @@ works as it does in the reference; FusedPostProcessing (the whole chain as one r
 from retinanet.model.layers import postprocessing_ops as _ops
 
 _REFERENCE_NAMES = ('FuseDetections', 'TransformBoxesAndScores', 'FilterTopKDetections', 'GenerateDetections')
-_OWN_NAMES = ('FusedPostProcessing',)
+_OWN_NAMES = ('FusedPostProcessing', 'FilterTopKDetectionsPerLevel')
 
 __all__ = sorted(_REFERENCE_NAMES + _OWN_NAMES)
 globals().update({name: getattr(_ops, name) for name in __all__})

@@ -296,6 +296,65 @@ class FilterTopKDetections(Layer):
         return {'scores': out_scores, 'boxes': out_boxes}
 
 
+class FilterTopKDetectionsPerLevel(FilterTopKDetections):
+    """Optional extension (BASELINE.json north_star: "per-level top-k pre-selection"; the reference's own filter runs
+    over the fused anchor axis, postprocessing_ops.py:128-161): FilterTopKDetections applied to every pyramid level's
+    segment of the anchor axis — `anchor_boundaries` of dataloader/anchor_generator.py:42-49 — and concatenated in
+    level order.  `top_k` is per level.  Stage entry: rpp_topk_levels.
+
+    Input: {'scores': [B,N,C], 'boxes': [B,N,4]} plus `anchor_boundaries`, or per-level lists / dicts of tensors
+    ([B,n_l,C] / [B,n_l,4], the natural layout of the head outputs: no copy)."""
+
+    def __init__(self, top_k=100, filter_per_class=True, anchor_boundaries=None, **kwargs):
+        super(FilterTopKDetectionsPerLevel, self).__init__(top_k=top_k, filter_per_class=filter_per_class, **kwargs)
+        self.anchor_boundaries = None if anchor_boundaries is None else [int(v) for v in anchor_boundaries]
+
+    @staticmethod
+    def _as_list(x):
+        if isinstance(x, dict):
+            return [x[k] for k in sorted(x, key=lambda v: int(v))]
+        return list(x)
+
+    def _levels(self, predictions):
+        scores, boxes = predictions['scores'], predictions['boxes']
+        if torch.is_tensor(scores):
+            bounds = self.anchor_boundaries
+            if bounds is None or bounds[0] != 0 or bounds[-1] != scores.shape[1] or sorted(bounds) != bounds:
+                raise ValueError('anchor_boundaries must partition the fused anchor axis [0, {}]'.format(
+                    scores.shape[1]))
+            pairs = [(scores[:, a:b], boxes[:, a:b]) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        else:
+            pairs = list(zip(self._as_list(scores), self._as_list(boxes)))
+        return [(_as_f32(s), _as_f32(b)) for s, b in pairs]
+
+    def call(self, predictions):
+        first = predictions['scores']
+        first = first if torch.is_tensor(first) else self._as_list(first)[0]
+        with _device_guard(first):
+            return self._call(predictions)
+
+    def _call(self, predictions):
+        levels = self._levels(predictions)
+        B, _, C = levels[0][0].shape
+        n_rows = [int(s.shape[1]) for s, _ in levels]
+        for (s, b), n in zip(levels, n_rows):
+            if tuple(s.shape) != (B, n, C) or tuple(b.shape) != (B, n, 4):
+                raise ValueError('expected per-level scores [B,n_l,C] and boxes [B,n_l,4]')
+        h = self._handle(C)
+        K = sum(min(self.top_k, n if self.filter_per_class else n * C) for n in n_rows)
+        dev = levels[0][0].device
+        out_scores = torch.empty((B, K, C), dtype=torch.float32, device=dev)
+        out_boxes = torch.empty((B, K, C, 4) if self.filter_per_class else (B, K, 4), dtype=torch.float32, device=dev)
+        L = len(levels)
+        sp = (ctypes.c_void_p * L)(*[s.data_ptr() for s, _ in levels])
+        bp = (ctypes.c_void_p * L)(*[b.data_ptr() for _, b in levels])
+        nr = (ctypes.c_long * L)(*n_rows)
+        ws = h.workspace(B, max(n_rows, key=lambda n: _native.lib().rpp_workspace_bytes(h.ptr, B, n)), dev)
+        _native.check(_native.lib().rpp_topk_levels(h.ptr, L, sp, bp, nr, B, out_scores.data_ptr(),
+                                                    out_boxes.data_ptr(), None, ws.data_ptr(), ws.numel(), _stream()))
+        return {'scores': out_scores, 'boxes': out_boxes}
+
+
 class GenerateDetections(Layer):
     """postprocessing_ops.py:176-561 — the five NMS modes, non-TPU branches, with the reference's per-mode output
     dtypes and padding.  Stage entry point: rpp_nms."""

@@ -5,8 +5,8 @@ import torch, bench
 from retinanet import _native
 from retinanet.cfg.config import AttrDict
 from retinanet.model.builder import ModelBuilder
-B, C, H = 64, bench.C, bench.H
-model = ModelBuilder(AttrDict(bench.CONFIG)).add_post_processing_stage(None)
+B, C, H = 64, 80, 640
+model = ModelBuilder(AttrDict(bench.BASE_CONFIG)).add_post_processing_stage(None)
 layer = model.layers[-1]
 h = layer.handle(C)
 g = torch.Generator(device='cuda'); g.manual_seed(42)
