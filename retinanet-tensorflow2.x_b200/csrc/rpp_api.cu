@@ -538,9 +538,11 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     pp.T_min = -INFINITY;
   }
   const size_t smem_nms = align_up(nms_shared_bytes(pp.M_lim), 16);
+  unsigned emit_grid = (unsigned)P;
   auto launch = [&](void) {
     // worklist launches (finish pass): a few persistent blocks per SM instead of one block per problem
-    const unsigned grid = pp.work_items ? (unsigned)std::min<size_t>(P, (size_t)h->sm_count * 4) : (unsigned)P;
+    const unsigned grid = pp.work_items ? (unsigned)std::min<size_t>(P, (size_t)h->sm_count * 4)
+                                        : (pp.n_loop > 0 ? emit_grid : (unsigned)P);
     if (ps.consumer == RPP_CONSUME_HARD)
       launch_k(h->pdl, col_problem_kernel<RPP_CONSUME_HARD>, dim3(grid), dim3(RPP_NMS_NT),
                smem_nms + (pp.argmax ? RPP_LIST_SMEM * sizeof(float4) : 0), st, pp);
@@ -573,12 +575,15 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   }
   if (emit && ps.direct && C == 1) {   // detections straight from the lists; what follows only does the images it left
     pp.emit_direct = 1;
-    launch_k(h->pdl, global_top_direct_kernel, dim3((unsigned)P), dim3(RPP_EMIT_NT), sizeof(EmitShared), st, pp, *ps.direct);
+    // ... with a few persistent blocks walking the (almost always all done) images instead of one block per image
+    pp.n_loop = (long)P;
+    emit_grid = (unsigned)std::min<size_t>(P, (size_t)h->sm_count);
+    launch_k(h->pdl, global_top_direct_kernel, dim3((unsigned)P), dim3(RPP_EMIT_NT), gtd_shared_bytes(), st, pp, *ps.direct);
     LAUNCHED();
     stage_mark(h, "nms:global_top_direct", st);
   }
   if (emit) {   // whole-list sort in shared memory where it applies; the generic kernel takes the rest
-    launch_k(h->pdl, emit_sort_kernel, dim3((unsigned)P), dim3(RPP_EMIT_NT), sizeof(EmitShared), st, pp);
+    launch_k(h->pdl, emit_sort_kernel, dim3(emit_grid), dim3(RPP_EMIT_NT), sizeof(EmitShared), st, pp);
     LAUNCHED();
   }
   launch();
@@ -902,7 +907,7 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
   const bool top_only = !per_class && sigma_tf == 0.0f && !tpu_branch(c) && M <= 1024;   // GlobalHardNMS: no suppression (B1)
   // GlobalHardNMS: one block per image turns the candidate list into the detections (global_top_direct_kernel); the
   // emission / rows / top kernels below only see the images it could not serve
-  const bool direct = top_only && h->top_direct && (long)C * std::min<long>(M, k) <= RPP_GTD_CAND;
+  const bool direct = top_only && h->top_direct;
   GlobalTopDirectParams gd{};
   int* skip = nullptr;
   if (direct) {
@@ -929,10 +934,12 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       if (!direct) CUDA_OK(cudaMemsetAsync(first, 0xff, (size_t)B * N * sizeof(u32), st));
       GlobalRowsParams rp{};
       rp.skip = skip; rp.init_first = direct ? 1 : 0;
+      rp.n_loop = direct ? B : 0;
+      const unsigned rows_grid = direct ? (unsigned)std::min(B, h->sm_count) : (unsigned)B;
       rp.emit_key = keys; rp.k = k; rp.C = C; rp.N = N;
       rp.first = first; rp.mraw = mraw; rp.skey = skey; rp.dkey = dkey; rp.sd_cnt = sd_cnt;
       rp.score_threshold = c.score_threshold;
-      launch_k(direct && h->pdl /* otherwise it follows a memset, not a kernel */, global_rows_kernel, dim3(B), dim3(RPP_GROWS_NT), 0, st, rp);
+      launch_k(direct && h->pdl /* otherwise it follows a memset, not a kernel */, global_rows_kernel, dim3(rows_grid), dim3(RPP_GROWS_NT), 0, st, rp);
       LAUNCHED();
       stage_mark(h, "rows:resolve", st);
     }
@@ -971,7 +978,8 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
       tp.out_boxes = out.boxes; tp.out_scores = out.scores; tp.out_classes = (long long*)out.classes;
       tp.out_valid = out.valid;
       tp.skip = skip;
-      launch_k(h->pdl, global_top_kernel, dim3(B), dim3(RPP_GTOP_NT), 0, st, tp);
+      tp.n_loop = direct ? B : 0;
+      launch_k(h->pdl, global_top_kernel, dim3(direct ? (unsigned)std::min(B, h->sm_count) : (unsigned)B), dim3(RPP_GTOP_NT), 0, st, tp);
       LAUNCHED();
       stage_mark(h, "nms:global_top", st);
       return RPP_OK;
@@ -1165,7 +1173,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaFuncSetAttribute(merge_padded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(global_soft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(emit_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-  cudaFuncSetAttribute(global_top_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  cudaFuncSetAttribute(global_top_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
   cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaFuncSetAttribute(sample_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(collect_cols4_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

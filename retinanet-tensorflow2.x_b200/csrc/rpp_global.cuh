@@ -35,6 +35,7 @@ struct GlobalRowsParams {
   float score_threshold;
   const int* skip;       // [B] or nullptr: 2 = global_top_direct_kernel already did the image
   int init_first;        // the block presets its image's `first` itself (no memset ahead of the kernel)
+  int n_loop;            // > 0: persistent blocks walk images [0, n_loop)
 };
 
 // candidate key of the Global* NMS: (score, row index j) with the row's payload slot free in the low bits
@@ -42,12 +43,10 @@ __device__ __forceinline__ u64 grow_key(float score, u32 j) { return make_key(sc
 
 #define RPP_GROWS_RPT 8   // consecutive rows per thread
 
-__global__ void __launch_bounds__(RPP_GROWS_NT) global_rows_kernel(GlobalRowsParams P) {
-  pdl_enter();
+__device__ __forceinline__ void global_rows_body(const GlobalRowsParams& P, const int b) {
   __shared__ int s_wsum[RPP_GROWS_NT / 32];
   __shared__ int s_run, s_nd;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x;
   const u64* ek = P.emit_key + (size_t)b * P.k;
   u32* fr = P.first + (size_t)b * P.N;
   const long span = (long)RPP_GROWS_NT * RPP_GROWS_RPT;
@@ -125,6 +124,18 @@ __global__ void __launch_bounds__(RPP_GROWS_NT) global_rows_kernel(GlobalRowsPar
   if (P.skey && tid == 0) { P.sd_cnt[2 * b] = s_run; P.sd_cnt[2 * b + 1] = s_nd; }
 }
 
+__global__ void __launch_bounds__(RPP_GROWS_NT) global_rows_kernel(GlobalRowsParams P) {
+  pdl_enter();
+  if (P.n_loop > 0) {   // a few persistent blocks over images that are almost all done (see GlobalRowsParams.skip)
+    for (int b = blockIdx.x; b < P.n_loop; b += gridDim.x) {
+      global_rows_body(P, b);
+      __syncthreads();
+    }
+  } else {
+    global_rows_body(P, blockIdx.x);
+  }
+}
+
 // ===============================================================================================================
 // global_top_kernel — GlobalHardNMS behind the global filter, non-TPU branch.  The reference passes iou_threshold = 1.0
 // to NonMaxSuppressionV5 there (postprocessing_ops.py:253), and an IoU computed as
@@ -142,6 +153,7 @@ struct GlobalTopParams {
   const float4* anchors; DecodeParams dp;
   float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
   const int* skip;       // [B] or nullptr: 2 = global_top_direct_kernel already did the image
+  int n_loop;            // > 0: persistent blocks walk images [0, n_loop)
 };
 
 struct GlobalTopShared {
@@ -150,11 +162,9 @@ struct GlobalTopShared {
   u64 top[1024];
 };
 
-__global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams P) {
-  pdl_enter();
+__device__ __forceinline__ void global_top_body(const GlobalTopParams& P, const int b) {
   __shared__ GlobalTopShared sh;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int b = blockIdx.x;
   if (P.skip && P.skip[b] == 2) return;
   const int ns = P.sd_cnt[2 * b], nd = P.sd_cnt[2 * b + 1];
   const int n1 = ns < P.M ? ns : P.M;
@@ -221,28 +231,49 @@ __global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams
   }
 }
 
+__global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams P) {
+  pdl_enter();
+  if (P.n_loop > 0) {
+    for (int b = blockIdx.x; b < P.n_loop; b += gridDim.x) {
+      global_top_body(P, b);
+      __syncthreads();
+    }
+  } else {
+    global_top_body(P, blockIdx.x);
+  }
+}
+
 // ===============================================================================================================
 // global_top_direct_kernel — the whole GlobalHardNMS-behind-the-global-filter stage of one image in ONE block, straight
 // from the image's candidate list: no sorted top-k emission, no row resolution.  (configs[4]: the 8 192-key sort was
 // half of the step.)  With nothing suppressed (see global_top_kernel) the detections are the first M rows in
-// (row maximum desc, row index asc) order, and a row's index is the rank of its own (anchor, class) pair in the top k:
-//   * K_cut = the k-th best pair key (exact radix descent over the scored list in shared memory, counting only);
-//   * an output row's anchor has its best pair among the M best pairs (the pairs ahead of an anchor's best pair all
-//     precede that pair's row in the output order), so: the M best pairs, sorted (select_chunk);
-//   * for each distinct anchor among them, all C classes are looked up in the logits: the pairs with key >= K_cut are
-//     exactly the anchor's rows (its duplicates, B12), each keyed (anchor's best score, own pair key);
-//   * the M best of those candidates (rank by counting: a few hundred at most) are written out.
-// A block that cannot serve its image (short list beyond the in-block re-collection, candidate overflow) leaves
-// emit_done = 0 and the emission / rows / top kernels that follow do the image; they skip the images marked 2.
+// (row maximum desc, row index asc) order, and a row's index is the rank of its own (anchor, class) pair in the top k.
+// Everything is selected on RAW keys (logit bits | ~flat index; the score is a monotone function of the logit) and
+// the binary64 sigmoid is evaluated for a few hundred elements per image instead of the ~10^4 of the list:
+//   1. the k-th best raw key (exact radix descent over the list in shared memory, counting only) and the interval
+//      [x_lo, x_hi] of logits whose score equals the score s_k of that key (found with the sigmoid itself): a pair is
+//      in the top k  <=>  logit > x_hi, or logit in [x_lo, x_hi] and flat index <= idx*, where idx* is the
+//      (k - #{logit > x_hi})-th smallest index of the tie group E = {logit in [x_lo, x_hi]} — TopKV2's order
+//      (score desc, index asc) exactly, also when distinct logits round to one score;
+//   2. the M + 32 best raw keys, scored and ranked by (score, index); those strictly above the score of the raw cut
+//      are complete (edge rule), and an output row's anchor has its best pair among the M best pairs (the pairs ahead
+//      of an anchor's best pair all precede that pair's row in the output order);
+//   3. for each distinct anchor among them, all C classes are looked up in the logits: the pairs in the top k are
+//      exactly the anchor's rows (its duplicates, B12), each keyed (anchor's best score, own pair key);
+//   4. the M best of those candidates (rank by counting: a few hundred at most) are written out.
+// A block that cannot serve its image (list short beyond the in-block re-collection, tie group or candidate overflow,
+// a tie group that reaches below the list's threshold) leaves emit_done = 0 and the emission / rows / top kernels that
+// follow do the image; they skip the images marked 2.
 // ===============================================================================================================
-#define RPP_GTD_CAND 4096
+#define RPP_GTD_CAND 3072
+#define RPP_GTD_TIES 1024
 
 struct GlobalTopDirectParams {
   Levels src;              // the [B, N, C] logits + deltas (class lookups, boxes)
   int C; long N; int M;
   const float4* anchors; DecodeParams dp;
   float score_threshold;   // of the NMS (the emission problem's own threshold is -inf: tf.nn.top_k has none)
-  int debug;               // env RPP_GTD_DEBUG: block 0 prints its per-phase cycle counts
+  int debug;               // env RPP_GTD_DEBUG: blocks 0 and 300 print their per-phase cycle counts
   float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
 };
 
@@ -304,98 +335,297 @@ __device__ u64 block_kth_key(const u64* keys, int n, u32 kth, SelectScratch<RPP_
   }
 }
 
+// Largest d >= 0 such that every ordered float encoding in [o, o + dir * d] has the score `s` (dir = +1 / -1): the
+// score is monotone in the logit, so the predicate is a prefix; galloping 32-ary search, one sigmoid per lane and round.
+// One warp; o is the encoding of a finite logit whose score is s.
+__device__ u32 gtd_tie_extent(u32 o, float s, int dir) {
+  const int lane = threadIdx.x & 31;
+  const u32 room = dir > 0 ? ord_f32(INFINITY) - o : o - ord_f32(-INFINITY);   // stay inside [-inf, +inf]
+  u32 base = 0u;       // known: predicate holds at base
+  u32 step = 1u;
+  for (;;) {           // gallop: find a step at which the 32 probes base + step * (lane + 1) do not all hold
+    const u64 d = (u64)base + (u64)step * (u32)(lane + 1);
+    const bool ok = d <= (u64)room && sigmoid_f32(unord_f32(dir > 0 ? o + (u32)d : o - (u32)d)) == s;
+    const u32 m = __ballot_sync(RPP_FULL_MASK, ok);
+    const int n_ok = m == 0xffffffffu ? 32 : __ffs(~m) - 1;   // probes are increasing: the holds form a prefix
+    base += step * (u32)n_ok;
+    if (n_ok == 32) {
+      if (step > (1u << 24)) return 0xffffffffu;   // a saturated score (0 or 1): millions of logits tie -> caller gives up
+      step <<= 5;
+      continue;
+    }
+    // the extent lies in [base, base + step): refine with smaller steps
+    while (step > 1u) {
+      step >>= 5;
+      if (step == 0u) step = 1u;
+      const u64 d2 = (u64)base + (u64)step * (u32)(lane + 1);
+      const bool ok2 = d2 <= (u64)room && sigmoid_f32(unord_f32(dir > 0 ? o + (u32)d2 : o - (u32)d2)) == s;
+      const u32 m2 = __ballot_sync(RPP_FULL_MASK, ok2);
+      // 31 probes lie strictly inside the bracket; the 32nd is its (failing) upper end
+      const int n2 = m2 == 0xffffffffu ? 31 : __ffs(~m2) - 1;
+      base += step * (u32)(n2 > 31 ? 31 : n2);
+    }
+    return base;
+  }
+}
+
 static_assert(RPP_RADIX_BINS == RPP_EMIT_NT, "block_kth_key: one bin per thread");
-static_assert(RPP_EMIT_CHUNK * 8 >= (1024 + 1024) * 8 + RPP_GTD_CAND * 12, "global_top_direct_kernel: scratch layout");
+static_assert(RPP_EMIT_CHUNK * 8 >= (1024 + 1024) * 8 + RPP_GTD_CAND * 12 + RPP_GTD_TIES * 4,
+              "global_top_direct_kernel: scratch layout");
+
+struct GtdState {
+  int ncand, over, fail, ne, ngt, nvalid, ntop, nkbin, nrows;
+  u32 o_lo, o_hi, idx_star;
+  u32 d_k, rk, d_m;
+  u64 kraw;
+  u32 min_o;
+};
+
+__host__ __device__ static inline size_t gtd_shared_bytes() { return sizeof(EmitShared) + 1024 * sizeof(float4); }
 
 __global__ void __launch_bounds__(RPP_EMIT_NT) global_top_direct_kernel(ColProblemParams P, GlobalTopDirectParams G) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
-  __shared__ int s_ncand, s_over;
+  float4* tbox = reinterpret_cast<float4*>(smem_raw + sizeof(EmitShared));   // [1024] boxes of the best pairs' anchors
+  __shared__ GtdState st;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x;   // C == 1: one emission problem per image
   const size_t p = blockIdx.x;
-  u64* selchunk = sh->chunk;                 // [1024] select_chunk's output
-  u64* top = sh->chunk + 1024;               // [1024] the M best pairs, sorted
+  u64* topraw = sh->chunk;                   // [1024] the best raw keys, then their scored keys, then per-pair scratch
+  u64* top = sh->chunk + 1024;               // [1024] keys of the k-th key's bin, then: the M best pairs as
+                                             //        (score, ~flat index) keys, sorted
   u64* cown = sh->chunk + 2048;              // [RPP_GTD_CAND] candidate rows: own pair key ...
   u32* cfirst = reinterpret_cast<u32*>(sh->chunk + 2048 + RPP_GTD_CAND);   // ... and the slot of the anchor's best pair in top[]
-  if (tid == 0) { P.emit_done[p] = 0; s_ncand = 0; s_over = 0; }
-  long long tdbg[6];
+  u32* eidx = cfirst + RPP_GTD_CAND;         // [RPP_GTD_TIES] flat indices of the tie group E
+  u32* hist = sh->sel.hist;
+  if (tid == 0) {
+    P.emit_done[p] = 0;
+    st.ncand = 0; st.over = 0; st.fail = 0; st.ne = 0; st.ngt = 0; st.nvalid = 0; st.ntop = 0; st.nkbin = 0; st.nrows = 0;
+    st.min_o = 0xffffffffu;
+  }
+  long long tdbg[8];
   int ndbg = 0;
 #define GTD_T() do { if (G.debug) tdbg[ndbg++] = clock64(); } while (0)
   GTD_T();
-  int n_keys = 0;
-  const int nv = emit_prepare(P, sh, p, b, 0, n_keys);
-  if (nv < 0) return;
+  // ---- 0. raw keys of the list (or of an in-block re-collection of the column) -------------------------------
+  u32 o_complete;   // the keys in sh->keys are ALL elements of the column whose ordered logit is >= o_complete
+  u64 kmin, kmax;
+  const int n_keys = emit_prepare_raw(P, sh, p, b, 0, o_complete, kmin, kmax);
+  if (n_keys < 0) return;
   GTD_T();
-  const u64 K_cut = block_kth_key(sh->keys, n_keys, (u32)P.k_lim, &sh->sel);
-  GTD_T();
-  // the M best pairs (a chunk may come back shorter than asked for: loop)
+  // ---- 1. ONE histogram over a linear map of [min key, max key] onto 1024 bins serves both selections: the bin of
+  //         the k-th best key (refined exactly inside the bin) and a cut that holds the M + 32 best keys.
+  //         (An MSB-first digit would put the whole list into a dozen bins: the logits of a list share their exponent.)
   const int Mp = (long)G.M < P.k_lim ? G.M : (int)P.k_lim;
-  int got = 0;
+  const u32 want = (u32)(Mp + 32 < 1024 ? Mp + 32 : 1024);
+  u64 mn = kmin, mx = kmax;   // (per-thread extrema from the key build)
   {
-    u64 KB = ~0ull;
-    while (got < Mp) {
-      const int m = select_chunk<RPP_EMIT_NT>([&](int i) { return sh->keys[i]; }, n_keys, KB, Mp - got, selchunk, 1024,
-                                              &sh->sel);
-      if (m == 0) break;
-      const int take = m < Mp - got ? m : Mp - got;
-      for (int i = tid; i < take; i += RPP_EMIT_NT) top[got + i] = selchunk[i];
-      got += take;
-      __syncthreads();
-    }
+    u32 cnt = 1;
+    block_cnt_max_min<RPP_EMIT_NT>(cnt, mx, mn, &sh->sel.bs);
   }
+  const u64 range = mx - mn;
+  const u64 q = range / 1024ull + 1ull;              // bin = floor((key - mn) / q) < 1024 (any monotone map would do)
+  const u64 rq = q > 1ull ? ~0ull / q : 0ull;        // floor((2^64 - 1) / q): umulhi(x, rq) <= x / q, monotone in x
+  auto bin_of = [&](u64 k) -> u32 { return q > 1ull ? (u32)__umul64hi(k - mn, rq) : (u32)(k - mn); };
+  hist[tid] = 0u;
+  __syncthreads();
+  for (int i = tid; i < n_keys; i += RPP_EMIT_NT) atomicAdd(&hist[bin_of(sh->keys[i])], 1u);
+  __syncthreads();
+  {
+    // thread t owns bin t: inclusive suffix count over the bins >= t
+    const u32 h = hist[tid];
+    u32 v = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_down_sync(RPP_FULL_MASK, v, o);
+      if (lane + o < 32) v += t;
+    }
+    if (lane == 0) sh->sel.part[warp] = v;
+    __syncthreads();
+    if (warp == 0) {   // exclusive suffix sums of the 32 warp totals
+      const u32 tot = sh->sel.part[lane];
+      u32 sfx = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_down_sync(RPP_FULL_MASK, sfx, o);
+        if (lane + o < 32) sfx += t;
+      }
+      sh->sel.part[32 + lane] = sfx - tot;
+    }
+    __syncthreads();
+    const u32 above = v - h + sh->sel.part[32 + warp];
+    const u32 kth = (u32)P.k_lim;
+    if (above < kth && above + h >= kth) { st.d_k = (u32)tid; st.rk = kth - above; if (h > 1024u) st.fail = 1; }
+    if (above < want && above + h >= want) { st.d_m = (u32)tid; if (above + h > 1024u) st.fail = 1; }
+    if (tid == 0 && above + h < want) st.d_m = 0u;   // fewer keys than wanted: all of them
+  }
+  __syncthreads();
+  if (st.fail) return;
+  const u32 d_k = st.d_k, d_m = st.d_m, rk = st.rk;
+  for (int i = tid; i < n_keys; i += RPP_EMIT_NT) {
+    const u64 k = sh->keys[i];
+    const u32 bin = bin_of(k);
+    if (bin >= d_m) { topraw[atomicAdd(&st.ntop, 1)] = k; atomicMin(&st.min_o, (u32)(k >> 32)); }
+    if (bin == d_k) top[atomicAdd(&st.nkbin, 1)] = k;
+  }
+  __syncthreads();
+  const int m_top = st.ntop, nkbin = st.nkbin;
+  for (int i = tid; i < nkbin; i += RPP_EMIT_NT) {   // the rk-th largest key of the bin (rank by counting)
+    const u64 k = top[i];
+    u32 rank = 0;
+    for (int j = 0; j < nkbin; ++j) rank += top[j] > k;
+    if (rank == rk - 1u) st.kraw = k;
+  }
+  __syncthreads();
+  const u32 o_k = (u32)(st.kraw >> 32);
   GTD_T();
-  // candidate rows: one warp per distinct anchor of the best pairs
-  for (int i = warp; i < got; i += RPP_EMIT_NT / 32) {
-    const u64 kb = top[i];
-    const u32 a = key_tie(kb) / (u32)G.C;
-    bool dup = false;
-    for (int j = lane; j < i; j += 32) dup = dup || key_tie(top[j]) / (u32)G.C == a;
-    if (__any_sync(RPP_FULL_MASK, dup)) continue;           // the anchor's best pair came earlier
-    if (!(key_score(kb) > G.score_threshold)) continue;     // NonMaxSuppressionV5 never sees the row (A.2)
-    for (int c0 = 0; c0 < G.C; c0 += 32) {
-      const int c = c0 + lane;
-      bool in = false;
-      u64 key = 0ull;
-      if (c < G.C) {
-        const float raw = lv_val(G.src, b, a, G.C, c);
-        if (raw >= P.T_min) {
-          key = make_key(col_score(P, raw), a * (u32)G.C + (u32)c);
-          in = key >= K_cut;
-        }
+  // ---- 2. warps 0 / 1: extent of the tie group of s_k above / below x_k; everybody else: score the best raw keys
+  const float s_k = sigmoid_f32(unord_f32(o_k));
+  if (warp == 0) {
+    const u32 d = gtd_tie_extent(o_k, s_k, +1);
+    if (lane == 0) { if (d == 0xffffffffu) st.fail = 1; else st.o_hi = o_k + d; }
+  } else if (warp == 1) {
+    const u32 d = gtd_tie_extent(o_k, s_k, -1);
+    if (lane == 0) { if (d == 0xffffffffu) st.fail = 1; else st.o_lo = o_k - d; }
+  }
+  // everything outside topraw has a raw key below the smallest key in it, i.e. a logit <= that key's: scores <= e0
+  const bool whole = m_top == n_keys && o_complete <= ord_f32(-INFINITY);
+  const float e0 = whole ? -INFINITY : sigmoid_f32(unord_f32(st.min_o));
+  if (warp >= 2)
+  for (int i = tid - 64; i < m_top; i += RPP_EMIT_NT - 64) {   // (every slot has one owner: in place)
+    const u64 rk2 = topraw[i];
+    const float sc = sigmoid_f32(unord_f32((u32)(rk2 >> 32)));
+    topraw[i] = sc > e0 ? make_key(sc, key_tie(rk2)) : 0ull;
+  }
+  __syncthreads();
+  if (st.fail) return;
+  const u32 o_lo = st.o_lo, o_hi = st.o_hi;
+  // tie group: E = {o_lo <= logit <= o_hi}, n_gt = #{logit > o_hi}; rank the scored best keys meanwhile
+  {
+    int ngt = 0;
+    for (int i = tid; i < n_keys; i += RPP_EMIT_NT) {
+      const u64 k = sh->keys[i];
+      const u32 o = (u32)(k >> 32);
+      if (o > o_hi) ++ngt;
+      else if (o >= o_lo) {
+        const int slot = atomicAdd(&st.ne, 1);
+        if (slot < RPP_GTD_TIES) eidx[slot] = key_tie(k);
       }
-      const u32 mask = __ballot_sync(RPP_FULL_MASK, in);
-      if (mask == 0u) continue;
-      int slot0 = 0;
-      if (lane == 0) slot0 = atomicAdd(&s_ncand, __popc(mask));
-      slot0 = __shfl_sync(RPP_FULL_MASK, slot0, 0);
-      if (in) {
-        const int slot = slot0 + __popc(mask & ((1u << lane) - 1u));
-        if (slot < RPP_GTD_CAND) { cown[slot] = key; cfirst[slot] = (u32)i; } else s_over = 1;
-      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ngt += __shfl_xor_sync(RPP_FULL_MASK, ngt, o);
+    if (lane == 0 && ngt) atomicAdd(&st.ngt, ngt);
+    // (8 lanes per key: the counting loop is the latency chain of this phase)
+    for (int i0 = 0; i0 < m_top; i0 += RPP_EMIT_NT / 8) {
+      const int i = i0 + (tid >> 3), sub = tid & 7;
+      const u64 k = i < m_top ? topraw[i] : 0ull;
+      int rank = 0;
+      if (k != 0ull)
+        for (int j = sub; j < m_top; j += 8) rank += topraw[j] > k;
+      rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 1);
+      rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 2);
+      rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 4);
+      if (k != 0ull && sub == 0) { top[rank] = k; atomicAdd(&st.nvalid, 1); }
     }
   }
   __syncthreads();
-  if (s_over) return;   // (cannot happen with C * M <= RPP_GTD_CAND) the kernels that follow do the image
-  GTD_T();
-  const int nc = s_ncand;
-  const int valid = nc < G.M ? nc : G.M;
-  if (tid == 0) { G.out_valid[b] = valid; P.emit_done[p] = 2; }
-  // rank by counting on (anchor's best score desc, own pair key desc) = (row maximum desc, row index asc)
-  for (int i = tid; i < nc; i += RPP_EMIT_NT) {
-    const u64 own = cown[i];
-    const u64 best = top[cfirst[i]];
-    const u32 sb = (u32)(best >> 32);
-    int rank = 0;
-    for (int j = 0; j < nc; ++j) {
-      const u32 sj = (u32)(top[cfirst[j]] >> 32);
-      rank += (sj > sb) || (sj == sb && cown[j] > own);
+  const int ne = st.ne, nvalid = st.nvalid;
+  const int slots = (int)P.k_lim - st.ngt;   // members of E inside the top k: its `slots` smallest flat indices
+  // the tie group must lie inside what the keys cover, and fit; the best pairs must be complete
+  if (ne > RPP_GTD_TIES || slots < 1 || slots > ne || o_lo < o_complete || nvalid < Mp) return;
+  if (slots == ne) {
+    if (tid == 0) st.idx_star = 0xffffffffu;
+  } else {
+    for (int i = tid; i < ne; i += RPP_EMIT_NT) {
+      const u32 v = eidx[i];
+      int rank = 0;
+      for (int j = 0; j < ne; ++j) rank += eidx[j] < v;
+      if (rank == slots - 1) st.idx_star = v;
     }
-    if (rank < G.M) {
+  }
+  // anchors of the M best pairs (topraw is free again: [0, 1024) as u32 anchors, flags behind them)
+  u32* anc = reinterpret_cast<u32*>(topraw);
+  u32* isf = anc + 1024;
+  const int got = Mp;
+  if (tid < got) anc[tid] = key_tie(top[tid]) / (u32)G.C;
+  __syncthreads();
+  GTD_T();
+  // ---- 3. one phase, no barrier inside: (a) thread i < M: box of pair i's anchor and "first pair of its anchor";
+  //         (b) every class of every pair's anchor looked up in the logits -> candidate rows (filtered by (a) later)
+  const u32 idx_star = st.idx_star;
+  {
+    float4 dl, an;
+    u32 a_i = 0u;
+    if (tid < got) {   // loads first, the dependent work after the look-ups were issued
+      a_i = anc[tid];
+      dl = lv_delta(G.src, b, a_i);
+      an = G.anchors[a_i];
+    }
+    for (int e = tid; e < got * G.C; e += RPP_EMIT_NT) {
+      const int i = e / G.C, c = e - i * G.C;
+      const u32 a = anc[i];
+      const float raw = lv_val(G.src, b, a, G.C, c);
+      if (!(raw >= P.T_min)) continue;
+      const u32 o = ord_f32(raw), flat = a * (u32)G.C + (u32)c;
+      if (o > o_hi || (o >= o_lo && flat <= idx_star)) {
+        const int slot = atomicAdd(&st.ncand, 1);
+        if (slot < RPP_GTD_CAND) { cown[slot] = make_key(sigmoid_f32(raw), flat); cfirst[slot] = (u32)i; }
+        else st.over = 1;
+      }
+    }
+    for (int i0 = 0; i0 < got; i0 += RPP_EMIT_NT / 8) {   // "first pair of its anchor": 8 lanes per pair
+      const int i = i0 + (tid >> 3), sub = tid & 7;
+      int dup = 0;
+      if (i < got) {
+        const u32 a = anc[i];
+        for (int j = sub; j < i; j += 8) dup |= anc[j] == a;
+      }
+      dup |= __shfl_xor_sync(RPP_FULL_MASK, dup, 1);
+      dup |= __shfl_xor_sync(RPP_FULL_MASK, dup, 2);
+      dup |= __shfl_xor_sync(RPP_FULL_MASK, dup, 4);
+      // NonMaxSuppressionV5 never sees a row at or below the score threshold (A.2)
+      if (i < got && sub == 0) isf[i] = (!dup && key_score(top[i]) > G.score_threshold) ? 1u : 0u;
+    }
+    if (tid < got) tbox[tid] = clip01(decode_box(dl, an, G.dp));
+  }
+  __syncthreads();
+  if (st.over) return;   // the kernels that follow do the image
+  GTD_T();
+  // ---- 4. rank by counting on (anchor's best score desc, own pair key desc) = (row maximum desc, row index asc)
+  const int nc_all = st.ncand;
+  u32* cs = reinterpret_cast<u32*>(sh->keys);   // [nc_all] (the list is done) score bits of the candidate's anchor, 0 = not a row (pair is not its anchor's first)
+  {
+    int local = 0;
+    for (int i = tid; i < nc_all; i += RPP_EMIT_NT) {
+      const u32 f = cfirst[i];
+      const u32 v = isf[f] ? (u32)(top[f] >> 32) : 0u;
+      cs[i] = v;
+      local += v != 0u;
+    }
+    if (local) atomicAdd(&st.nrows, local);
+  }
+  __syncthreads();
+  const int nrows = st.nrows;
+  const int valid = nrows < G.M ? nrows : G.M;
+  if (tid == 0) { G.out_valid[b] = valid; P.emit_done[p] = 2; }
+  for (int i0 = 0; i0 < nc_all; i0 += RPP_EMIT_NT / 8) {   // 8 lanes per candidate
+    const int i = i0 + (tid >> 3), sub = tid & 7;
+    const u32 sb = i < nc_all ? cs[i] : 0u;
+    const u64 own = i < nc_all ? cown[i] : 0ull;
+    int rank = 0;
+    if (sb != 0u)
+      for (int j = sub; j < nc_all; j += 8) {
+        const u32 sj = cs[j];
+        rank += (sj > sb) || (sj == sb && cown[j] > own);
+      }
+    rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 1);
+    rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 2);
+    rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 4);
+    if (sb != 0u && sub == 0 && rank < G.M) {
       const size_t o = (size_t)b * G.M + rank;
-      const u32 a = key_tie(own) / (u32)G.C;
-      G.out_boxes[o] = clip01(decode_box(lv_delta(G.src, b, a), G.anchors[a], G.dp));
+      const u64 best = top[cfirst[i]];
+      G.out_boxes[o] = tbox[cfirst[i]];
       G.out_scores[o] = key_score(best);
       G.out_classes[o] = (long long)(key_tie(best) % (u32)G.C);   // tf.argmax of the row: the anchor's best pair
     }
@@ -403,8 +633,7 @@ __global__ void __launch_bounds__(RPP_EMIT_NT) global_top_direct_kernel(ColProbl
   // padded selected index 0 -> boxes[0] (clipped), score -1, class -1 (:258-268)
   for (int i = valid + tid; i < G.M; i += RPP_EMIT_NT) {
     const size_t o = (size_t)b * G.M + i;
-    const u32 a0 = got > 0 ? key_tie(top[0]) / (u32)G.C : 0u;
-    G.out_boxes[o] = clip01(decode_box(lv_delta(G.src, b, a0), G.anchors[a0], G.dp));
+    G.out_boxes[o] = tbox[0];
     G.out_scores[o] = -1.0f;
     G.out_classes[o] = -1;
   }
@@ -412,11 +641,13 @@ __global__ void __launch_bounds__(RPP_EMIT_NT) global_top_direct_kernel(ColProbl
     __syncthreads();
     GTD_T();
     if (tid == 0 && (b == 0 || b == 300))
-      printf("gtd b=%d n_keys=%d nv=%d nc=%d prepare=%lld kth=%lld topM=%lld cand=%lld out=%lld\n", b, n_keys, nv, nc,
-             tdbg[1] - tdbg[0], tdbg[2] - tdbg[1], tdbg[3] - tdbg[2], tdbg[4] - tdbg[3], tdbg[5] - tdbg[4]);
+      printf("gtd b=%d n_keys=%d m_top=%d nkbin=%d ne=%d rows=%d/%d prepare=%lld select=%lld ties+score=%lld cand=%lld out=%lld\n",
+             b, n_keys, m_top, nkbin, ne, nrows, nc_all, tdbg[1] - tdbg[0], tdbg[2] - tdbg[1], tdbg[3] - tdbg[2],
+             tdbg[4] - tdbg[3], tdbg[5] - tdbg[4]);
   }
 #undef GTD_T
 }
+
 
 // ===============================================================================================================
 // global_soft_kernel — NonMaxSuppressionV5 with soft_nms_sigma > 0 for ONE image per block, with the

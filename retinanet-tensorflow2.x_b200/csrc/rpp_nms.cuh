@@ -74,6 +74,8 @@ struct ColProblemParams {
   int* emit_done;          // [P] 1 = emit_sort_kernel already wrote this problem's keys; 2 = global_top_direct_kernel
                            // already wrote the image's detections (nothing downstream has work for it)
   int emit_direct;         // emit_done was initialised by global_top_direct_kernel
+  long n_loop;             // > 0: a few persistent blocks walk problems [0, n_loop) (almost all of them are already done:
+                           // the kernels behind global_top_direct_kernel); 0: one block per problem
   // tf.image.non_max_suppression_padded semantics (the TPU branches, postprocessing_ops.py:288-432; consumer
   // RPP_CONSUME_PADDED): 1 = _tpu_global_hard_nms (score filter inside), 2 = _tpu_per_class_hard_nms (every row is
   // a candidate; score_threshold / T_min of this struct are -inf and stop_score holds the config threshold)
@@ -833,6 +835,10 @@ __global__ void __launch_bounds__(RPP_NMS_NT) col_problem_kernel(ColProblemParam
       __syncthreads();
       if (s_item >= P.work_ctl[0]) break;
       p = P.work_items[s_item];
+    } else if (P.n_loop > 0) {
+      p = blockIdx.x + (size_t)it * gridDim.x;
+      if ((long)p >= P.n_loop) break;
+      if (it > 0) __syncthreads();
     } else if (it > 0) {
       break;
     }
@@ -1136,12 +1142,56 @@ __device__ __forceinline__ int emit_prepare(const ColProblemParams& P, EmitShare
   return nv;
 }
 
-__global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams P) {
-  pdl_enter();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
+// RAW keys (ordered logit bits | ~row) of one emission problem in sh->keys[0 .. n): the candidate list when it holds at
+// least k_lim elements, else an in-block exact re-collection of the column's best rows (as in emit_prepare).  The keys
+// are ALL elements of the column whose ordered logit encoding is >= o_complete.  Returns n >= k_lim, or -1 when the
+// block cannot serve the problem.
+// kmin / kmax: per-THREAD extrema of the keys the thread handled (~0 / 0 when it handled none): the caller reduces them.
+__device__ __forceinline__ int emit_prepare_raw(const ColProblemParams& P, EmitShared* sh, size_t p, int b, int c,
+                                                u32& o_complete, u64& kmin, u64& kmax) {
   const int tid = threadIdx.x;
-  const size_t p = blockIdx.x;
+  o_complete = 0xffffffffu;
+  kmin = ~0ull; kmax = 0ull;
+  const u32 n_raw = P.cand_count[p];
+  const float T = P.T[p];        // (both loads in flight together)
+  if (n_raw & 0x80000000u) return -1;
+  if (P.force_scan) return -1;   // debug: the generic kernel's exact scan is what is being tested
+  const bool list_ok = !(n_raw > (u32)P.CAP || n_raw > RPP_EMIT_CAP || (long)n_raw < P.k_lim);
+  if (list_ok) {
+    const uint2* lst = P.cand + p * (size_t)P.CAP;
+#pragma unroll 4
+    for (int i = tid; i < (int)n_raw; i += RPP_EMIT_NT) {
+      const uint2 e = lst[i];
+      const u64 k = ((u64)ord_f32(__uint_as_float(e.x)) << 32) | (u64)(0xffffffffu - e.y);
+      sh->keys[i] = k;
+      kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax;
+    }
+    __syncthreads();
+    o_complete = ord_f32(T > P.T_min ? T : P.T_min);
+    return (int)n_raw;
+  }
+  u64 KBr = ~0ull;
+  u32 population = 0u;
+  const long want = P.k_lim + P.k_lim / 8 + 64;
+  if (want > RPP_EMIT_CAP) return -1;   // more than one block's worth: the generic kernel takes it
+  const int m = select_chunk<RPP_EMIT_NT>(
+      [&](int i) -> u64 {
+        const float raw = lv_val(P.lv, b, i, P.C, c);
+        return raw >= P.T_min ? (((u64)ord_f32(raw) << 32) | (u64)(0xffffffffu - (u32)i)) : 0ull;
+      },
+      (int)P.N, KBr, (int)want, sh->keys, RPP_EMIT_CAP, &sh->sel, /*sort=*/false, &population);
+  if ((long)m < P.k_lim) return -1;
+  for (int i = tid; i < m; i += RPP_EMIT_NT) {
+    const u64 k = sh->keys[i];
+    kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax;
+  }
+  // rows with the cut's own logit may have been left out (higher row index): complete strictly above it
+  o_complete = (u32)m == population ? ord_f32(P.T_min) : (u32)(KBr >> 32) + 1u;
+  return m;
+}
+
+__device__ __forceinline__ void emit_sort_body(const ColProblemParams& P, EmitShared* sh, const size_t p) {
+  const int tid = threadIdx.x;
   const int b = (int)(p / P.C), c = (int)(p % P.C);
   if (P.emit_direct && P.emit_done[p] == 2) return;   // global_top_direct_kernel already wrote the image's detections
   if (tid == 0) P.emit_done[p] = 0;
@@ -1162,4 +1212,18 @@ __global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams
     __syncthreads();
   }
   if (tid == 0 && emitted == P.k_lim) P.emit_done[p] = 1;
+}
+
+__global__ void __launch_bounds__(RPP_EMIT_NT) emit_sort_kernel(ColProblemParams P) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  EmitShared* sh = reinterpret_cast<EmitShared*>(smem_raw);
+  if (P.n_loop > 0) {
+    for (size_t p = blockIdx.x; (long)p < P.n_loop; p += gridDim.x) {
+      emit_sort_body(P, sh, p);
+      __syncthreads();
+    }
+  } else {
+    emit_sort_body(P, sh, blockIdx.x);
+  }
 }
