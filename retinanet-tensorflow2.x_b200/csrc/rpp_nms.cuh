@@ -901,7 +901,14 @@ __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int
 // bound[p] = score of the last kept box when the cap was hit, else an upper bound for anything the class can still
 // keep (e0, the collect edge, or -inf when the class is exhausted).  Exactness never depends on tau.
 // ---------------------------------------------------------------------------------------------------------------
-#define RPP_PROBE_WARPS 8
+// 4 warps per block, at least 9 blocks per SM (<= 56 registers): all 5 120 problems of configs[1] are resident at once
+// (8-warp blocks at 50 registers left 48 of the 640 blocks to a second wave)
+#ifndef RPP_PROBE_WARPS
+#define RPP_PROBE_WARPS 4
+#endif
+#ifndef RPP_PROBE_MINB
+#define RPP_PROBE_MINB 9
+#endif
 #define RPP_PROBE_MAXCAP 16
 
 struct ProbeWarpShared {
@@ -918,7 +925,7 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
   return v;
 }
 
-__global__ void __launch_bounds__(RPP_PROBE_WARPS * 32) probe_warp_kernel(ColProblemParams P, size_t n_problems) {
+__global__ void __launch_bounds__(RPP_PROBE_WARPS * 32, RPP_PROBE_MINB) probe_warp_kernel(ColProblemParams P, size_t n_problems) {
   pdl_enter();
   __shared__ ProbeWarpShared s_all[RPP_PROBE_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
