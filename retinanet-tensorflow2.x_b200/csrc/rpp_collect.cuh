@@ -127,35 +127,34 @@ collect_cols4_levels_kernel(Levels lv /*[B,N,C] in per-level pieces*/, const flo
   u32* s_base = s_cnt + C;                               // [C]
   __shared__ long s_tile;
   __shared__ u32 s_span;
-  __shared__ long s_nl, s_goff, s_r0;      // per-tile level geometry, resolved once by thread 0
-  __shared__ const float* s_xb;
   const int tid = threadIdx.x;
   const int cq = tid % C4, rl = tid / C4;
   const bool active = rl < lanes;
   const long n_tiles = (long)B * tiles_per_image;
   for (;;) {
-    if (tid == 0) {
-      const long t = (long)atomicAdd(tile_counter, 1u);
-      s_tile = t;
-      if (t < n_tiles) {
-        const int bb = (int)(t / tiles_per_image), t_img = (int)(t % tiles_per_image);
-        int l = 0;
-        while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
-        s_nl = lv.off[l + 1] - lv.off[l];
-        s_goff = lv.off[l];
-        s_r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
-        s_xb = lv.x[l] + (size_t)bb * (lv.off[l + 1] - lv.off[l]) * C;
-      }
-    }
+    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
     if (tid == 0) s_span = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
     const int b = (int)(tile / tiles_per_image);
+    // Level geometry of the tile, by every thread from the block-uniform tile index with a select chain over the
+    // table in the kernel parameters: the values stay in UNIFORM registers.  (Staged through shared memory by thread
+    // 0 they came back in ordinary registers — four 64-bit values more per thread — and ptxas, at the 40-register
+    // budget of 3 x 512 threads per SM, re-used the destinations of the four loads of a round, i.e. serialised them:
+    // 282 us instead of 256 us for the same bytes.)
+    const int t_img = (int)(tile % tiles_per_image);
+    long off_lo = lv.off[0], off_hi = lv.off[1];
+    int toff = 0;
+    const float* xl = lv.x[0];
+#pragma unroll
+    for (int i = 1; i < RPP_MAX_LEVELS; ++i) {
+      if (i < lv.L && t_img >= lv.tile_off[i]) { off_lo = lv.off[i]; off_hi = lv.off[i + 1]; toff = lv.tile_off[i]; xl = lv.x[i]; }
+    }
     // rows are LOCAL to the level inside the loop; `goff` turns them into fused row indices when staged
-    const long n_l = s_nl, goff = s_goff, r0 = s_r0;
-    const float* __restrict__ xb = s_xb;
+    const long n_l = off_hi - off_lo, goff = off_lo, r0 = (long)(t_img - toff) * rows_per_tile;
+    const float* __restrict__ xb = xl + (size_t)b * n_l * C;
     const long r1 = r0 + rows_per_tile < n_l ? r0 + rows_per_tile : n_l;
     const size_t pbase = (size_t)b * C;
     if (active) {
@@ -244,37 +243,32 @@ collect_cols8_half_kernel(Levels lv, const float* __restrict__ T /*[B*C]*/, u32*
   u32* s_base = s_cnt + C;
   __shared__ long s_tile;
   __shared__ u32 s_span;
-  __shared__ long s_nl, s_goff, s_r0;      // per-tile level geometry, resolved once by thread 0
-  __shared__ const unsigned short* s_xb;
   const int tid = threadIdx.x;
   const int co = tid % C8, rl = tid / C8;
   const bool active = rl < lanes;
   const int dtype = lv.dtype;
   const long n_tiles = (long)B * tiles_per_image;
   for (;;) {
-    if (tid == 0) {
-      const long t = (long)atomicAdd(tile_counter, 1u);
-      s_tile = t;
-      if (t < n_tiles) {
-        const int bb = (int)(t / tiles_per_image), t_img = (int)(t % tiles_per_image);
-        int l = 0;
-        while (l + 1 < lv.L && t_img >= lv.tile_off[l + 1]) ++l;
-        s_nl = lv.off[l + 1] - lv.off[l];
-        s_goff = lv.off[l];
-        s_r0 = (long)(t_img - lv.tile_off[l]) * rows_per_tile;
-        s_xb = reinterpret_cast<const unsigned short*>(lv.x[l]) + (size_t)bb * (lv.off[l + 1] - lv.off[l]) * C;
-      }
-    }
+    if (tid == 0) s_tile = (long)atomicAdd(tile_counter, 1u);
     for (int i = tid; i < C; i += RPP_COLLECT_NT) s_cnt[i] = 0u;
     if (tid == 0) s_span = 0u;
     __syncthreads();
     const long tile = s_tile;
     if (tile >= n_tiles) break;
     const int b = (int)(tile / tiles_per_image);
-    const long n_l = s_nl, goff = s_goff, r0 = s_r0;
+    // level geometry from the block-uniform tile index (uniform registers: see collect_cols4_levels_kernel)
+    const int t_img = (int)(tile % tiles_per_image);
+    long off_lo = lv.off[0], off_hi = lv.off[1];
+    int toff = 0;
+    const float* xl = lv.x[0];
+#pragma unroll
+    for (int i = 1; i < RPP_MAX_LEVELS; ++i) {
+      if (i < lv.L && t_img >= lv.tile_off[i]) { off_lo = lv.off[i]; off_hi = lv.off[i + 1]; toff = lv.tile_off[i]; xl = lv.x[i]; }
+    }
+    const long n_l = off_hi - off_lo, goff = off_lo, r0 = (long)(t_img - toff) * rows_per_tile;
     const long r1 = r0 + rows_per_tile < n_l ? r0 + rows_per_tile : n_l;
     const size_t pbase = (size_t)b * C;
-    const unsigned short* __restrict__ xb = s_xb;
+    const unsigned short* __restrict__ xb = reinterpret_cast<const unsigned short*>(xl) + (size_t)b * n_l * C;
     if (active) {
       u32 th[4];   // the 8 class thresholds of this thread, packed in the input's 16-bit type
       {

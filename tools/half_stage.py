@@ -6,11 +6,11 @@ from retinanet import _native
 from retinanet.cfg.config import AttrDict
 from retinanet.model.layers import FusedPostProcessing
 B = 64
-layer = FusedPostProcessing(AttrDict(bench.CONFIG))
-h = layer.handle(bench.C)
+layer = FusedPostProcessing(AttrDict(bench.BASE_CONFIG))
+h = layer.handle(80)
 g = torch.Generator(device='cuda'); g.manual_seed(42)
-logits = torch.randn((B, bench.N_ANCHORS, bench.C), generator=g, device='cuda')
-deltas = (torch.randn((B, bench.N_ANCHORS, 4), generator=g, device='cuda') * 0.5).clamp_(-4, 4)
+logits = torch.randn((B, 76725, 80), generator=g, device='cuda')
+deltas = (torch.randn((B, 76725, 4), generator=g, device='cuda') * 0.5).clamp_(-4, 4)
 L = _native.lib()
 for name, tdt in (('f32', torch.float32), ('bf16', torch.bfloat16), ('f16', torch.float16)):
     x = {'class_logits': logits.to(tdt), 'encoded_boxes': deltas.to(tdt)}
