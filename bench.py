@@ -366,13 +366,18 @@ class Bench:
         flush = B * bpi < 190e6
         for dist in timed_dists:
             x = self.inputs(wl, params, B, dist, seed_offset=self.rank)
-            for _ in range(3):
-                layer(x)
-            replay, _ = layer.capture(x)
-            for _ in range(2):
-                replay()
+            # inputs that are not flushed out of L2 between steps alternate between two distinct sets (as the headline
+            # does): a 200-400 MB input replayed alone would find a third of itself in the 126 MB L2
+            xs = [x] if flush else [x, self.inputs(wl, params, B, dist, seed_offset=self.rank + 100)]
+            replays = []
+            for xi in xs:
+                for _ in range(3):
+                    layer(xi)
+                replays.append(layer.capture(xi)[0])
+            for rp in replays:
+                rp()
             torch.cuda.synchronize()
-            ms = self.time_steps([replay], steps, flush)
+            ms = self.time_steps(replays, steps, flush)
             rep, _ = self.stages(layer, h, x, min(steps, 10))
             dom = max(rep.items(), key=lambda kv: kv[1]) if rep else (None, None)
             r = {'ms_per_step': ms, 'images_per_s': B / ms * 1e3,
@@ -383,7 +388,7 @@ class Bench:
                 row.update(r)
             else:
                 row[dist] = r
-            del x, replay
+            del x, xs, replays
             torch.cuda.empty_cache()
         row['l2_flush_between_steps'] = bool(flush)
         row['path_bytes_per_image'] = bpi
@@ -539,6 +544,42 @@ def run_ours(args, rank, local_rank, world):
             'clustered_images_per_s': B / ms_clu * 1e3,
             'note': 'same step, eager calls: rpp_debug_force_exact_scan(1) = no sampled list is used, every '
                     '(image, class) problem selects from its whole column; clustered = tools/synth_inputs.py'}
+
+        # optional per-level pre-selection (north_star "per-level top-k"; the reference filters over the fused axis):
+        # FilterTopKDetectionsPerLevel (rpp_topk_levels), top-1000 per class and level on 16 images of the same
+        # geometry, scores resident; parity of 2 images against the oracle's composition of the reference filter
+        try:
+            from retinanet.model.layers import FilterTopKDetectionsPerLevel
+            from oracle import ref
+            import numpy as np
+            Bl = min(B, 16)
+            bounds = [0, 57600, 72000, 75600, 76500, 76725]
+            sc = torch.sigmoid(logits[:Bl])
+            bx = deltas[:Bl].contiguous()
+            lv_s = [sc[:, a:b_].contiguous() for a, b_ in zip(bounds[:-1], bounds[1:])]
+            lv_b = [bx[:, a:b_].contiguous() for a, b_ in zip(bounds[:-1], bounds[1:])]
+            del sc
+            flt = FilterTopKDetectionsPerLevel(1000, True)
+            xin = {'scores': lv_s, 'boxes': lv_b}
+            for _ in range(2):
+                o3 = flt(xin)
+            torch.cuda.synchronize()
+            ms_lv = bn.time_steps([lambda: flt(xin)], max(3, steps // 4), False)
+            es, eb, _ = ref.filter_per_level(np.concatenate([t[:2].cpu().numpy() for t in lv_s], axis=1),
+                                             np.concatenate([t[:2].cpu().numpy() for t in lv_b], axis=1), 1000, bounds,
+                                             per_class=True, threads=ref.hardware_threads())
+            same = bool(np.array_equal(o3['scores'][:2].cpu().numpy(), es)
+                        and np.array_equal(o3['boxes'][:2].cpu().numpy(), eb))
+            extras['per_level_top_k'] = {
+                'batch': Bl, 'k_per_level': 1000, 'rows_out': int(o3['scores'].shape[1]), 'ms_per_step': ms_lv,
+                'images_per_s': Bl / ms_lv * 1e3, 'bit_exact_vs_oracle': same,
+                'note': 'stage entry rpp_topk_levels on per-level score tensors [B,n_l,80] (per-class filter, '
+                        'outputs [B,4125,80] + boxes [B,4125,80,4] materialised); reported separately: the '
+                        'reference has no per-level mode'}
+            del lv_s, lv_b, o3, flt, xin
+            torch.cuda.empty_cache()
+        except Exception as exc:   # informational row: never fails the bench
+            extras['per_level_top_k'] = {'error': repr(exc)[:200]}
 
     # ---- end to end: pinned host buffers -> rpp_detect_host -> host outputs ------------------------------------
     e2e = None
