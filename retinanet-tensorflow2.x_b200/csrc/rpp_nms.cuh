@@ -1197,6 +1197,85 @@ __device__ __forceinline__ int emit_prepare_raw(const ColProblemParams& P, EmitS
   return m;
 }
 
+#define RPP_EMIT_BIN_MAX 256   // largest bin the bucket sort ranks by counting
+// Writes the k_lim best of the scored keys sh->keys[0 .. n_keys) (0 = not a key; at least k_lim are) to emit_key in
+// descending order.  Returns false (nothing written that matters) when the key distribution does not suit it.
+__device__ bool emit_bucket_sort(const ColProblemParams& P, EmitShared* sh, size_t p, int n_keys) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u32* hist = sh->sel.hist;     // [1024] counts, then scatter cursors
+  u32* offs = sh->sel.part;     // [1024] keys in the bins above (thread t owns bin t)
+  __shared__ u32 s_dk, s_total, s_bad;
+  u32 cnt = 0;
+  u64 mx = 0ull, mn = ~0ull;
+  for (int i = tid; i < n_keys; i += RPP_EMIT_NT) {
+    const u64 k = sh->keys[i];
+    if (k != 0ull) { ++cnt; mx = k > mx ? k : mx; mn = k < mn ? k : mn; }
+  }
+  block_cnt_max_min<RPP_EMIT_NT>(cnt, mx, mn, &sh->sel.bs);
+  if ((long)cnt < P.k_lim) return false;
+  const u64 q = (mx - mn) / 1024ull + 1ull;          // bin = floor((key - mn) / q) < 1024 (any monotone map would do)
+  const u64 rq = q > 1ull ? ~0ull / q : 0ull;        // umulhi(x, floor((2^64 - 1) / q)) <= x / q, monotone in x
+  auto bin_of = [&](u64 k) -> u32 { return q > 1ull ? (u32)__umul64hi(k - mn, rq) : (u32)(k - mn); };
+  hist[tid] = 0u;
+  if (tid == 0) s_bad = 0u;
+  __syncthreads();
+  for (int i = tid; i < n_keys; i += RPP_EMIT_NT) {
+    const u64 k = sh->keys[i];
+    if (k != 0ull) atomicAdd(&hist[bin_of(k)], 1u);
+  }
+  __syncthreads();
+  {
+    const u32 h = hist[tid];
+    u32 v = h;   // inclusive suffix count over the bins >= tid
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 t = __shfl_down_sync(RPP_FULL_MASK, v, o);
+      if (lane + o < 32) v += t;
+    }
+    __shared__ u32 s_wtot[32], s_wsfx[32];
+    if (lane == 0) s_wtot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      const u32 tot = s_wtot[lane];
+      u32 sfx = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_down_sync(RPP_FULL_MASK, sfx, o);
+        if (lane + o < 32) sfx += t;
+      }
+      s_wsfx[lane] = sfx - tot;
+    }
+    __syncthreads();
+    const u32 above = v - h + s_wsfx[warp];
+    offs[tid] = above;
+    const u32 kth = (u32)P.k_lim;
+    if (above < kth && above + h >= kth) { s_dk = (u32)tid; s_total = above + h; }
+    if (above < kth && h > RPP_EMIT_BIN_MAX) s_bad = 1u;   // a crowded bin at or above the k-th
+  }
+  __syncthreads();
+  const u32 d_k = s_dk, total = s_total;
+  if (s_bad || total > RPP_EMIT_CHUNK) return false;
+  hist[tid] = 0u;   // cursors
+  __syncthreads();
+  for (int i = tid; i < n_keys; i += RPP_EMIT_NT) {
+    const u64 k = sh->keys[i];
+    if (k == 0ull) continue;
+    const u32 bin = bin_of(k);
+    if (bin >= d_k) sh->chunk[offs[bin] + atomicAdd(&hist[bin], 1u)] = k;
+  }
+  __syncthreads();
+  u64* out = P.emit_key + p * (size_t)P.k_lim;
+  for (u32 i = tid; i < total; i += RPP_EMIT_NT) {
+    const u64 k = sh->chunk[i];
+    const u32 bin = bin_of(k);
+    const u32 s0 = offs[bin], e0 = s0 + hist[bin];
+    u32 rank = s0;
+    for (u32 j = s0; j < e0; ++j) rank += sh->chunk[j] > k;
+    if ((long)rank < P.k_lim) out[rank] = k;
+  }
+  return true;
+}
+
 __device__ __forceinline__ void emit_sort_body(const ColProblemParams& P, EmitShared* sh, const size_t p) {
   const int tid = threadIdx.x;
   const int b = (int)(p / P.C), c = (int)(p % P.C);
@@ -1204,6 +1283,16 @@ __device__ __forceinline__ void emit_sort_body(const ColProblemParams& P, EmitSh
   if (tid == 0) P.emit_done[p] = 0;
   int n_keys = 0;
   if (emit_prepare(P, sh, p, b, c, n_keys) < 0) return;
+  // ---- bucket sort: ONE histogram over a linear map of [min key, max key] onto 1024 bins orders the keys up to their
+  // bin (~10 keys per bin for a list of 10^4); the bins from the top down to the one that holds the k-th key are
+  // scattered into place and ranked inside themselves by counting.  Replaces a radix cut (whose MSB-first digits put a
+  // whole list into a dozen bins: the scores of a list share their exponent) plus an 8 192-key bitonic sort; lists with
+  // a crowded bin (heavy ties) or more than a chunk's worth above the k-th bin take that path below.
+  if (emit_bucket_sort(P, sh, p, n_keys)) {
+    if (tid == 0) P.emit_done[p] = 1;
+    return;
+  }
+  __syncthreads();
   // the k best keys, in order: usually ONE exact radix cut to [k, 8192] keys and one bitonic sort of that chunk
   u64 KB = ~0ull;
   long emitted = 0;
