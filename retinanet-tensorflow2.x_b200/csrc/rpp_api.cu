@@ -931,15 +931,14 @@ int detect_pipeline(Handle* h, Arena& ar, const float4* deltas, const float* log
     u64* dkey = (soft || top_only) ? ar.take<u64>((size_t)B * k) : nullptr;
     int* sd_cnt = (soft || top_only) ? ar.take<int>((size_t)B * 2) : nullptr;
     if (!ar.dry) {
-      if (!direct) CUDA_OK(cudaMemsetAsync(first, 0xff, (size_t)B * N * sizeof(u32), st));
       GlobalRowsParams rp{};
-      rp.skip = skip; rp.init_first = direct ? 1 : 0;
+      rp.skip = skip; rp.init_first = 1;   // every block presets its image's `first` itself: no memset node in the chain
       rp.n_loop = direct ? B : 0;
       const unsigned rows_grid = direct ? (unsigned)std::min(B, h->sm_count) : (unsigned)B;
       rp.emit_key = keys; rp.k = k; rp.C = C; rp.N = N;
       rp.first = first; rp.mraw = mraw; rp.skey = skey; rp.dkey = dkey; rp.sd_cnt = sd_cnt;
       rp.score_threshold = c.score_threshold;
-      launch_k(direct && h->pdl /* otherwise it follows a memset, not a kernel */, global_rows_kernel, dim3(rows_grid), dim3(RPP_GROWS_NT), 0, st, rp);
+      launch_k(h->pdl, global_rows_kernel, dim3(rows_grid), dim3(RPP_GROWS_NT), 0, st, rp);
       LAUNCHED();
       stage_mark(h, "rows:resolve", st);
     }

@@ -313,8 +313,9 @@ __device__ __forceinline__ float4 canon_or_empty(float4 orig, float& area) {
   return make_float4(INFINITY, INFINITY, -INFINITY, -INFINITY);
 }
 
+// prepared: abox[] already holds the boxes and every candidate was already tested against the kept boxes.
 __device__ void hard_nms_argmax(const ColProblemParams& P, NmsShared* sh, float4* abox, u64* keys, int m, int b, int c,
-                                size_t p, float L) {
+                                size_t p, float L, bool prepared) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float4* kbox = nms_kbox(sh);
   float* karea = nms_karea(sh, P.M_lim);
@@ -326,6 +327,10 @@ __device__ void hard_nms_argmax(const ColProblemParams& P, NmsShared* sh, float4
   for (int i = tid; i < m; i += RPP_NMS_NT) {
     const u64 k = keys[i];
     if (k == 0ull) continue;
+    if (prepared) {
+      if (k > best) { best = k; best_i = i; }
+      continue;
+    }
     float4 orig = col_box(P, b, c, key_tie(k));
     if (P.clip_before) orig = clip01(orig);
     abox[i] = orig;
@@ -623,6 +628,7 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
     sh->done = 0;
     sh->need_all = 0;
     sh->nk_slot[0] = 0;
+    sh->nk_slot[1] = 0;
     if (MODE == RPP_CONSUME_SOFT) ss->rcount = 0;
     if (MODE == RPP_CONSUME_PADDED && P.padded == 2) {
       float s0 = -INFINITY;
@@ -667,22 +673,44 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
   // sorted and consumed here; if the consumer wants more, phase A continues below the bound e0 with the full list.
   u64 KB_A = ~0ull;          // phase A consumes keys below this bound
   bool skip_A = false;
-  // ---- finish pass of the hard modes: argmax-iterate over the whole list (hard_nms_argmax) -------------------
+  // ---- finish pass of the hard modes: argmax-iterate (hard_nms_argmax) over what the probe's boxes leave alive -----
+  // The boxes the probe kept ARE the first boxes greedy NMS keeps, so the finish pass continues from them instead of
+  // starting over: ONE pass over the list scores every candidate at or above the bound (a logit clearly below the
+  // bound's pre-image is dropped without evaluating the sigmoid), decodes it, tests it against the probe's boxes and
+  // stages the survivors — on trained-detector inputs a few per cent of a hot class's list — in shared memory, where
+  // the argmax rounds run.  More survivors than shared memory holds (a class whose candidates mostly do NOT overlap:
+  // the case the tile NMS below is built for) leaves the class to the generic path, from scratch.
+  bool argmax_done = false;
   if (MODE == RPP_CONSUME_HARD && P.pass == 2 && P.argmax && n_list > 0 && (long)n_list <= P.k_lim) {
     float4* abox = reinterpret_cast<float4*>(ss);
+    float4* kbox = nms_kbox(sh);
+    float* karea = nms_karea(sh, P.M_lim);
+    u64* pk = sh->chunk;   // keys of the probe's boxes
     const float L = P.stop_L[b];
-    uint2* lst = P.cand + p * (size_t)P.CAP;
-    u64* gkeys = reinterpret_cast<u64*>(lst);
-    const bool in_smem = n_list <= RPP_LIST_SMEM;
-    u64* keys = in_smem ? sh->lkeys : gkeys;
-    // scored keys of the consumable candidates at or above the bound (a logit clearly below the bound's pre-image is
-    // dropped without evaluating the sigmoid); `below` = some consumable candidate was dropped for being below L
+    const float thr = P.iou_threshold;
+    const uint2* lst = P.cand + p * (size_t)P.CAP;
+    const u64* gkeys = reinterpret_cast<const u64*>(lst);
+    int nk0 = P.sel_cnt[p];
+    if (nk0 > P.M_cap) nk0 = P.M_cap;
+    if (tid < nk0) {
+      float area;
+      kbox[tid] = canon_or_empty(P.sel_box[p * P.M + tid], area);
+      karea[tid] = area;
+      pk[tid] = P.sel_key[p * P.M + tid];
+    }
     float raw_lo = -INFINITY;
     if (P.is_logit && L > 0.0f && L < 1.0f) {
       const float x = __logf(L / (1.0f - L));
       raw_lo = x - 1e-3f * (1.0f + fabsf(x));
     }
+    // The probe's boxes must all come out of the LIST: a probe that went on into the exact scan below the list's edge
+    // kept boxes the scan of this pass would meet again (a zero-area box, or an IoU threshold of 1, is not suppressed
+    // by its own copy) — such a class starts over on the generic path.
+    const bool from_list =
+        __syncthreads_and(tid >= nk0 || list_complete || key_score(P.sel_key[p * P.M + tid]) > s_edge) != 0;
+    // `below` = some consumable candidate was dropped for being below L (the class is then finished once the list is)
     int below = 0, n_valid = 0;
+    if (from_list)
     for (int i = tid; i < n_list; i += RPP_NMS_NT) {
       u64 k = 0ull;
       if (converted) {
@@ -700,35 +728,43 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
           }
         }
       }
-      if (in_smem || converted) { if (in_smem) sh->lkeys[i] = k; else if (k == 0ull) gkeys[i] = 0ull; }
-      else gkeys[i] = k;
-      n_valid += k != 0ull;
+      if (k == 0ull) continue;
+      ++n_valid;
+      bool dead = false;
+      for (int q = 0; q < nk0; ++q) dead = dead || pk[q] == k;   // one of the probe's own boxes
+      if (dead) continue;
+      float4 orig = col_box(P, b, c, key_tie(k));
+      if (P.clip_before) orig = clip01(orig);
+      float area;
+      const float4 bx = canon_or_empty(orig, area);
+      for (int q = 0; q < nk0; ++q)
+        if (iou_gt(bx, area, kbox[q], karea[q], thr)) { dead = true; break; }
+      if (dead) continue;
+      const int slot = atomicAdd(&sh->nk_slot[1], 1);
+      if (slot < RPP_LIST_SMEM) { sh->lkeys[slot] = k; abox[slot] = orig; }
     }
-    if (n_valid) atomicAdd(&sh->nk_slot[0], n_valid);   // (zeroed with the other per-problem state above)
+    if (n_valid) atomicAdd(&sh->nk_slot[0], n_valid);   // (both counters are zeroed with the per-problem state above)
     below = __syncthreads_or(below);
     n_valid = sh->nk_slot[0];
-    if (!converted && !in_smem && tid == 0) P.cand_count[p] = n_raw | 0x80000000u;
-    if (in_smem) {
-      hard_nms_argmax(P, sh, abox, sh->lkeys, n_list, b, c, p, L);
-    } else {
-      u64 KB = ~0ull;
-      while (!sh->done) {
-        const int m = select_chunk<RPP_NMS_NT>([&](int i) { return gkeys[i]; }, n_list, KB, RPP_LIST_SMEM, sh->lkeys,
-                                               RPP_LIST_SMEM, &sh->sel, /*sort=*/false);
-        if (m == 0) break;
-        hard_nms_argmax(P, sh, abox, sh->lkeys, m, b, c, p, L);
-        __syncthreads();
-      }
-    }
-    consumed += n_valid;
-    // the list is exhausted: what was left out of it scores at most s_edge — if that (or anything dropped above) is
-    // below the bound, the class is finished; otherwise phase B continues below the edge
-    if (!sh->done && (below || list_complete || s_edge < L)) {
+    const int nsurv = sh->nk_slot[1];
+    if (from_list && nsurv <= RPP_LIST_SMEM) {
+      if (tid == 0) { sh->nkept = nk0; if (nk0 >= P.M_cap) sh->done = 1; }
       __syncthreads();
-      if (tid == 0) sh->done = 1;
+      if (nk0 < P.M_cap) hard_nms_argmax(P, sh, abox, sh->lkeys, nsurv, b, c, p, L, /*prepared=*/true);
+      consumed += n_valid;
+      // the list is exhausted: what was left out of it scores at most s_edge — if that (or anything dropped above)
+      // is below the bound, the class is finished; otherwise phase B continues below the edge
+      if (!sh->done && (below || list_complete || s_edge < L)) {
+        __syncthreads();
+        if (tid == 0) sh->done = 1;
+      }
+      __syncthreads();
+      skip_A = true;
+      argmax_done = true;
     }
     __syncthreads();
-    skip_A = true;
+  }
+  if (argmax_done) {
   } else
   if (MODE != RPP_CONSUME_EMIT && P.is_logit && n_list > 0 && n_list <= RPP_LIST_SMEM && !converted) {
     const uint2* lst = P.cand + p * (size_t)P.CAP;

@@ -11,11 +11,11 @@ for w in c1 c2 c3 c4 c5 c2s c2:clustered c3:clustered; do
 done > gpurun_out/${TAG}_launch_summary.txt 2>&1
 full() {  # workload kernel-regex
   timeout 300 ncu --set full --import-source on --clock-control none -k "regex:$2" -c 1 -f \
-    -o gpurun_out/${TAG}_full_$1_$3 python bench.py --workload ${1%%:*} $( [[ $1 == *:* ]] && echo --logits ${1#*:} ) \
+    -o gpurun_out/${TAG}_full_${1/:/_}_$3 python bench.py --workload ${1%%:*} $( [[ $1 == *:* ]] && echo --logits ${1#*:} ) \
     --quick --steps 2 --warmup 3 > gpurun_out/${TAG}_fullncu_$3.log 2>&1
-  python tools/ncu_summary.py gpurun_out/${TAG}_full_$1_$3.ncu-rep >> gpurun_out/${TAG}_ncu_summary.txt 2>&1
-  python tools/ncu_lines.py gpurun_out/${TAG}_full_$1_$3.ncu-rep "$2" 25 > gpurun_out/${TAG}_ncu_lines_$3.txt 2>&1
-  rm -f gpurun_out/${TAG}_full_$1_$3.ncu-rep   # (the merge back is capped at 64 MiB: keep the text, drop the report)
+  python tools/ncu_summary.py gpurun_out/${TAG}_full_${1/:/_}_$3.ncu-rep >> gpurun_out/${TAG}_ncu_summary.txt 2>&1
+  python tools/ncu_lines.py gpurun_out/${TAG}_full_${1/:/_}_$3.ncu-rep "$2" 25 > gpurun_out/${TAG}_ncu_lines_$3.txt 2>&1
+  rm -f gpurun_out/${TAG}_full_${1/:/_}_$3.ncu-rep   # (the merge back is capped at 64 MiB: keep the text, drop the report)
 }
 rm -f gpurun_out/${TAG}_ncu_summary.txt
 full c2 collect_cols4_kernel collect_cols4
@@ -27,6 +27,7 @@ full c3 collect_flat_kernel collect_flat
 full c3 emit_sort_kernel emit_sort
 full c3 global_rows_kernel global_rows
 full c3 global_soft_kernel global_soft
-full c5 global_top_kernel global_top
+full c5 global_top_direct_kernel global_top_direct
+full c2:clustered 'col_problem_kernel' col_problem_finish_clustered
 full c4 collect_cols4_kernel collect_cols4_c4
 tail -5 gpurun_out/${TAG}_launch_summary.txt; wc -l gpurun_out/${TAG}_ncu_summary.txt
