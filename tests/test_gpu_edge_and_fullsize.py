@@ -465,3 +465,29 @@ def test_sharded_batches_equal_the_whole_batch(mode, fpc):
     shuffled = to_numpy(layer({k: v[perm].contiguous() for k, v in x.items()}))
     for key in whole:
         assert np.array_equal(whole[key][perm.cpu().numpy()], shuffled[key]), key
+
+
+@pytest.mark.parametrize('mode', ['PerClassHardNMS', 'CombinedNMS'])
+@pytest.mark.parametrize('iou', [0.5, 1.0])
+def test_finish_pass_argmax_equals_tile_path_on_clustered_inputs(ref, monkeypatch, mode, iou):
+    """Trained-detector-like inputs at the configs[1] geometry: the finish pass that continues from the probe's boxes
+    (hard_nms_argmax over the survivors) against the sorted-chunk / tile NMS it replaces (RPP_FINISH_ARGMAX=0) and the
+    oracle; iou 1.0 = nothing suppressed (every candidate survives the prefilter: the overflow route)."""
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    from tools import synth_inputs
+    from retinanet.model.layers import FusedPostProcessing
+    p = make_params(640, num_classes=80, mode=mode, pre_nms_top_k=5000, filter_per_class=True, iou_threshold=iou)
+    H, W = p.input.input_shape
+    ap = p.anchor_params
+    anchors = torch.from_numpy(ref.anchors(H, W, 3, 7, ap.areas, ap.aspect_ratios, ap.scales)[0])
+    lg, dl = synth_inputs.make_inputs('clustered', 4, anchors, 80, 640, 640, 'cpu', seed_logits=11, seed_deltas=12)
+    x = {'class_logits': lg.cuda(), 'encoded_boxes': dl.cuda()}
+    monkeypatch.setenv('RPP_FINISH_ARGMAX', '1')
+    got = to_numpy(FusedPostProcessing(p)(x))
+    monkeypatch.setenv('RPP_FINISH_ARGMAX', '0')
+    old = to_numpy(FusedPostProcessing(p)(x))
+    exp = oracle_detect(ref, p, lg.numpy(), dl.numpy(), threads=8)
+    assert image_mismatches(got, exp) == []
+    assert image_mismatches(old, exp) == []

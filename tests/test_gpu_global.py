@@ -196,3 +196,46 @@ def test_every_mode_reads_head_outputs_in_place(ref, monkeypatch, dtype, mode, k
     deltas = np.concatenate([box[str(l)].float().numpy().reshape(B, -1, 4) for l in range(3, 8)], 1)
     exp = oracle_detect(ref, p, logits, deltas)
     assert image_mismatches(got, exp) == []
+
+
+def _coarse(rng, shape):
+    """a handful of distinct values: huge tie groups, saturated scores (sigmoid(20) == sigmoid(40) == 1.0f)"""
+    return rng.choice(np.array([-30.0, -3.0, -0.5, 0.0, 0.5, 3.0, 20.0, 40.0], np.float32), size=shape)
+
+
+@pytest.mark.parametrize('H,C,B,k,M', [(320, 5, 6, 5000, 100), (192, 3, 3, 1000, 100), (320, 80, 2, 5000, 100),
+                                       (320, 5, 3, 5000, 1000), (128, 2, 2, 50, 100)])
+@pytest.mark.parametrize('dist', ['dense', 'quantized', 'coarse', 'constant', 'near_ties'])
+def test_global_hard_direct_kernel_vs_sorted_path_and_oracle(ref, monkeypatch, H, C, B, k, M, dist):
+    """GlobalHardNMS behind the global filter: global_top_direct_kernel (raw-key selection, tie group of the k-th score
+    resolved with the sigmoid itself) against the sorted-emission path (RPP_TOP_DIRECT=0) and the oracle — dense logits,
+    heavy exact ties, saturated scores and constant logits (the direct kernel gives those images up: the kernels behind
+    it take over), and logits a few ulps apart that round to ONE score around the k-th position."""
+    from retinanet.model.layers import FusedPostProcessing
+    p = make_params(H, num_classes=C, mode='GlobalHardNMS', pre_nms_top_k=k, filter_per_class=False, max_detections=M,
+                    score_threshold=0.05)
+    N = _anchors(ref, p).shape[0]
+    rng = np.random.default_rng(H * 7 + C * 13 + k + len(dist))
+    if dist == 'dense':
+        logits = rng.standard_normal((B, N, C)).astype(np.float32)
+        logits[:, :, 0] += 0.5 * logits[:, :, -1]
+    elif dist == 'quantized':
+        logits = (np.round(rng.standard_normal((B, N, C)) * 8) / 8).astype(np.float32)
+    elif dist == 'coarse':
+        logits = _coarse(rng, (B, N, C))
+    elif dist == 'constant':
+        logits = np.full((B, N, C), 1.25, np.float32)
+    else:   # values spaced by single ulps around 3.0: groups of ~8 consecutive floats share one fp32 score
+        base = np.float32(3.0).view(np.int32)
+        logits = (base + rng.integers(-600, 600, size=(B, N, C)).astype(np.int32)).view(np.float32)
+    deltas = np.clip(rng.standard_normal((B, N, 4)) * 0.3, -4, 4).astype(np.float32)
+    x = {'class_logits': torch.from_numpy(logits).cuda(), 'encoded_boxes': torch.from_numpy(deltas).cuda()}
+    monkeypatch.setenv('RPP_TOP_DIRECT', '1')
+    got = to_numpy(FusedPostProcessing(p)(x))
+    monkeypatch.setenv('RPP_TOP_DIRECT', '0')
+    srt = to_numpy(FusedPostProcessing(p)(x))
+    exp = oracle_detect(ref, p, logits, deltas, threads=8)
+    assert image_mismatches(got, exp) == []
+    assert image_mismatches(srt, exp) == []
+    for key in ('scores', 'classes', 'valid_detections', 'boxes'):
+        assert np.array_equal(got[key], srt[key]), key
