@@ -563,7 +563,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
     else
       launch();
     LAUNCHED();
-    const int bthreads = (int)std::min<size_t>(1024, align_up((size_t)C * m1, 32));
+    const int bthreads = (int)std::min<size_t>(1024, align_up((size_t)C * m1 * 2, 32));   // the rank loop uses 4 lanes per box
     u32* work_ctl = tile_counter + 16;   // zeroed with the counters by the memset above
     launch_k(h->pdl, perclass_bound_kernel, dim3(B), dim3(bthreads), (size_t)C * m1 * sizeof(float), st, ps.sel_key, ps.sel_cnt, C, ps.M, m1,
                                                                               ps.M, stop_L, bound, work_items,

@@ -904,15 +904,19 @@ __global__ void perclass_bound_kernel(const u64* __restrict__ sel_key, const int
   if (local) atomicAdd(&s_n, local);
   __syncthreads();
   if (s_n >= Mtop) {
-    for (int i = threadIdx.x; i < n_all; i += blockDim.x) {
-      const float v = s_sc[i];
-      if (!(v > -INFINITY)) continue;
+    // rank by counting, 4 lanes per element (the counting loop is this kernel's latency chain)
+    for (int i0 = 0; i0 < n_all; i0 += blockDim.x / 4) {
+      const int i = i0 + (threadIdx.x >> 2), sub = threadIdx.x & 3;
+      const float v = i < n_all ? s_sc[i] : -INFINITY;
       int rank = 0;
-      for (int j = 0; j < n_all; ++j) {
-        const float o = s_sc[j];
-        rank += (o > v) || (o == v && j < i);
-      }
-      if (rank == Mtop - 1) s_L = v;   // exactly one element has this rank
+      if (v > -INFINITY)
+        for (int j = sub; j < n_all; j += 4) {
+          const float o = s_sc[j];
+          rank += (o > v) || (o == v && j < i);
+        }
+      rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 1);
+      rank += __shfl_xor_sync(RPP_FULL_MASK, rank, 2);
+      if (v > -INFINITY && sub == 0 && rank == Mtop - 1) s_L = v;   // exactly one element has this rank
     }
   }
   __syncthreads();
