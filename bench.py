@@ -536,12 +536,19 @@ def run_ours(args, rank, local_rank, world):
         for _ in range(3):
             layer(xc)
         torch.cuda.synchronize()
+        _native.exact_scans(h.ptr, reset=True)
+        layer(xs[0])
+        scans_dense = _native.exact_scans(h.ptr, reset=True)
+        layer(xc)
+        scans_clu = _native.exact_scans(h.ptr, reset=True)
         ms_clu = bn.time_steps([lambda: layer(xc)], steps, False)
         del xc
         torch.cuda.empty_cache()
         extras['worst_case'] = {
             'forced_exact_scan_ms_per_step': ms_scan, 'clustered_ms_per_step': ms_clu,
             'clustered_images_per_s': B / ms_clu * 1e3,
+            'exact_scans_per_step': {'dense': scans_dense, 'clustered': scans_clu, 'problems': B * C,
+                                     'note': 'rpp_debug_exact_scans: problems whose sampled list ran dry'},
             'note': 'same step, eager calls: rpp_debug_force_exact_scan(1) = no sampled list is used, every '
                     '(image, class) problem selects from its whole column; clustered = tools/synth_inputs.py'}
 

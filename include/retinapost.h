@@ -209,6 +209,12 @@ int rpp_classes_itemsize(void* handle);
  * selection (1), or restore the default sampled pre-threshold (0). */
 int rpp_debug_force_exact_scan(void* handle, int on);
 
+/* How often the sampled pre-threshold missed: the number of problems ((image, class) columns, or flat columns of the
+ * global filter) that left their candidate list for an exact scan / re-collection of the whole column in the calls on
+ * this handle since the last reset — results never depend on it, speed does (DESIGN.md "perf cliff").  Synchronises
+ * the device.  No reference counterpart. */
+int rpp_debug_exact_scans(void* handle, unsigned long long* h_count, int reset);
+
 /* Test hook (no device needed): the sampling plan the library would use for columns of n rows and C classes —
  * NMS problems (emit = 0, k_lim ignored) or top-k emission of k_lim rows (emit = 1).  h_out[8] = {sampled?, stride,
  * groups G, sampled rows per group, rank of the group maximum used as threshold, list capacity, targeted list

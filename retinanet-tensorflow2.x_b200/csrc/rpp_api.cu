@@ -63,6 +63,7 @@ struct Handle {
   int levels;
   AnchorParams ap;
   float4* d_anchors;
+  u32* d_scan_count;     // problems that left their candidate list for an exact scan of the column (rpp_debug_exact_scans)
   float T_logit;   // smallest logit whose sigmoid exceeds score_threshold
   int device;
   int sm_count;
@@ -523,6 +524,7 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   pp.M = ps.M; pp.M_lim = ps.M_lim; pp.k_lim = ps.k_lim;
   pp.T = T; pp.cand_count = cand_count; pp.cand = cand; pp.CAP = plan.CAP;
   pp.force_scan = scan_only;
+  pp.scan_count = h->d_scan_count;
   pp.sel_key = ps.sel_key; pp.sel_box = ps.sel_box; pp.sel_cnt = ps.sel_cnt;
   pp.soft_scale = ps.soft_sigma_tf > 0.0f ? -0.5f / ps.soft_sigma_tf : 0.0f;
   pp.soft_ignores_iou = h->cfg.soft_ignores_iou_threshold;
@@ -1071,6 +1073,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   Handle* h = new (std::nothrow) Handle();
   if (!h) return fail(RPP_EINVAL, "out of host memory");
   h->d_anchors = nullptr;
+  h->d_scan_count = nullptr;
   h->side = nullptr;
   h->ev_join = nullptr;
   for (int i = 0; i < 8; ++i) h->ev_chunk[i] = nullptr;
@@ -1156,6 +1159,7 @@ int rpp_create(const rpp_config* cfg, void** handle) {
   cudaError_t e = cudaMalloc(&h->d_anchors, (size_t)n * sizeof(float4));
   if (e != cudaSuccess) return fail(RPP_ECUDA, "cudaMalloc anchors: %s", cudaGetErrorString(e));
   anchors_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ap, n, h->d_anchors);
+  if (cudaMalloc(&h->d_scan_count, sizeof(u32)) == cudaSuccess) cudaMemset(h->d_scan_count, 0, sizeof(u32));
   float* d_t = nullptr;
   e = cudaMalloc(&d_t, sizeof(float));
   if (e == cudaSuccess) {
@@ -1198,6 +1202,7 @@ int rpp_destroy(void* handle) {
   Handle* h = (Handle*)handle;
   if (!h) return RPP_OK;
   cudaFree(h->d_anchors);
+  cudaFree(h->d_scan_count);
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   host_path_free(h);
   if (h->side) cudaStreamDestroy(h->side);
@@ -1224,6 +1229,19 @@ int rpp_classes_itemsize(void* handle) {
 int rpp_debug_force_exact_scan(void* handle, int on) {
   if (!handle) return fail(RPP_EINVAL, "null handle");
   ((Handle*)handle)->force_scan = on ? 1 : 0;
+  return RPP_OK;
+}
+
+int rpp_debug_exact_scans(void* handle, unsigned long long* h_count, int reset) {
+  Handle* h = (Handle*)handle;
+  if (!h || !h_count) return fail(RPP_EINVAL, "null argument");
+  if (int rc = check_device(h)) return rc;
+  u32 v = 0;
+  if (h->d_scan_count) {
+    CUDA_OK(cudaMemcpy(&v, h->d_scan_count, sizeof(u32), cudaMemcpyDeviceToHost));   // (synchronises the device)
+    if (reset) CUDA_OK(cudaMemset(h->d_scan_count, 0, sizeof(u32)));
+  }
+  *h_count = v;
   return RPP_OK;
 }
 

@@ -57,6 +57,7 @@ struct ColProblemParams {
   uint2* cand;             // [P][CAP]
   int CAP;
   int force_scan;          // debug: ignore the lists, use the exact column scan only
+  u32* scan_count;         // handle-wide counter: problems that went on to an exact scan of their column
   // outputs per problem
   u64* sel_key;            // [P][M]  (final score bits | ~row index)
   float4* sel_box;         // [P][M]  kept boxes as they leave NMS (clipped iff clip_before)
@@ -830,6 +831,7 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
   }
   // ---- phase B: exact scan of the column for everything at or below the edge ---------------------------------
   if (!sh->done && consumed < P.k_lim && (!list_complete || overflow || P.force_scan)) {
+    if (tid == 0 && P.scan_count) atomicAdd(P.scan_count, 1u);
     u64 KB = (s_edge == INFINITY) ? ~0ull : ((u64)(ord_f32(s_edge) + 1u) << 32);
     auto keyfn = [&](int i) -> u64 {
       const float raw = lv_val(P.lv, b, i, P.C, c);
@@ -1161,6 +1163,7 @@ __device__ __forceinline__ int emit_prepare(const ColProblemParams& P, EmitShare
     u32 population = 0u;
     long want = P.k_lim + P.k_lim / 8 + 64;
     if (want > RPP_EMIT_CAP) return -1;   // more than one block's worth: the generic kernel takes it
+    if (tid == 0 && P.scan_count) atomicAdd(P.scan_count, 1u);
     const int m = select_chunk<RPP_EMIT_NT>(
         [&](int i) -> u64 {
           const float raw = lv_val(P.lv, b, i, P.C, c);
@@ -1221,6 +1224,7 @@ __device__ __forceinline__ int emit_prepare_raw(const ColProblemParams& P, EmitS
   u32 population = 0u;
   const long want = P.k_lim + P.k_lim / 8 + 64;
   if (want > RPP_EMIT_CAP) return -1;   // more than one block's worth: the generic kernel takes it
+  if (tid == 0 && P.scan_count) atomicAdd(P.scan_count, 1u);
   const int m = select_chunk<RPP_EMIT_NT>(
       [&](int i) -> u64 {
         const float raw = lv_val(P.lv, b, i, P.C, c);

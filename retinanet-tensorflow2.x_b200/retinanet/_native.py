@@ -18,7 +18,7 @@ EXPORTS = [
     'rpp_anchors', 'rpp_workspace_bytes', 'rpp_decode', 'rpp_topk', 'rpp_topk_levels', 'rpp_nms', 'rpp_detect', 'rpp_detect_levels', 'rpp_detect_typed',
     'rpp_detect_host', 'rpp_detect_host_typed', 'rpp_coco_format', 'rpp_efficient_nms',
     'rpp_last_launch_count', 'rpp_classes_itemsize', 'rpp_debug_force_exact_scan', 'rpp_debug_stage_timing',
-    'rpp_debug_stage_ms', 'rpp_debug_stage_report', 'rpp_debug_sample_plan',
+    'rpp_debug_stage_ms', 'rpp_debug_stage_report', 'rpp_debug_sample_plan', 'rpp_debug_exact_scans',
 ]
 
 
@@ -87,6 +87,8 @@ def lib():
         L.rpp_efficient_nms.argtypes = [vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
         L.rpp_classes_itemsize.argtypes = [vp]
         L.rpp_debug_force_exact_scan.argtypes = [vp, ci]
+        if hasattr(L, 'rpp_debug_exact_scans'):
+            L.rpp_debug_exact_scans.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong), ci]
         L.rpp_debug_sample_plan.argtypes = [cl, ci, cl, ci, ctypes.POINTER(ci)]
         L.rpp_debug_stage_timing.argtypes = [vp, ci]
         L.rpp_debug_stage_ms.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ci)]
@@ -106,6 +108,14 @@ def stage_report(handle_ptr):
             k, v = item.rsplit('=', 1)
             out[k] = float(v)
     return out, int(n.value)
+
+
+def exact_scans(handle_ptr, reset=True):
+    """Problems that left their candidate list for an exact scan of the whole column since the last reset (how often
+    the sampled pre-threshold missed; include/retinapost.h rpp_debug_exact_scans).  Synchronises the device."""
+    n = ctypes.c_ulonglong()
+    check(lib().rpp_debug_exact_scans(handle_ptr, ctypes.byref(n), int(bool(reset))))
+    return int(n.value)
 
 
 def last_error():

@@ -491,3 +491,26 @@ def test_finish_pass_argmax_equals_tile_path_on_clustered_inputs(ref, monkeypatc
     exp = oracle_detect(ref, p, lg.numpy(), dl.numpy(), threads=8)
     assert image_mismatches(got, exp) == []
     assert image_mismatches(old, exp) == []
+
+
+def test_exact_scan_counter(ref):
+    """rpp_debug_exact_scans: 0 on ordinary inputs (the sampled lists serve every problem), every problem counted once
+    with the lists bypassed (rpp_debug_force_exact_scan), reset on read."""
+    from retinanet import _native
+    from retinanet.model.layers import FusedPostProcessing
+    p = make_params(320, num_classes=8, mode='PerClassHardNMS', pre_nms_top_k=5000, filter_per_class=True)
+    layer = FusedPostProcessing(p)
+    h = layer.handle(8)
+    logits, deltas = synth_inputs(3, h.num_anchors, 8, seed=5)
+    x = {'class_logits': torch.from_numpy(logits).cuda(), 'encoded_boxes': torch.from_numpy(deltas).cuda()}
+    _native.exact_scans(h.ptr, reset=True)
+    a = to_numpy(layer(x))
+    assert _native.exact_scans(h.ptr, reset=True) == 0
+    _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 1))
+    b = to_numpy(layer(x))
+    n = _native.exact_scans(h.ptr, reset=False)
+    assert n >= 3 * 8                      # probe pass and finish pass both scan: at least once per problem
+    assert _native.exact_scans(h.ptr, reset=True) == n and _native.exact_scans(h.ptr) == 0
+    _native.check(_native.lib().rpp_debug_force_exact_scan(h.ptr, 0))
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
