@@ -328,8 +328,13 @@ int run_problem_set(Handle* h, Arena& ar, ProblemSet& ps, cudaStream_t st, cudaS
   if (plan.on && !h->force_scan) {
     const int threads = (int)align_up((size_t)plan.lanes * C, 32);
     // narrow problem sets (C = 1: 48 active threads per block) need more blocks in flight to cover the load latency
-    const int max_split = threads <= 64 ? 64 : 16;
-    const int split = plan.rows_per_group < max_split ? plan.rows_per_group : max_split;
+    static const int split_env = [] { const char* v = getenv("RPP_SAMPLE_SPLIT"); return v ? atoi(v) : 0; }();
+    const int max_split = split_env > 0 ? split_env : (threads <= 64 ? 64 : 16);
+    int split = plan.rows_per_group < max_split ? plan.rows_per_group : max_split;
+    // two 960-thread blocks per SM: about two full waves of blocks (configs[1]: 64 x 9 = 576 of 592) instead of 3.5
+    // (64 x 16) — the tail of the last partial wave cost 2 us of the 23
+    if (split_env <= 0 && threads > 64 && (long)B * split > 4L * h->sm_count)
+      split = std::max(1, (int)(4L * h->sm_count / B));
     if (C == 1 && lv.L == 1 && lv.dtype == RPP_DT_F32 && plan.rows_per_group >= 8) {
       const int lead = (int)(((uintptr_t)lv.x[0] % 16) / 4);
       sample_max_flat4_kernel<<<dim3(B, std::min(plan.rows_per_group / 4, max_split)), threads, 0, st>>>(
