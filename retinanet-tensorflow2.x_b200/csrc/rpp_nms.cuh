@@ -711,38 +711,68 @@ __device__ __forceinline__ void col_problem_body(const ColProblemParams& P, cons
         __syncthreads_and(tid >= nk0 || list_complete || key_score(P.sel_key[p * P.M + tid]) > s_edge) != 0;
     // `below` = some consumable candidate was dropped for being below L (the class is then finished once the list is)
     int below = 0, n_valid = 0;
+    // (four candidates per thread and trip: the list entries, then the deltas / anchors of the live ones, are loaded
+    // together — one candidate at a time the loop was a chain of three dependent global loads per candidate, and this
+    // kernel has 16 warps per SM to hide them with)
+    const bool plain_boxes = !P.boxes && !P.row_keys && P.dlv.L == 0;   // rows of the delta tensor itself
     if (from_list)
-    for (int i = tid; i < n_list; i += RPP_NMS_NT) {
-      u64 k = 0ull;
+    for (int i0 = tid; i0 < n_list; i0 += 4 * RPP_NMS_NT) {
+      u64 k4[4];
       if (converted) {
-        k = gkeys[i];
-        if (k != 0ull && key_score(k) < L) { k = 0ull; below = 1; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) k4[u] = i0 + u * RPP_NMS_NT < n_list ? gkeys[i0 + u * RPP_NMS_NT] : 0ull;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (k4[u] != 0ull && key_score(k4[u]) < L) { k4[u] = 0ull; below = 1; }
       } else {
-        const uint2 e = lst[i];
-        const float raw = __uint_as_float(e.x);
-        if (P.is_logit && raw < raw_lo) {
-          below = 1;   // (its score is below L; whether it was consumable at all does not matter: it only cuts)
-        } else {
-          const float s = col_score(P, raw);
-          if (s > P.score_threshold && (list_complete || s > s_edge)) {
-            if (s < L) below = 1; else k = make_key(s, e.y);
+        uint2 e4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          e4[u] = i0 + u * RPP_NMS_NT < n_list ? lst[i0 + u * RPP_NMS_NT] : make_uint2(0xff800000u /* -inf */, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          k4[u] = 0ull;
+          if (i0 + u * RPP_NMS_NT >= n_list) continue;
+          const float raw = __uint_as_float(e4[u].x);
+          if (P.is_logit && raw < raw_lo) {
+            below = 1;   // (its score is below L; whether it was consumable at all does not matter: it only cuts)
+          } else {
+            const float s = col_score(P, raw);
+            if (s > P.score_threshold && (list_complete || s > s_edge)) {
+              if (s < L) below = 1; else k4[u] = make_key(s, e4[u].y);
+            }
           }
         }
       }
-      if (k == 0ull) continue;
-      ++n_valid;
-      bool dead = false;
-      for (int q = 0; q < nk0; ++q) dead = dead || pk[q] == k;   // one of the probe's own boxes
-      if (dead) continue;
-      float4 orig = col_box(P, b, c, key_tie(k));
-      if (P.clip_before) orig = clip01(orig);
-      float area;
-      const float4 bx = canon_or_empty(orig, area);
-      for (int q = 0; q < nk0; ++q)
-        if (iou_gt(bx, area, kbox[q], karea[q], thr)) { dead = true; break; }
-      if (dead) continue;
-      const int slot = atomicAdd(&sh->nk_slot[1], 1);
-      if (slot < RPP_LIST_SMEM) { sh->lkeys[slot] = k; abox[slot] = orig; }
+      float4 d4[4], a4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k4[u] == 0ull) continue;
+        ++n_valid;
+        bool own = false;
+        for (int q = 0; q < nk0; ++q) own = own || pk[q] == k4[u];   // one of the probe's own boxes
+        if (own) { k4[u] = 0ull; continue; }
+        if (plain_boxes) {
+          const u32 row = key_tie(k4[u]);
+          d4[u] = lv_delta(P.lv, b, row);
+          a4[u] = P.anchors[row];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const u64 k = k4[u];
+        if (k == 0ull) continue;
+        float4 orig = plain_boxes ? decode_box(d4[u], a4[u], P.dp) : col_box(P, b, c, key_tie(k));
+        if (P.clip_before) orig = clip01(orig);
+        float area;
+        const float4 bx = canon_or_empty(orig, area);
+        bool dead = false;
+        for (int q = 0; q < nk0; ++q)
+          if (iou_gt(bx, area, kbox[q], karea[q], thr)) { dead = true; break; }
+        if (dead) continue;
+        const int slot = atomicAdd(&sh->nk_slot[1], 1);
+        if (slot < RPP_LIST_SMEM) { sh->lkeys[slot] = k; abox[slot] = orig; }
+      }
     }
     if (n_valid) atomicAdd(&sh->nk_slot[0], n_valid);   // (both counters are zeroed with the per-problem state above)
     below = __syncthreads_or(below);
