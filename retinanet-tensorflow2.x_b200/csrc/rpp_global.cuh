@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(RPP_GTOP_NT) global_top_kernel(GlobalTopParams
 // (row maximum desc, row index asc) order, and a row's index is the rank of its own (anchor, class) pair in the top k.
 // Everything is selected on RAW keys (logit bits | ~flat index; the score is a monotone function of the logit) and
 // the binary64 sigmoid is evaluated for a few hundred elements per image instead of the ~10^4 of the list:
-//   1. the k-th best raw key (exact radix descent over the list in shared memory, counting only) and the interval
+//   1. the k-th best raw key (ONE shared-memory histogram over a linear map of [min key, max key] onto 1 024 bins,
+//      shared with the cut of step 2, then counting inside the key's bin) and the interval
 //      [x_lo, x_hi] of logits whose score equals the score s_k of that key (found with the sigmoid itself): a pair is
 //      in the top k  <=>  logit > x_hi, or logit in [x_lo, x_hi] and flat index <= idx*, where idx* is the
 //      (k - #{logit > x_hi})-th smallest index of the tie group E = {logit in [x_lo, x_hi]} — TopKV2's order
@@ -276,64 +277,6 @@ struct GlobalTopDirectParams {
   int debug;               // env RPP_GTD_DEBUG: blocks 0 and 300 print their per-phase cycle counts
   float4* out_boxes; float* out_scores; long long* out_classes; int* out_valid;
 };
-
-// k-th largest (1-based) of the non-zero unique keys in shared memory; at least kth of them exist.
-__device__ u64 block_kth_key(const u64* keys, int n, u32 kth, SelectScratch<RPP_EMIT_NT>* sc) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  u32 cnt = 0;
-  u64 mx = 0ull, mn = ~0ull;
-  for (int i = tid; i < n; i += RPP_EMIT_NT) {
-    const u64 k = keys[i];
-    if (k != 0ull) { ++cnt; mx = k > mx ? k : mx; mn = k < mn ? k : mn; }
-  }
-  block_cnt_max_min<RPP_EMIT_NT>(cnt, mx, mn, &sc->bs);
-  if (mn == mx) return mx;
-  int top_shift = 64 - __clzll((long long)(mn ^ mx));   // bits >= top_shift are common to every key
-  u64 base = top_shift >= 64 ? 0ull : ((mx >> top_shift) << top_shift);
-  u32 remaining = kth;
-  for (;;) {
-    const int bits = top_shift < RPP_RADIX_BITS ? top_shift : RPP_RADIX_BITS;
-    const int shift = top_shift - bits;
-    sc->hist[tid] = 0;   // RPP_RADIX_BINS == RPP_EMIT_NT
-    __syncthreads();
-    for (int i = tid; i < n; i += RPP_EMIT_NT) {
-      const u64 k = keys[i];
-      if (k != 0ull && k >= base && (top_shift >= 64 || ((k - base) >> top_shift) == 0ull))
-        atomicAdd(&sc->hist[(u32)((k - base) >> shift)], 1u);
-    }
-    __syncthreads();
-    // thread t owns bin t: inclusive suffix count over the bins >= t
-    const u32 h = sc->hist[tid];
-    u32 v = h;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u32 t = __shfl_down_sync(RPP_FULL_MASK, v, o);
-      if (lane + o < 32) v += t;
-    }
-    if (lane == 0) sc->part[warp] = v;
-    __syncthreads();
-    u32 above = v - h;
-    for (int w = warp + 1; w < RPP_EMIT_NT / 32; ++w) above += sc->part[w];
-    if (above < remaining && above + h >= remaining) { sc->d_star = (u32)tid; sc->cum_above = above; sc->cnt_bin = h; }
-    __syncthreads();
-    const u32 d = sc->d_star;
-    remaining -= sc->cum_above;
-    const u32 cnt_bin = sc->cnt_bin;
-    base += (u64)d << shift;
-    top_shift = shift;
-    if (shift == 0) return base;
-    if (cnt_bin == 1) {   // the only key left under the prefix
-      __syncthreads();
-      for (int i = tid; i < n; i += RPP_EMIT_NT) {
-        const u64 k = keys[i];
-        if (k != 0ull && k >= base && ((k - base) >> top_shift) == 0ull) sc->bs.ra = k;
-      }
-      __syncthreads();
-      return sc->bs.ra;
-    }
-    __syncthreads();   // hist / d_star are rewritten next round
-  }
-}
 
 // Largest d >= 0 such that every ordered float encoding in [o, o + dir * d] has the score `s` (dir = +1 / -1): the
 // score is monotone in the logit, so the predicate is a prefix; galloping 32-ary search, one sigmoid per lane and round.
@@ -369,7 +312,7 @@ __device__ u32 gtd_tie_extent(u32 o, float s, int dir) {
   }
 }
 
-static_assert(RPP_RADIX_BINS == RPP_EMIT_NT, "block_kth_key: one bin per thread");
+static_assert(RPP_RADIX_BINS == RPP_EMIT_NT, "global_top_direct_kernel: one histogram bin per thread");
 static_assert(RPP_EMIT_CHUNK * 8 >= (1024 + 1024) * 8 + RPP_GTD_CAND * 12 + RPP_GTD_TIES * 4,
               "global_top_direct_kernel: scratch layout");
 

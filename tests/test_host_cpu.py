@@ -396,3 +396,29 @@ def test_bench_workloads_match_baseline_configs():
     p = bench.workload_params(w['c3'])
     assert p.inference.mode == 'GlobalSoftNMS' and p.inference.filter_per_class is False
     assert p.inference.pre_nms_top_k == 5000 and p.inference.soft_nms_sigma == 0.5
+
+
+def test_collect_kernels_keep_their_loads_in_flight():
+    """SASS guard (cuobjdump, no GPU): in the streaming loop of the fused, per-level and 16-bit column collects the 128-bit
+    loads of a round must go to DISTINCT destination registers.  At the 40-register budget of 3 x 512 threads per SM any
+    extra live value makes ptxas re-use a destination, i.e. wait for one load before issuing the next: that cost the
+    per-level collect 10 % and several rejected variants of the fused one 70 %."""
+    import shutil
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    lib = os.path.join(PKG, 'libretinapost.so')
+    txt = subprocess.check_output([cuobjdump, '-sass', lib], text=True, stderr=subprocess.STDOUT)
+    checked = 0
+    for fn in re.split(r'\n\s*Function : ', txt):
+        name = fn.split('\n', 1)[0]
+        m = re.search(r'collect_cols4_kernelILi4ELi3E|collect_cols4_levels_kernelILi4ELi3E|collect_cols8_half_kernelILi(\d)E', name)
+        if not m:
+            continue
+        unroll = int(m.group(1)) if m.group(1) else 4
+        dests = re.findall(r'LDG\.E\.128\.CONSTANT (R\d+),', fn)
+        # the last `unroll` 128-bit loads of the function are the round's (threshold loads come first)
+        assert len(dests) >= unroll, (name, dests)
+        assert len(set(dests[-unroll:])) == unroll, (name, dests)
+        checked += 1
+    assert checked >= 4
