@@ -243,7 +243,7 @@ def _simulate_list_lengths(plan, n, trials, rng):
 
 def test_sampling_plan_margins():
     """The sampled pre-threshold only steers speed, but a top-k list that comes up short of k (or overflows) costs a
-    fallback: the plans of the BASELINE geometries must keep both tails far away."""
+    fallback: the plans of the BASELINE geometries must keep both tails far away ("Top-k emission robustness")."""
     from retinanet import _native
     rng = np.random.default_rng(0)
     out = (ctypes.c_int * 8)()
