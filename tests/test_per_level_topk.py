@@ -96,3 +96,36 @@ def test_gpu_per_level_topk_indices_and_full_size(ref):
     torch.cuda.synchronize()
     assert np.array_equal(so.cpu().numpy(), es) and np.array_equal(bo.cpu().numpy(), eb)
     assert np.array_equal(io.cpu().numpy(), ei)
+
+
+# ---- golden vectors: the UNMODIFIED reference FilterTopKDetections run on every anchor_boundaries segment --------------
+# (tests/golden/make_golden_per_level.py, executed in the build container over tests/golden/tf_shim.py)
+import glob
+import os
+
+_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'perlevel_*.npz')))
+
+
+def test_per_level_fixture_inventory():
+    assert len(_GOLDEN) == 8
+
+
+@pytest.mark.parametrize('path', _GOLDEN, ids=os.path.basename)
+def test_oracle_per_level_vs_reference_filter(ref, path):
+    g = np.load(path)
+    fs, fb, _ = ref.filter_per_level(g['scores'], g['boxes'], int(g['k']), g['boundaries'].tolist(),
+                                     per_class=bool(g['filter_per_class']))
+    assert fs.shape == g['filtered_scores'].shape and fb.shape == g['filtered_boxes'].shape
+    assert np.array_equal(fs, g['filtered_scores']) and np.array_equal(fb, g['filtered_boxes'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('path', _GOLDEN, ids=os.path.basename)
+def test_gpu_per_level_vs_reference_filter(path):
+    torch = pytest.importorskip('torch')
+    from retinanet.model.layers import FilterTopKDetectionsPerLevel
+    g = np.load(path)
+    layer = FilterTopKDetectionsPerLevel(int(g['k']), bool(g['filter_per_class']),
+                                         anchor_boundaries=g['boundaries'].tolist())
+    got = to_numpy(layer({'scores': torch.from_numpy(g['scores']).cuda(), 'boxes': torch.from_numpy(g['boxes']).cuda()}))
+    assert np.array_equal(got['scores'], g['filtered_scores']) and np.array_equal(got['boxes'], g['filtered_boxes'])
