@@ -73,3 +73,37 @@ def test_padded_nms_is_the_greedy_scan(ref, seed, n, M, clustered):
         if (b[i] > 0).any() and all(ref.iou_padded(b[j], b[i]) < 0.5 for j in kept):
             kept.append(i)
     assert valid == len(kept) and idx[:valid].tolist() == kept and (idx[valid:] == 0).all()
+
+
+@settings(max_examples=40, deadline=None)
+@given(seed=st.integers(0, 10 ** 6), C=st.integers(1, 5), k=st.integers(1, 40), per_class=st.booleans(),
+       cuts=st.lists(st.integers(1, 59), min_size=0, max_size=4, unique=True), ties=st.booleans())
+def test_per_level_filter_invariants(ref, seed, C, k, per_class, cuts, ties):
+    """rpp_topk_levels' definition (ref.filter_per_level): the reference filter per anchor_boundaries segment.  Every
+    segment contributes min(k, its size) rows taken from inside it, in the filter's own order; one segment = the fused
+    filter; splitting a segment never loses a row the fused filter keeps among that segment's first k."""
+    rng = np.random.default_rng(seed)
+    n = 60
+    s = rng.random((2, n, C)).astype(np.float32)
+    if ties:
+        s = (np.round(s * 8) / 8).astype(np.float32)
+    b = rng.random((2, n, 4)).astype(np.float32)
+    bounds = [0] + sorted(cuts) + [n]
+    fs, fb, fi = ref.filter_per_level(s, b, k, bounds, per_class=per_class)
+    off = 0
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        kk = min(k, (hi - lo) if per_class else (hi - lo) * C)
+        idx = fi[..., off:off + kk]
+        anchor = idx if per_class else idx // C
+        assert ((anchor >= lo) & (anchor < hi)).all()
+        seg = fs[:, off:off + kk]
+        if per_class:      # per class: scores of a segment are sorted descending and are the segment's own top-kk
+            assert (np.diff(seg, axis=1) <= 0).all()
+            top = -np.sort(-s[:, lo:hi], axis=1)[:, :kk]
+            assert np.array_equal(seg, top)
+        off += kk
+    assert off == fs.shape[1] == fb.shape[1]
+    one_s, one_b, one_i = ref.filter_per_level(s, b, k, [0, n], per_class=per_class)
+    f = ref.filter_per_class if per_class else ref.filter_global
+    es, eb, ei = f(s, b, k)
+    assert np.array_equal(one_s, es) and np.array_equal(one_b, eb) and np.array_equal(one_i, ei)
